@@ -1,0 +1,990 @@
+// C-ABI of the B200-native traj2dEcsv hot path (include/cgromcorr.h): context, streaming pipeline, writers.
+#include "../../include/cgromcorr.h"
+
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "host_parse.h"
+#include "kernels.cuh"
+
+using namespace cgc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define CUDA_OK(expr)                                                                                         \
+  do {                                                                                                        \
+    cudaError_t e__ = (expr);                                                                                 \
+    if (e__ != cudaSuccess) {                                                                                 \
+      throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" +               \
+                      std::to_string(__LINE__) + ")");                                                        \
+    }                                                                                                         \
+  } while (0)
+
+// One half of the double-buffered stream: text in, dE out.
+struct Slot {
+  char* h_text = nullptr;   // pinned staging (file path only)
+  char* d_text = nullptr;
+  int64_t* d_off = nullptr;
+  int64_t* h_off = nullptr;  // pinned
+  float* d_xyz8 = nullptr;
+  float4* d_sites = nullptr;
+  double* d_acc = nullptr;
+  float* d_dE = nullptr;
+  float* h_dE = nullptr;     // pinned
+  cudaEvent_t ev_copied = nullptr, ev_done = nullptr;
+  int frames = 0;            // frames of the batch in flight
+  int64_t out_frame = 0;     // where its rows go in the caller's dE block
+  bool busy = false;
+};
+
+}  // namespace
+
+struct cgc_context {
+  ChargeTable table;
+  int device = -1;
+  int sm_count = 148;
+  mutable std::string err;
+
+  // trajectory text
+  const char* text = nullptr;
+  int64_t nbytes = 0;
+  bool mapped = false;
+  bool registered = false;  // text is page-locked for the device (cudaHostRegister): H2D straight from it
+  FrameLayout L;
+  std::vector<FrameSpan> frames;  // frames located so far
+  bool index_complete = false;
+  bool opened = false;
+
+  // static per-atom data (host copies kept for the getters)
+  std::vector<float> q_ground;    // table charge of the atom's own key
+  std::vector<float> q_exc;       // dQ for chromophore atoms (their ",EXC" entry), 0 otherwise
+  std::vector<int32_t> col;
+  DeviceSystem sys;
+  bool dev_static = false;
+
+  // options
+  int n_sites = 0;
+  int cov_opt = -1;  // -1 auto
+  int batch_frames = 0;
+
+  // pipeline
+  Slot slot[2];
+  bool dev_pipeline = false;
+  int alloc_batch = 0;
+  int64_t alloc_text = 0;
+  cudaStream_t st_copy = nullptr, st_comp = nullptr;
+  int* d_err = nullptr;
+  int64_t launches = 0;
+
+  // Correlate
+  double* d_cov = nullptr;
+  bool cov_bound = false;
+  bool shift_set = false;
+  float* d_compat = nullptr;  // float32 [2][S*G]
+
+  ~cgc_context();
+};
+
+namespace {
+
+void release_text(cgc_context* c) {
+  if (c->registered && c->text) cudaHostUnregister((void*)c->text);
+  c->registered = false;
+  if (c->mapped && c->text) munmap((void*)c->text, (size_t)c->nbytes);
+  c->text = nullptr;
+  c->nbytes = 0;
+  c->mapped = false;
+}
+
+void free_pipeline(cgc_context* c) {
+  if (c->device < 0) return;
+  cudaSetDevice(c->device);
+  for (auto& s : c->slot) {
+    if (s.h_text) cudaFreeHost(s.h_text);
+    if (s.d_text) cudaFree(s.d_text);
+    if (s.d_off) cudaFree(s.d_off);
+    if (s.h_off) cudaFreeHost(s.h_off);
+    if (s.d_xyz8) cudaFree(s.d_xyz8);
+    if (s.d_sites) cudaFree(s.d_sites);
+    if (s.d_acc) cudaFree(s.d_acc);
+    if (s.d_dE) cudaFree(s.d_dE);
+    if (s.h_dE) cudaFreeHost(s.h_dE);
+    if (s.ev_copied) cudaEventDestroy(s.ev_copied);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    s = Slot();
+  }
+  c->dev_pipeline = false;
+  c->alloc_batch = 0;
+  c->alloc_text = 0;
+}
+
+void free_static(cgc_context* c) {
+  if (c->device < 0) return;
+  cudaSetDevice(c->device);
+  if (c->sys.kq) cudaFree(c->sys.kq);
+  if (c->sys.col) cudaFree(c->sys.col);
+  if (c->sys.slot) cudaFree(c->sys.slot);
+  if (c->sys.slot_dq) cudaFree(c->sys.slot_dq);
+  c->sys.kq = nullptr; c->sys.col = nullptr; c->sys.slot = nullptr; c->sys.slot_dq = nullptr;
+  if (c->d_cov && !c->cov_bound) cudaFree(c->d_cov);
+  c->d_cov = nullptr;
+  c->cov_bound = false;
+  if (c->d_compat) cudaFree(c->d_compat);
+  c->d_compat = nullptr;
+  c->shift_set = false;
+  c->dev_static = false;
+}
+
+}  // namespace
+
+cgc_context::~cgc_context() {
+  free_pipeline(this);
+  free_static(this);
+  if (device >= 0) {
+    if (st_copy) cudaStreamDestroy(st_copy);
+    if (st_comp) cudaStreamDestroy(st_comp);
+    if (d_err) cudaFree(d_err);
+  }
+  release_text(this);
+}
+
+namespace {
+
+template <typename F>
+int guarded(cgc_context* c, F&& fn) {
+  try {
+    return fn();
+  } catch (const InputFileMalformed& e) {
+    if (c) c->err = e.what(); else g_create_error = e.what();
+    return CGC_ERR_INPUT_MALFORMED;
+  } catch (const InputFileMinorMalformed& e) {
+    if (c) c->err = e.what(); else g_create_error = e.what();
+    return CGC_ERR_INPUT_MINOR;
+  } catch (const ReadError& e) {
+    if (c) c->err = e.what(); else g_create_error = e.what();
+    return CGC_ERR_READ;
+  } catch (const Unsupported& e) {
+    if (c) c->err = e.what(); else g_create_error = e.what();
+    return CGC_ERR_UNSUPPORTED;
+  } catch (const CudaError& e) {
+    if (c) c->err = e.what(); else g_create_error = e.what();
+    return CGC_ERR_CUDA;
+  } catch (const std::exception& e) {
+    if (c) c->err = e.what(); else g_create_error = e.what();
+    return CGC_ERR_ARG;
+  }
+}
+
+int fail(const cgc_context* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+
+void need_device(cgc_context* c) {
+  if (c->device < 0) throw CudaError("this context was created without a CUDA device (device < 0); there is no CPU path");
+  CUDA_OK(cudaSetDevice(c->device));
+}
+
+// Everything AtomDataLookup_v2 (reference src/grom2atomFMO.cpp:549-610) resolves, done once: per-atom ground charge,
+// per-atom dQ for chromophore atoms, dE column per atom.
+void resolve_atoms(cgc_context* c) {
+  const FrameLayout& L = c->L;
+  const int n = L.n_atoms;
+  c->q_ground.assign(n, 0.f);
+  c->q_exc.assign(n, 0.f);
+  c->col.assign(n, -1);
+  for (int a = 0; a < n; a++) {
+    const std::string& key = L.keys[a];
+    int j = c->table.find(key);
+    if (j < 0) throw InputFileMalformed("Atom name " + key + " from input file not found in lookup table.");
+    c->q_ground[a] = c->table.charges[j];
+    const int g = L.groups[a];
+    if (g < 0) {
+      // the reference looks the ",EXC" entry up whenever this atom's chromophore is the excited site (:579-596)
+      int k = c->table.find(key + ",EXC");
+      if (k < 0) throw InputFileMalformed("Atom name " + key + ",EXC from input file not found in lookup table.");
+      c->q_exc[a] = c->table.charges[k];
+      // the reference's outer loop runs over 1..nGroups, so a chromophore index beyond nGroups is never visited
+      // (reference src/grom2atomFMO.cpp:669,674)
+      c->col[a] = (-g <= L.n_groups) ? (-g - 1) : -1;
+    } else {
+      c->col[a] = L.n_chromo + g - 1;
+    }
+  }
+}
+
+void build_static(cgc_context* c) {
+  need_device(c);
+  free_pipeline(c);
+  free_static(c);
+  const FrameLayout& L = c->L;
+  DeviceSystem& sys = c->sys;
+  const int n = L.n_atoms;
+  sys.n_atoms = n;
+  sys.n_pad = (n + kTileAtoms - 1) / kTileAtoms * kTileAtoms;
+  sys.n_chromo = L.n_chromo;
+  sys.n_groups = L.n_groups;
+  sys.num_tot = L.n_chromo + L.n_groups;
+  sys.n_sites = c->n_sites;
+  sys.line_bytes = L.line_bytes;
+  sys.x_col = L.x_col;
+  sys.field_w = L.field_w;
+  sys.ndec = L.ndec;
+  // dQ != 0 atoms of every computed site, in file order (zero-dQ atoms add exactly +-0 to every bin)
+  std::vector<int> count(sys.n_sites, 0);
+  std::vector<int32_t> slot(sys.n_pad, -1);
+  for (int a = 0; a < n; a++) {
+    int g = L.groups[a];
+    if (g < 0 && -g <= sys.n_sites && c->q_exc[a] != 0.f) count[-g - 1]++;
+  }
+  int P = 1;
+  for (int s = 0; s < sys.n_sites; s++) P = std::max(P, count[s]);
+  sys.site_cap = P;
+  if (cdc_smem_bytes(sys) > 200 * 1024) {
+    throw Unsupported("site block (sites x dQ atoms x 32 B, double buffered) exceeds shared memory; lower the \"sites\" option");
+  }
+  std::vector<float> slot_dq((size_t)sys.n_sites * P, 0.f);
+  std::fill(count.begin(), count.end(), 0);
+  for (int a = 0; a < n; a++) {
+    int g = L.groups[a];
+    if (g < 0 && -g <= sys.n_sites && c->q_exc[a] != 0.f) {
+      int s = -g - 1;
+      slot[a] = s * P + count[s];
+      slot_dq[(size_t)s * P + count[s]] = c->q_exc[a];
+      count[s]++;
+    }
+  }
+  std::vector<double> kq(sys.n_pad, 0.0);
+  std::vector<int32_t> col(sys.n_pad, -1);
+  for (int a = 0; a < n; a++) {
+    kq[a] = (double)33.2f * (double)c->q_ground[a];  // reference src/grom2atomFMO.cpp:666,687
+    col[a] = c->col[a];
+  }
+  CUDA_OK(cudaMalloc(&sys.kq, sizeof(double) * sys.n_pad));
+  CUDA_OK(cudaMalloc(&sys.col, sizeof(int32_t) * sys.n_pad));
+  CUDA_OK(cudaMalloc(&sys.slot, sizeof(int32_t) * sys.n_pad));
+  CUDA_OK(cudaMalloc(&sys.slot_dq, sizeof(float) * slot_dq.size()));
+  CUDA_OK(cudaMemcpy(sys.kq, kq.data(), sizeof(double) * sys.n_pad, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(sys.col, col.data(), sizeof(int32_t) * sys.n_pad, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(sys.slot, slot.data(), sizeof(int32_t) * sys.n_pad, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(sys.slot_dq, slot_dq.data(), sizeof(float) * slot_dq.size(), cudaMemcpyHostToDevice));
+  if (!c->st_copy) CUDA_OK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+  if (!c->st_comp) CUDA_OK(cudaStreamCreateWithFlags(&c->st_comp, cudaStreamNonBlocking));
+  if (!c->d_err) {
+    CUDA_OK(cudaMalloc(&c->d_err, sizeof(int)));
+    CUDA_OK(cudaMemset(c->d_err, 0, sizeof(int)));
+  }
+  c->dev_static = true;
+}
+
+int64_t cov_doubles(const cgc_context* c) {
+  const int64_t SG = (int64_t)c->sys.n_sites * c->sys.num_tot;
+  return 1 + 2 * SG + SG * c->sys.num_tot;
+}
+
+bool cov_enabled(const cgc_context* c) {
+  if (c->cov_opt == 0) return false;
+  if (c->cov_opt == 1) return true;
+  return cov_doubles(c) * 8 <= ((int64_t)8 << 30);  // auto: on while the partial sums stay under 8 GiB
+}
+
+void ensure_cov(cgc_context* c) {
+  if (!cov_enabled(c)) return;
+  const int64_t SG = (int64_t)c->sys.n_sites * c->sys.num_tot;
+  if (!c->d_cov) {
+    CUDA_OK(cudaMalloc(&c->d_cov, sizeof(double) * cov_doubles(c)));
+    CUDA_OK(cudaMemset(c->d_cov, 0, sizeof(double) * cov_doubles(c)));
+    c->cov_bound = false;
+    c->shift_set = false;
+  }
+  if (!c->d_compat) {
+    CUDA_OK(cudaMalloc(&c->d_compat, sizeof(float) * 2 * SG));
+    CUDA_OK(cudaMemset(c->d_compat, 0, sizeof(float) * 2 * SG));
+  }
+}
+
+int default_batch(const cgc_context* c) {
+  const int64_t frame_text = (int64_t)c->L.n_atoms * c->L.line_bytes + 256;
+  int64_t b = ((int64_t)512 << 20) / frame_text;
+  // the FP64 bins of a batch should stay small next to the text
+  const int64_t per_frame_out = (int64_t)c->sys.n_sites * c->sys.num_tot * 12;
+  b = std::min<int64_t>(b, ((int64_t)2 << 30) / std::max<int64_t>(1, per_frame_out));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(256, b));
+}
+
+void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_host_text) {
+  need_device(c);
+  if (!c->dev_static) throw std::runtime_error("internal: static data missing");
+  const DeviceSystem& sys = c->sys;
+  if (c->dev_pipeline && c->alloc_batch >= batch && c->alloc_text >= text_bytes &&
+      (!need_host_text || c->slot[0].h_text)) {
+    return;
+  }
+  free_pipeline(c);
+  const int64_t sg = (int64_t)sys.n_sites * sys.num_tot;
+  for (auto& s : c->slot) {
+    CUDA_OK(cudaMalloc(&s.d_text, (size_t)text_bytes + 64));
+    if (need_host_text) CUDA_OK(cudaHostAlloc(&s.h_text, (size_t)text_bytes + 64, cudaHostAllocDefault));
+    CUDA_OK(cudaMalloc(&s.d_off, sizeof(int64_t) * batch));
+    CUDA_OK(cudaHostAlloc(&s.h_off, sizeof(int64_t) * batch, cudaHostAllocDefault));
+    CUDA_OK(cudaMalloc(&s.d_xyz8, sizeof(float) * 3 * (size_t)sys.n_pad * batch));
+    CUDA_OK(cudaMalloc(&s.d_sites, (size_t)32 * sys.n_sites * sys.site_cap * batch));
+    CUDA_OK(cudaMalloc(&s.d_acc, sizeof(double) * sg * batch));
+    CUDA_OK(cudaMemset(s.d_acc, 0, sizeof(double) * sg * batch));
+    CUDA_OK(cudaMalloc(&s.d_dE, sizeof(float) * sg * batch));
+    CUDA_OK(cudaHostAlloc(&s.h_dE, sizeof(float) * sg * batch, cudaHostAllocDefault));
+    CUDA_OK(cudaEventCreateWithFlags(&s.ev_copied, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    launch_init_sites(sys, s.d_sites, batch, c->st_comp);
+    c->launches++;
+  }
+  CUDA_OK(cudaStreamSynchronize(c->st_comp));
+  c->dev_pipeline = true;
+  c->alloc_batch = batch;
+  c->alloc_text = text_bytes;
+}
+
+// make sure frames [0, upto] are located; returns the number of frames known
+int64_t index_upto(cgc_context* c, int64_t upto) {
+  while (!c->index_complete && (int64_t)c->frames.size() <= upto) {
+    int64_t pos = c->frames.empty() ? 0 : c->frames.back().end;
+    FrameSpan sp;
+    bool trunc = false;
+    if (!locate_frame(c->text, c->nbytes, pos, c->L.n_atoms, c->L.line_bytes, sp, nullptr, &trunc)) {
+      c->index_complete = true;
+      break;
+    }
+    c->frames.push_back(sp);
+  }
+  return (int64_t)c->frames.size();
+}
+
+void parallel_copy(char* dst, const char* src, int64_t n) {
+  const int64_t kMin = 8 << 20;
+  int nt = (int)std::min<int64_t>(std::max(1u, std::min(8u, std::thread::hardware_concurrency())), std::max<int64_t>(1, n / kMin));
+  if (nt <= 1) {
+    memcpy(dst, src, (size_t)n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const int64_t chunk = ((n + nt - 1) / nt + 4095) & ~(int64_t)4095;
+  for (int i = 0; i < nt; i++) {
+    int64_t b = (int64_t)i * chunk, e = std::min(n, b + chunk);
+    if (b >= e) break;
+    th.emplace_back([=] { memcpy(dst + b, src + b, (size_t)(e - b)); });
+  }
+  for (auto& t : th) t.join();
+}
+
+// K1 -> K2 -> finish (-> K3) for one batch whose text is already in d_text; everything on `st`
+void enqueue_compute(cgc_context* c, const char* d_text, int64_t text_bytes, const int64_t* d_off, int n_frames,
+                     float* d_xyz8, float4* d_sites, double* d_acc, float* d_dE, bool accumulate, cudaStream_t st) {
+  const DeviceSystem& sys = c->sys;
+  launch_decode(sys, d_text, text_bytes, d_off, n_frames, d_xyz8, d_sites, c->d_err, st);
+  launch_cdc(sys, d_xyz8, d_sites, d_acc, n_frames, c->sm_count, st);
+  launch_finish(d_acc, d_dE, (int64_t)n_frames * sys.n_sites * sys.num_tot, st);
+  c->launches += 3;
+  if (accumulate && c->d_cov) {
+    if (!c->shift_set) {
+      launch_cov_set_shift(d_dE, c->d_cov, sys.n_sites, sys.num_tot, st);
+      c->shift_set = true;
+      c->launches++;
+    }
+    launch_cov_accumulate(d_dE, n_frames, c->d_cov, c->d_compat, sys.n_sites, sys.num_tot, st);
+    c->launches += 2;
+  }
+  CUDA_OK(cudaGetLastError());
+}
+
+void open_common(cgc_context* c) {
+  c->frames.clear();
+  c->index_complete = false;
+  c->opened = false;
+  FrameSpan sp;
+  c->L = FrameLayout();
+  scan_first_frame(c->text, c->nbytes, c->L, sp);
+  c->frames.push_back(sp);
+  resolve_atoms(c);
+  c->n_sites = c->L.n_chromo;
+  c->cov_opt = -1;
+  c->batch_frames = 0;
+  if (c->L.n_chromo < 1) throw InputFileMalformed("no BCL/BCX residue in the trajectory: nothing to excite");
+  if (c->device >= 0) build_static(c);
+  c->opened = true;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+const char* cgc_version(void) { return "cgromcorr-b200 0.1 (sm_100a)"; }
+
+const char* cgc_last_error(const cgc_context* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int cgc_create(const char* topology_path, const char* excited_itp_path, int device, cgc_context** out) {
+  if (!out || !topology_path || !excited_itp_path) return fail(nullptr, CGC_ERR_ARG, "null argument");
+  *out = nullptr;
+  cgc_context* c = new cgc_context();
+  int rc = guarded(nullptr, [&]() {
+    load_tables(topology_path, excited_itp_path, c->table);
+    c->device = device;
+    if (device >= 0) {
+      int count = 0;
+      CUDA_OK(cudaGetDeviceCount(&count));
+      if (device >= count) throw CudaError("CUDA device " + std::to_string(device) + " not present");
+      CUDA_OK(cudaSetDevice(device));
+      cudaDeviceProp prop;
+      CUDA_OK(cudaGetDeviceProperties(&prop, device));
+      if (prop.major < 10) throw CudaError(std::string("device '") + prop.name + "' is not sm_100-class; this library is built for sm_100a only");
+      c->sm_count = prop.multiProcessorCount;
+    }
+    return CGC_OK;
+  });
+  if (rc != CGC_OK) {
+    c->device = -1;
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return CGC_OK;
+}
+
+void cgc_destroy(cgc_context* ctx) { delete ctx; }
+
+int cgc_table_size(const cgc_context* ctx) { return ctx ? (int)ctx->table.names.size() : 0; }
+
+int cgc_table_entry(const cgc_context* ctx, int i, char* name, int name_cap, float* mass, float* charge) {
+  if (!ctx || i < 0 || i >= (int)ctx->table.names.size()) return fail(ctx, CGC_ERR_ARG, "table index out of range");
+  if (name && name_cap > 0) {
+    snprintf(name, (size_t)name_cap, "%s", ctx->table.names[i].c_str());
+  }
+  if (mass) *mass = ctx->table.masses[i];
+  if (charge) *charge = ctx->table.charges[i];
+  return CGC_OK;
+}
+
+int cgc_topology_warnings(const cgc_context* ctx) { return ctx ? ctx->table.warnings : 0; }
+
+int cgc_open(cgc_context* ctx, const char* traj_path) {
+  if (!ctx || !traj_path) return fail(ctx, CGC_ERR_ARG, "null argument");
+  return guarded(ctx, [&]() {
+    if (ctx->device >= 0) { free_pipeline(ctx); }
+    release_text(ctx);
+    int fd = open(traj_path, O_RDONLY);
+    if (fd < 0) throw ReadError("Open failed on file passed in.");  // reference src/grom2atomFMO.cpp:495-497
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || sb.st_size == 0) {
+      close(fd);
+      throw ReadError("trajectory file is empty or cannot be stat'ed");
+    }
+    void* p = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) throw ReadError("mmap of the trajectory failed");
+    madvise(p, (size_t)sb.st_size, MADV_SEQUENTIAL);
+    ctx->text = (const char*)p;
+    ctx->nbytes = sb.st_size;
+    ctx->mapped = true;
+    open_common(ctx);
+    return CGC_OK;
+  });
+}
+
+int cgc_open_memory(cgc_context* ctx, const char* text, int64_t nbytes) {
+  if (!ctx || !text || nbytes <= 0) return fail(ctx, CGC_ERR_ARG, "null or empty text");
+  return guarded(ctx, [&]() {
+    if (ctx->device >= 0) { free_pipeline(ctx); }
+    release_text(ctx);
+    ctx->text = text;
+    ctx->nbytes = nbytes;
+    ctx->mapped = false;
+    // A caller-pinned buffer (cudaHostAlloc / cudaHostRegister / torch pin_memory) is detected in cgc_run and then
+    // copied H2D directly, without the pinned staging copy.
+    open_common(ctx);
+    return CGC_OK;
+  });
+}
+
+int cgc_dims(const cgc_context* ctx, int* n_atoms, int* n_chromo, int* n_groups, int* num_tot) {
+  if (!ctx || !ctx->opened) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  if (n_atoms) *n_atoms = ctx->L.n_atoms;
+  if (n_chromo) *n_chromo = ctx->L.n_chromo;
+  if (n_groups) *n_groups = ctx->L.n_groups;
+  if (num_tot) *num_tot = ctx->L.n_chromo + ctx->L.n_groups;
+  return CGC_OK;
+}
+
+int cgc_get_groups(const cgc_context* ctx, int32_t* out) {
+  if (!ctx || !ctx->opened || !out) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  memcpy(out, ctx->L.groups.data(), sizeof(int32_t) * ctx->L.groups.size());
+  return CGC_OK;
+}
+
+int cgc_get_columns(const cgc_context* ctx, int32_t* out) {
+  if (!ctx || !ctx->opened || !out) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  memcpy(out, ctx->col.data(), sizeof(int32_t) * ctx->col.size());
+  return CGC_OK;
+}
+
+int cgc_get_site_charges(const cgc_context* ctx, int site, float* out) {
+  if (!ctx || !ctx->opened || !out) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  if (site < 0 || site > ctx->L.n_chromo) return fail(ctx, CGC_ERR_ARG, "site out of range");
+  for (int a = 0; a < ctx->L.n_atoms; a++) {
+    out[a] = (ctx->L.groups[a] == -site && site > 0) ? ctx->q_exc[a] : ctx->q_ground[a];
+  }
+  return CGC_OK;
+}
+
+int cgc_get_key(const cgc_context* ctx, int atom, char* buf, int cap) {
+  if (!ctx || !ctx->opened || !buf || cap <= 0) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  if (atom < 0 || atom >= ctx->L.n_atoms) return fail(ctx, CGC_ERR_ARG, "atom out of range");
+  snprintf(buf, (size_t)cap, "%s", ctx->L.keys[atom].c_str());
+  return CGC_OK;
+}
+
+int cgc_get_layout(const cgc_context* ctx, int* line_bytes, int* x_col, int* field_width, int* decimals) {
+  if (!ctx || !ctx->opened) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  if (line_bytes) *line_bytes = ctx->L.line_bytes;
+  if (x_col) *x_col = ctx->L.x_col;
+  if (field_width) *field_width = ctx->L.field_w;
+  if (decimals) *decimals = ctx->L.ndec;
+  return CGC_OK;
+}
+
+int cgc_frame_count(cgc_context* ctx, int64_t* n_frames) {
+  if (!ctx || !ctx->opened || !n_frames) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  return guarded(ctx, [&]() {
+    *n_frames = index_upto(ctx, INT64_MAX - 1);
+    return CGC_OK;
+  });
+}
+
+int64_t cgc_frame_atoms_offset(cgc_context* ctx, int64_t frame) {
+  if (!ctx || !ctx->opened || frame < 0) return -1;
+  int64_t r = -1;
+  guarded(ctx, [&]() {
+    if (index_upto(ctx, frame) > frame) r = ctx->frames[(size_t)frame].atoms;
+    return CGC_OK;
+  });
+  return r;
+}
+
+int cgc_set_option(cgc_context* ctx, const char* key, double value) {
+  if (!ctx || !key) return fail(ctx, CGC_ERR_ARG, "null argument");
+  if (!ctx->opened) return fail(ctx, CGC_ERR_STATE, "options are per trajectory: call cgc_open first");
+  return guarded(ctx, [&]() {
+    std::string k(key);
+    if (k == "sites") {
+      int v = (int)value;
+      if (v < 1 || v > ctx->L.n_chromo) {
+        // the reference asserts that the site exists (src/grom2atomFMO.cpp:632)
+        throw std::invalid_argument("sites must be within 1.." + std::to_string(ctx->L.n_chromo));
+      }
+      if (v != ctx->n_sites) {
+        ctx->n_sites = v;
+        if (ctx->device >= 0) build_static(ctx);
+      }
+    } else if (k == "covariance") {
+      ctx->cov_opt = value != 0.0 ? 1 : 0;
+    } else if (k == "batch_frames") {
+      if (value < 1 || value > 65535) throw std::invalid_argument("batch_frames must be within 1..65535");
+      ctx->batch_frames = (int)value;
+    } else {
+      throw std::invalid_argument("unknown option '" + k + "'");
+    }
+    return CGC_OK;
+  });
+}
+
+double cgc_get_option(const cgc_context* ctx, const char* key) {
+  if (!ctx || !key || !ctx->opened) return NAN;
+  std::string k(key);
+  if (k == "sites") return ctx->n_sites;
+  if (k == "covariance") return ctx->device >= 0 && ctx->dev_static ? (cov_enabled(ctx) ? 1 : 0) : ctx->cov_opt;
+  if (k == "batch_frames") return ctx->batch_frames > 0 ? ctx->batch_frames : default_batch(ctx);
+  if (k == "site_cap") return ctx->sys.site_cap;
+  if (k == "n_pad") return ctx->sys.n_pad;
+  return NAN;
+}
+
+int64_t cgc_launch_count(const cgc_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int cgc_decode_errors(cgc_context* ctx, int* flags) {
+  if (!ctx || !flags) return fail(ctx, CGC_ERR_ARG, "null argument");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    *flags = 0;
+    if (ctx->d_err) CUDA_OK(cudaMemcpy(flags, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    return CGC_OK;
+  });
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int cgc_run(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_kcal, int64_t* frames_done) {
+  if (frames_done) *frames_done = 0;
+  if (!ctx) return CGC_ERR_ARG;
+  if (!ctx->opened) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  if (first_frame < 0 || n_frames < 0) return fail(ctx, CGC_ERR_ARG, "negative frame range");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    const DeviceSystem& sys = ctx->sys;
+    const int B = ctx->batch_frames > 0 ? ctx->batch_frames : default_batch(ctx);
+    const int64_t frame_text_max = (int64_t)sys.n_atoms * sys.line_bytes + 4096;
+    // is the text already page-locked (caller-pinned memory given to cgc_open_memory)?
+    bool direct = false;
+    if (!ctx->mapped) {
+      cudaPointerAttributes at;
+      direct = cudaPointerGetAttributes(&at, ctx->text) == cudaSuccess && at.type == cudaMemoryTypeHost;
+      cudaGetLastError();
+    }
+    ensure_pipeline(ctx, B, frame_text_max * B, !direct);
+    ensure_cov(ctx);
+    const int64_t sg = (int64_t)sys.n_sites * sys.num_tot;
+
+    // The shift c of the Correlate sums is the dE row of the trajectory's frame 0 on EVERY rank (so partial sums of
+    // different frame ranges add up).  A run that does not start at frame 0 evaluates frame 0 first, unaccumulated.
+    if (ctx->d_cov && !ctx->shift_set && first_frame != 0) {
+      Slot& s = ctx->slot[0];
+      const FrameSpan& f0 = ctx->frames[0];
+      const int64_t b0 = f0.atoms & ~(int64_t)15;
+      const int64_t nb = f0.atoms + (int64_t)sys.n_atoms * sys.line_bytes - b0;
+      const int64_t nb_clamped = std::min(nb, ctx->nbytes - b0);
+      CUDA_OK(cudaMemcpyAsync(s.d_text, ctx->text + b0, (size_t)nb_clamped, cudaMemcpyHostToDevice, ctx->st_comp));
+      s.h_off[0] = f0.atoms - b0;
+      CUDA_OK(cudaMemcpyAsync(s.d_off, s.h_off, sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st_comp));
+      enqueue_compute(ctx, s.d_text, nb_clamped, s.d_off, 1, s.d_xyz8, s.d_sites, s.d_acc, s.d_dE, false, ctx->st_comp);
+      launch_cov_set_shift(s.d_dE, ctx->d_cov, sys.n_sites, sys.num_tot, ctx->st_comp);
+      ctx->launches++;
+      ctx->shift_set = true;
+      CUDA_OK(cudaStreamSynchronize(ctx->st_comp));
+    }
+
+    auto drain = [&](Slot& s) {
+      if (!s.busy) return;
+      CUDA_OK(cudaEventSynchronize(s.ev_done));
+      if (dE_kcal) memcpy(dE_kcal + s.out_frame * sg, s.h_dE, sizeof(float) * (size_t)(sg * s.frames));
+      if (frames_done) *frames_done += s.frames;
+      s.busy = false;
+    };
+
+    int64_t done = 0;
+    int which = 0;
+    bool eof = false;
+    while (done < n_frames && !eof) {
+      const int64_t f_begin = first_frame + done;
+      int want = (int)std::min<int64_t>(B, n_frames - done);
+      const int64_t known = index_upto(ctx, f_begin + want - 1);
+      if (known < f_begin + want) {
+        want = (int)std::max<int64_t>(0, known - f_begin);
+        eof = true;
+        if (want == 0) break;
+      }
+      Slot& s = ctx->slot[which];
+      drain(s);  // the slot's previous batch must have left before its buffers are reused
+      const FrameSpan& fa = ctx->frames[(size_t)f_begin];
+      const FrameSpan& fb = ctx->frames[(size_t)(f_begin + want - 1)];
+      const int64_t b0 = fa.atoms & ~(int64_t)15;
+      int64_t b1 = fb.atoms + (int64_t)sys.n_atoms * sys.line_bytes;
+      b1 = std::min(b1, ctx->nbytes);
+      const int64_t nb = b1 - b0;
+      if (nb > ctx->alloc_text) throw std::runtime_error("internal: batch text larger than the staging buffer");
+      for (int i = 0; i < want; i++) s.h_off[i] = ctx->frames[(size_t)(f_begin + i)].atoms - b0;
+      const char* src = ctx->text + b0;
+      if (!direct) {
+        parallel_copy(s.h_text, src, nb);  // page cache / pageable memory -> pinned
+        src = s.h_text;
+      }
+      CUDA_OK(cudaMemcpyAsync(s.d_text, src, (size_t)nb, cudaMemcpyHostToDevice, ctx->st_copy));
+      CUDA_OK(cudaMemcpyAsync(s.d_off, s.h_off, sizeof(int64_t) * want, cudaMemcpyHostToDevice, ctx->st_copy));
+      CUDA_OK(cudaEventRecord(s.ev_copied, ctx->st_copy));
+      CUDA_OK(cudaStreamWaitEvent(ctx->st_comp, s.ev_copied, 0));
+      enqueue_compute(ctx, s.d_text, nb, s.d_off, want, s.d_xyz8, s.d_sites, s.d_acc, s.d_dE, true, ctx->st_comp);
+      if (dE_kcal) {
+        CUDA_OK(cudaMemcpyAsync(s.h_dE, s.d_dE, sizeof(float) * (size_t)(sg * want), cudaMemcpyDeviceToHost, ctx->st_comp));
+      }
+      CUDA_OK(cudaEventRecord(s.ev_done, ctx->st_comp));
+      s.frames = want;
+      s.out_frame = done;
+      s.busy = true;
+      done += want;
+      which ^= 1;
+    }
+    drain(ctx->slot[which]);
+    drain(ctx->slot[which ^ 1]);
+    int flags = 0;
+    CUDA_OK(cudaMemcpy(&flags, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flags) {
+      CUDA_OK(cudaMemset(ctx->d_err, 0, sizeof(int)));
+      std::string m = "device decode found malformed coordinate text:";
+      if (flags & kDecBadChar) m += " unexpected character in a coordinate field;";
+      if (flags & kDecBadPoint) m += " decimal point not at the column found in frame 0;";
+      if (flags & kDecBadNewline) m += " atom line of a different length than in frame 0;";
+      throw InputFileMalformed(m);
+    }
+    return done < n_frames ? CGC_EOF : CGC_OK;
+  });
+}
+
+int cgc_run_device(cgc_context* ctx, const void* d_text, int64_t text_bytes, const int64_t* atoms_offset, int n_frames,
+                   float* d_dE_kcal, void* stream) {
+  if (!ctx) return CGC_ERR_ARG;
+  if (!ctx->opened) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  if (!d_text || !atoms_offset || !d_dE_kcal || n_frames < 1) return fail(ctx, CGC_ERR_ARG, "bad argument");
+  if (((uintptr_t)d_text & 15) != 0) return fail(ctx, CGC_ERR_ARG, "d_text must be 16-byte aligned");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    const int B = std::max(n_frames, ctx->batch_frames > 0 ? ctx->batch_frames : default_batch(ctx));
+    ensure_pipeline(ctx, B, std::max<int64_t>(ctx->alloc_text, 64), false);
+    Slot& s = ctx->slot[0];
+    cudaStream_t st = (cudaStream_t)stream;
+    // pageable source: the runtime stages it before returning, so the caller's array may be reused at once
+    CUDA_OK(cudaMemcpyAsync(s.d_off, atoms_offset, sizeof(int64_t) * n_frames, cudaMemcpyHostToDevice, st));
+    enqueue_compute(ctx, (const char*)d_text, text_bytes, s.d_off, n_frames, s.d_xyz8, s.d_sites, s.d_acc, d_dE_kcal,
+                    false, st);
+    return CGC_OK;
+  });
+}
+
+int cgc_decode_device(cgc_context* ctx, const void* d_text, int64_t text_bytes, const int64_t* atoms_offset,
+                      int n_frames, float* d_xyz, void* stream) {
+  if (!ctx) return CGC_ERR_ARG;
+  if (!ctx->opened) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  if (!d_text || !atoms_offset || !d_xyz || n_frames < 1) return fail(ctx, CGC_ERR_ARG, "bad argument");
+  if (((uintptr_t)d_text & 15) != 0) return fail(ctx, CGC_ERR_ARG, "d_text must be 16-byte aligned");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    const int B = std::max(n_frames, ctx->batch_frames > 0 ? ctx->batch_frames : default_batch(ctx));
+    ensure_pipeline(ctx, B, std::max<int64_t>(ctx->alloc_text, 64), false);
+    Slot& s = ctx->slot[0];
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_OK(cudaMemcpyAsync(s.d_off, atoms_offset, sizeof(int64_t) * n_frames, cudaMemcpyHostToDevice, st));
+    launch_decode(ctx->sys, (const char*)d_text, text_bytes, s.d_off, n_frames, s.d_xyz8, s.d_sites, ctx->d_err, st);
+    launch_unblock(ctx->sys, s.d_xyz8, d_xyz, n_frames, st);
+    ctx->launches += 2;
+    CUDA_OK(cudaGetLastError());
+    return CGC_OK;
+  });
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int64_t cgc_cov_size(const cgc_context* ctx) {
+  if (!ctx || !ctx->opened || ctx->device < 0 || !cov_enabled(ctx)) return 0;
+  return cov_doubles(ctx);
+}
+
+int cgc_cov_bind(cgc_context* ctx, double* d_buffer) {
+  if (!ctx || !d_buffer) return fail(ctx, CGC_ERR_ARG, "null argument");
+  if (!ctx->opened) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    if (!cov_enabled(ctx)) throw std::invalid_argument("covariance is switched off for this trajectory");
+    if (ctx->d_cov && !ctx->cov_bound) CUDA_OK(cudaFree(ctx->d_cov));
+    ctx->d_cov = d_buffer;
+    ctx->cov_bound = true;
+    ctx->shift_set = false;
+    CUDA_OK(cudaMemset(ctx->d_cov, 0, sizeof(double) * cov_doubles(ctx)));
+    ensure_cov(ctx);
+    const int64_t SG = (int64_t)ctx->sys.n_sites * ctx->sys.num_tot;
+    CUDA_OK(cudaMemset(ctx->d_compat, 0, sizeof(float) * 2 * SG));
+    return CGC_OK;
+  });
+}
+
+int cgc_cov_reset(cgc_context* ctx) {
+  if (!ctx || !ctx->opened) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    ensure_cov(ctx);
+    if (!ctx->d_cov) throw std::invalid_argument("covariance is switched off for this trajectory");
+    const int64_t SG = (int64_t)ctx->sys.n_sites * ctx->sys.num_tot;
+    CUDA_OK(cudaMemset(ctx->d_cov, 0, sizeof(double) * cov_doubles(ctx)));
+    CUDA_OK(cudaMemset(ctx->d_compat, 0, sizeof(float) * 2 * SG));
+    ctx->shift_set = false;
+    return CGC_OK;
+  });
+}
+
+int cgc_cov_set_shift_device(cgc_context* ctx, const float* d_row, void* stream) {
+  if (!ctx || !d_row) return fail(ctx, CGC_ERR_ARG, "null argument");
+  if (!ctx->opened) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    ensure_cov(ctx);
+    if (!ctx->d_cov) throw std::invalid_argument("covariance is switched off for this trajectory");
+    launch_cov_set_shift(d_row, ctx->d_cov, ctx->sys.n_sites, ctx->sys.num_tot, (cudaStream_t)stream);
+    ctx->launches++;
+    ctx->shift_set = true;
+    return CGC_OK;
+  });
+}
+
+int cgc_cov_accumulate_device(cgc_context* ctx, const float* d_dE_kcal, int n_frames, void* stream) {
+  if (!ctx || !d_dE_kcal || n_frames < 1) return fail(ctx, CGC_ERR_ARG, "bad argument");
+  if (!ctx->opened) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    ensure_cov(ctx);
+    if (!ctx->d_cov) throw std::invalid_argument("covariance is switched off for this trajectory");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!ctx->shift_set) {
+      launch_cov_set_shift(d_dE_kcal, ctx->d_cov, ctx->sys.n_sites, ctx->sys.num_tot, st);
+      ctx->shift_set = true;
+      ctx->launches++;
+    }
+    launch_cov_accumulate(d_dE_kcal, n_frames, ctx->d_cov, ctx->d_compat, ctx->sys.n_sites, ctx->sys.num_tot, st);
+    ctx->launches += 2;
+    CUDA_OK(cudaGetLastError());
+    return CGC_OK;
+  });
+}
+
+int cgc_cov_partials(cgc_context* ctx, double* host_out) {
+  if (!ctx || !host_out) return fail(ctx, CGC_ERR_ARG, "null argument");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    if (!ctx->d_cov) throw std::invalid_argument("no covariance sums on this context");
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(host_out, ctx->d_cov, sizeof(double) * cov_doubles(ctx), cudaMemcpyDeviceToHost));
+    return CGC_OK;
+  });
+}
+
+int cgc_cov_finalize(cgc_context* ctx, int ddof, double* mean, double* cov) {
+  if (!ctx || !mean || !cov) return fail(ctx, CGC_ERR_ARG, "null argument");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    if (!ctx->d_cov) throw std::invalid_argument("no covariance sums on this context");
+    const int S = ctx->sys.n_sites, G = ctx->sys.num_tot;
+    double *d_mean = nullptr, *d_covm = nullptr;
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMalloc(&d_mean, sizeof(double) * S * G));
+    CUDA_OK(cudaMalloc(&d_covm, sizeof(double) * (size_t)S * G * G));
+    launch_cov_finalize(ctx->d_cov, S, G, ddof, d_mean, d_covm, ctx->st_comp);
+    ctx->launches++;
+    cudaError_t e1 = cudaMemcpyAsync(mean, d_mean, sizeof(double) * S * G, cudaMemcpyDeviceToHost, ctx->st_comp);
+    cudaError_t e2 = cudaMemcpyAsync(cov, d_covm, sizeof(double) * (size_t)S * G * G, cudaMemcpyDeviceToHost, ctx->st_comp);
+    cudaError_t e3 = cudaStreamSynchronize(ctx->st_comp);
+    cudaFree(d_mean);
+    cudaFree(d_covm);
+    CUDA_OK(e1);
+    CUDA_OK(e2);
+    CUDA_OK(e3);
+    return CGC_OK;
+  });
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// writers
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+// "%g" of a float, as std::ostream << float prints it (precision 6)
+inline int fmt_g(char* p, float v) { return snprintf(p, 32, "%g", (double)v); }
+
+// format rows [r0, r1) of a float matrix into `out`
+void format_rows(const float* m, int64_t r0, int64_t r1, int ncol, bool to_cm, std::string& out) {
+  out.clear();
+  out.reserve((size_t)(r1 - r0) * ncol * 10);
+  char buf[40];
+  for (int64_t r = r0; r < r1; r++) {
+    const float* row = m + r * ncol;
+    for (int j = 0; j < ncol; j++) {
+      float v = row[j];
+      if (to_cm) v = (float)((double)v * 349.7);  // reference src/FMOparse.cpp:151
+      if (j) out.push_back(',');
+      int n = fmt_g(buf, v);
+      out.append(buf, (size_t)n);
+    }
+    out.push_back('\n');
+  }
+}
+
+int write_matrix_text(const char* path, bool truncate, const float* m, int64_t rows, int ncol, bool to_cm) {
+  FILE* f = fopen(path, truncate ? "wb" : "ab");
+  if (!f) return -1;
+  const int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  const int64_t per = std::max<int64_t>(1, (((int64_t)4 << 20) / std::max(1, ncol * 9)));  // ~4 MB of text per task
+  for (int64_t base = 0; base < rows; base += per * nt) {
+    std::vector<std::string> parts((size_t)nt);
+    std::vector<std::thread> th;
+    for (int i = 0; i < nt; i++) {
+      int64_t r0 = base + i * per, r1 = std::min(rows, r0 + per);
+      if (r0 >= r1) break;
+      th.emplace_back([&, i, r0, r1] { format_rows(m, r0, r1, ncol, to_cm, parts[(size_t)i]); });
+    }
+    for (auto& t : th) t.join();
+    for (auto& p : parts)
+      if (!p.empty() && fwrite(p.data(), 1, p.size(), f) != p.size()) {
+        fclose(f);
+        return -1;
+      }
+  }
+  return fclose(f) == 0 ? 0 : -1;
+}
+
+}  // namespace
+
+int cgc_write_time(const char* path, int truncate, const float* dE_kcal, int64_t rows, int num_tot) {
+  if (!path || (rows > 0 && !dE_kcal) || num_tot < 1) return CGC_ERR_ARG;
+  if (write_matrix_text(path, truncate != 0, dE_kcal, rows, num_tot, true) != 0) return CGC_ERR_READ;
+  return CGC_OK;
+}
+
+int cgc_write_mtx(cgc_context* ctx, const char* path, int compat) {
+  if (!ctx || !path) return fail(ctx, CGC_ERR_ARG, "null argument");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    if (!ctx->d_cov) throw std::invalid_argument("no covariance sums on this context");
+    const int S = ctx->sys.n_sites, G = ctx->sys.num_tot;
+    std::vector<float> m((size_t)S * G * G);
+    if (!compat) {
+      std::vector<double> mean((size_t)S * G), cov((size_t)S * G * G);
+      int rc = cgc_cov_finalize(ctx, 0, mean.data(), cov.data());
+      if (rc != CGC_OK) return rc;
+      for (size_t i = 0; i < cov.size(); i++) m[i] = (float)cov[i];
+    } else {
+      // the reference's literal arithmetic (src/FMOparse.cpp:189-206 with dEsize == 0), float32 throughout
+      CUDA_OK(cudaDeviceSynchronize());
+      double n = 0;
+      CUDA_OK(cudaMemcpy(&n, ctx->d_cov, sizeof(double), cudaMemcpyDeviceToHost));
+      const int T = (int)n;
+      std::vector<float> cs((size_t)2 * S * G);
+      CUDA_OK(cudaMemcpy(cs.data(), ctx->d_compat, sizeof(float) * cs.size(), cudaMemcpyDeviceToHost));
+      for (int k = 0; k < S; k++) {
+        float* sum = cs.data() + (size_t)k * G;
+        float* row0 = cs.data() + (size_t)S * G + (size_t)k * G;
+        for (int i = 0; i < G; i++) {
+          sum[i] /= T;
+          for (int j = 0; j < G; j++) row0[j] /= T;  // the same row, divided once per i
+        }
+        for (int i = 0; i < G; i++)
+          for (int j = 0; j < G; j++) {
+            volatile float prod = sum[i] * sum[j];  // keep the product a rounded float32 (no FMA contraction)
+            m[((size_t)k * G + i) * G + j] = row0[j] - prod;
+          }
+      }
+    }
+    if (write_matrix_text(path, true, m.data(), (int64_t)S * G, G, false) != 0) throw ReadError(std::string("cannot write ") + path);
+    return CGC_OK;
+  });
+}
+
+}  // extern "C"

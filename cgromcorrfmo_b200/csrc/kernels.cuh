@@ -1,0 +1,58 @@
+// Device kernels of the traj2dEcsv hot path (sm_100a only) — launch wrappers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace cgc {
+
+constexpr int kTileThreads = 256;   // threads per CTA of the pair kernel
+constexpr int kAtomsPerThread = 8;  // environment atoms held in registers by one thread
+constexpr int kTileAtoms = kTileThreads * kAtomsPerThread;
+constexpr int kDecodeThreads = 256; // atom lines per CTA of the decode kernel
+
+// decode error flags (device -> host)
+enum : int {
+  kDecBadChar = 1,      // a coordinate field holds something other than [ -.0-9]
+  kDecBadPoint = 2,     // the decimal point is not where the frame-0 layout says
+  kDecBadNewline = 4,   // an atom line does not end where the frame-0 layout says
+};
+
+struct DeviceSystem {
+  // static, built once per trajectory
+  int n_atoms = 0, n_pad = 0;           // n_pad: n_atoms rounded up to kTileAtoms
+  int n_chromo = 0, n_groups = 0, num_tot = 0;
+  int n_sites = 0;                      // sites computed (<= n_chromo)
+  int site_cap = 0;                     // P: dQ atoms per site, padded to the largest site
+  int line_bytes = 0, x_col = 20, field_w = 8, ndec = 3;
+  double* kq = nullptr;                 // [n_pad] (double)33.2f * (double)q
+  int32_t* col = nullptr;               // [n_pad] dE column, -1 = contributes nowhere (pads)
+  int32_t* slot = nullptr;              // [n_pad] s*P + c for the c-th dQ atom of site s, else -1
+  float* slot_dq = nullptr;             // [n_sites*P] dQ per slot (0 for padding slots)
+};
+
+// K1: fixed-column text -> xyz8 (3 floats per atom in blocks of 8 atoms [x0..x7][y0..y7][z0..z7], n_pad atoms per
+// frame) + per-frame site blocks.
+// text: device pointer, 16-byte aligned.  atoms_off: DEVICE int64[n_frames].
+void launch_decode(const DeviceSystem& sys, const char* text, int64_t text_bytes, const int64_t* atoms_off,
+                   int n_frames, float* xyz8, float4* sites, int* err_flags, cudaStream_t st);
+// xyz8 -> plain float32 [n_frames][n_atoms][3]
+void launch_unblock(const DeviceSystem& sys, const float* xyz8, float* xyz, int n_frames, cudaStream_t st);
+
+// fill every slot of the per-frame site blocks with the neutral padding entry
+void launch_init_sites(const DeviceSystem& sys, float4* sites, int n_frames, cudaStream_t st);
+
+// K2: CDC pair sums.  acc: double [n_frames][n_sites][num_tot], must be zero on entry.
+void launch_cdc(const DeviceSystem& sys, const float* xyz8, const float4* sites, double* acc, int n_frames,
+                int sm_count, cudaStream_t st);
+size_t cdc_smem_bytes(const DeviceSystem& sys);
+
+// acc (double) -> dE (float32), and re-zero acc for the next batch.
+void launch_finish(double* acc, float* dE, int64_t n, cudaStream_t st);
+
+// K3: per-site shifted sums.  buf = [ n | c (S*G) | sum (S*G) | sumsq (S*G*G) ]
+void launch_cov_set_shift(const float* dE_row0, double* buf, int S, int G, cudaStream_t st);
+void launch_cov_accumulate(const float* dE, int n_frames, double* buf, float* compat /* float32 [2][S*G] or null */,
+                           int S, int G, cudaStream_t st);
+void launch_cov_finalize(const double* buf, int S, int G, int ddof, double* mean, double* cov, cudaStream_t st);
+
+}  // namespace cgc

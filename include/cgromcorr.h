@@ -1,0 +1,151 @@
+/* cgromcorr.h — C-ABI of the B200-native traj2dEcsv hot path.
+ *
+ * One shared library (cgromcorrfmo_b200/libcgromcorr.so), plain C types only, never throws across the boundary.
+ * Two clients bind it: the C++ CLI driver `traj2dEcsv` (drop-in for the reference program) and the ctypes layer
+ * cgromcorrfmo_b200/capi.py used by the pyPCA shim, the tests and bench.py.
+ *
+ * The reference (jrhaberstroh/cGromCorrFMO) has no FFI layer; the interface this replaces is the C++ library
+ * src/grom2atomFMO.h plus the frame loop of src/FMOparse.cpp.  Every entry point cites what it stands in for.
+ * There is NO CPU fallback: every compute entry point needs a CUDA device (sm_100a) and fails with CGC_ERR_CUDA
+ * otherwise.
+ *
+ * Units: coordinates nm, charges e, dE in kcal/mol (the reference's cdc_kcal).  `.time` text is in cm^-1
+ * (x 349.7, reference src/FMOparse.cpp:151).
+ * Layout of every dE block: float32 [frames][sites][numTot], C order, column = chromophore index 0..nChromo-1 first,
+ * then environment groups (reference src/grom2atomFMO.cpp:688-693).
+ */
+#ifndef CGROMCORR_H
+#define CGROMCORR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cgc_context cgc_context;
+
+/* ---- status codes.  The three reference exception classes (src/grom2atomFMO.h:12-27) map to the first three. ---- */
+#define CGC_OK                    0
+#define CGC_EOF                   1   /* fewer frames in the trajectory than requested; *frames_done tells how many.
+                                         (The reference segfaults here, README.md:31.) */
+#define CGC_ERR_INPUT_MALFORMED  (-1) /* InputFileMalformed */
+#define CGC_ERR_INPUT_MINOR      (-2) /* InputFileMinorMalformed — only ever reported, never fatal (main() swallows it,
+                                         src/FMOparse.cpp:358-366) */
+#define CGC_ERR_READ             (-3) /* ReadError */
+#define CGC_ERR_ARG              (-4)
+#define CGC_ERR_CUDA             (-5)
+#define CGC_ERR_STATE            (-6) /* call order violated (e.g. run before open) */
+#define CGC_ERR_UNSUPPORTED      (-7) /* input is legal for the reference's tokeniser but not fixed-column */
+
+const char *cgc_version(void);
+
+/* Message of the last failure on this context; ctx == NULL returns the message of the last failed cgc_create on the
+ * calling thread. */
+const char *cgc_last_error(const cgc_context *ctx);
+
+/* ---- tables -----------------------------------------------------------------------------------------------------
+ * cgc_create replaces the two ParseTopology calls of main() (src/FMOparse.cpp:355-366; ParseTopology itself
+ * src/grom2atomFMO.cpp:78-234): excited_itp is parsed in Excited::YES mode first, then topology in Excited::NO mode
+ * (following #include).  Keys are "<residue>,<atom><nr>" and "<residue>,<atom><nr>,EXC"; first occurrence wins.
+ * device < 0 builds the tables only (no CUDA call is made; useful for inspecting the parse). */
+int cgc_create(const char *topology_path, const char *excited_itp_path, int device, cgc_context **out);
+void cgc_destroy(cgc_context *ctx);
+
+int cgc_table_size(const cgc_context *ctx);
+/* i-th table entry in insertion order == the reference's (mergeNameTable, massTable, chargeTable)[i]. */
+int cgc_table_entry(const cgc_context *ctx, int i, char *name, int name_cap, float *mass, float *charge);
+/* number of "conflicts with prior entry" notes (what the reference packs into InputFileMinorMalformed). */
+int cgc_topology_warnings(const cgc_context *ctx);
+
+/* ---- trajectory -------------------------------------------------------------------------------------------------
+ * cgc_open replaces everything ReadOneTimeGrom2Atom (src/grom2atomFMO.cpp:338-498) and AtomDataLookup_v2 (:549-610)
+ * derive that does NOT change from frame to frame: group ids, lookup keys, per-atom charges, per-site dQ lists.  It
+ * is done once on frame 0 with the reference's whitespace-token rules; the coordinates of every frame are then decoded
+ * on the device from fixed columns (layout checked against the token values on frame 0, CGC_ERR_UNSUPPORTED if they
+ * disagree).  cgc_open_memory is the same for trajectory text that already sits in host memory (not copied: it must
+ * stay valid until the context is destroyed or re-opened). */
+int cgc_open(cgc_context *ctx, const char *traj_path);
+int cgc_open_memory(cgc_context *ctx, const char *text, int64_t nbytes);
+
+int cgc_dims(const cgc_context *ctx, int *n_atoms, int *n_chromo, int *n_groups, int *num_tot);
+/* atomGroupi of ReadOneTimeGrom2Atom: -k for the k-th chromophore, +g for the g-th other residue. int32[n_atoms] */
+int cgc_get_groups(const cgc_context *ctx, int32_t *out);
+/* dE column of every atom. int32[n_atoms] */
+int cgc_get_columns(const cgc_context *ctx, int32_t *out);
+/* atomChargei_e of AtomDataLookup_v2 for excitationSite = site (1-based). float32[n_atoms] */
+int cgc_get_site_charges(const cgc_context *ctx, int site, float *out);
+/* lookup key "<mol>,<atom><ordinal>" of one atom (src/grom2atomFMO.cpp:460) */
+int cgc_get_key(const cgc_context *ctx, int atom, char *buf, int cap);
+/* frame geometry found by cgc_open: bytes per atom line (incl. newline), column of x, field width, decimals */
+int cgc_get_layout(const cgc_context *ctx, int *line_bytes, int *x_col, int *field_width, int *decimals);
+/* Index the whole trajectory and return the number of complete frames. */
+int cgc_frame_count(cgc_context *ctx, int64_t *n_frames);
+/* Byte offset (from the start of the text) of the first atom line of frame f; -1 past the end. */
+int64_t cgc_frame_atoms_offset(cgc_context *ctx, int64_t frame);
+
+/* ---- options ----------------------------------------------------------------------------------------------------
+ * "sites"        number of excitation sites to compute, 1..nChromo (default nChromo; the reference hard-codes 7,
+ *                src/FMOparse.cpp:133)
+ * "covariance"   0/1: accumulate n, sum(x-c), sum (x-c)(x-c)^T per site while running (default 1 when it fits)
+ * "batch_frames" frames per device batch (default: sized from the frame text size)
+ * Must be set after cgc_open and before the first cgc_run. */
+int cgc_set_option(cgc_context *ctx, const char *key, double value);
+double cgc_get_option(const cgc_context *ctx, const char *key);
+
+/* ---- the hot path -----------------------------------------------------------------------------------------------
+ * cgc_run replaces the per-frame body of main_Cr (src/FMOparse.cpp:68-179): for frames [first, first+n) it streams the
+ * text through pinned double-buffered H2D copies, decodes it (K1), evaluates ComputeCDC_v1 for every site (K2), and
+ * accumulates the Correlate sums (K3).  dE_kcal (nullable) receives float32 [n][sites][numTot], caller-owned HOST memory.
+ * Returns CGC_OK, or CGC_EOF with *frames_done < n when the trajectory ends early. */
+int cgc_run(cgc_context *ctx, int64_t first_frame, int64_t n_frames, float *dE_kcal, int64_t *frames_done);
+
+/* Same computation on text that is already in DEVICE memory (d_text 16-byte aligned; atoms_offset[f] = byte offset of
+ * the first atom line of frame f, HOST array).  d_dE_kcal: DEVICE float32 [n_frames][sites][numTot].  Work is enqueued
+ * on `stream` (a cudaStream_t, NULL = default stream) and NOT synchronised.  n_frames must not exceed "batch_frames". */
+int cgc_run_device(cgc_context *ctx, const void *d_text, int64_t text_bytes, const int64_t *atoms_offset,
+                   int n_frames, float *d_dE_kcal, void *stream);
+
+/* Decode only (K1): float32 [n_frames][n_atoms][3] = x,y,z into caller-owned DEVICE memory; for parity tests of the
+ * decoder against (float)atof (src/grom2atomFMO.cpp:448-450). */
+int cgc_decode_device(cgc_context *ctx, const void *d_text, int64_t text_bytes, const int64_t *atoms_offset,
+                      int n_frames, float *d_xyz, void *stream);
+
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t cgc_launch_count(const cgc_context *ctx);
+/* device-side decode error flags accumulated so far (0 = every coordinate field was well-formed) */
+int cgc_decode_errors(cgc_context *ctx, int *flags);
+
+/* ---- Correlate ("MergeDE", src/FMOparse.cpp:168-221) ---------------------------------------------------------------
+ * Partial sums live in one flat DEVICE buffer of doubles:  [ n | shift c (S*G) | sum(x-c) (S*G) | sum (x-c)(x-c)^T (S*G*G) ]
+ * with x in kcal/mol and c the dE row of the trajectory's frame 0 (identical on every rank), so that buffers of
+ * different ranks can be added element-wise except for the shift block, which is identical on all of them.
+ * cgc_cov_bind lets the caller own that buffer (e.g. a torch tensor that is then all-reduced over NCCL). */
+int64_t cgc_cov_size(const cgc_context *ctx);                       /* number of doubles; 0 when covariance is off */
+int cgc_cov_bind(cgc_context *ctx, double *d_buffer);               /* DEVICE pointer, cgc_cov_size doubles, zeroed here */
+int cgc_cov_reset(cgc_context *ctx);
+int cgc_cov_partials(cgc_context *ctx, double *host_out);           /* copy the flat buffer to HOST */
+/* Set the shift c from a DEVICE row float32 [sites][numTot] (the dE row of the trajectory's frame 0).  cgc_run does this
+ * itself; cgc_cov_accumulate_device falls back to the first row it is given when no shift was set. */
+int cgc_cov_set_shift_device(cgc_context *ctx, const float *d_row, void *stream);
+/* Accumulate rows that are already on the device: d_dE float32 [n_frames][sites][numTot] */
+int cgc_cov_accumulate_device(cgc_context *ctx, const float *d_dE_kcal, int n_frames, void *stream);
+/* mean [S][G] and covariance [S][G][G] (HOST, double) from the partial sums; ddof 0 = population (the formula the
+ * reference intends, src/FMOparse.cpp:189-206), 1 = np.cov as used by depca (scripts/depca/depca/sidechain_corr.py:67). */
+int cgc_cov_finalize(cgc_context *ctx, int ddof, double *mean, double *cov);
+
+/* ---- writers ----------------------------------------------------------------------------------------------------
+ * cgc_write_time appends rows to <path> exactly as src/FMOparse.cpp:151-165 does: value = float(double(kcal)*349.7),
+ * printed with "%g" (6 significant digits), ',' separated, one line per (frame, site).  truncate != 0 empties the file
+ * first (src/FMOparse.cpp:48-50). */
+int cgc_write_time(const char *path, int truncate, const float *dE_kcal, int64_t rows, int num_tot);
+/* cgc_write_mtx writes sites*numTot lines of numTot values (src/FMOparse.cpp:208-221).  compat == 0: population
+ * covariance in (kcal/mol)^2; compat != 0: the reference's literal arithmetic including its zero stride
+ * (src/FMOparse.cpp:42,193,202), i.e. sum_t x_0 x_j / T^numTot - <x_i><x_j> in float32. */
+int cgc_write_mtx(cgc_context *ctx, const char *path, int compat);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGROMCORR_H */
