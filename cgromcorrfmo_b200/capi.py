@@ -49,6 +49,7 @@ SIGNATURES = {
     "cgc_run": (c_int, [c_void_p, c_int64, c_int64, c_void_p, POINTER(c_int64)]),
     "cgc_run_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "cgc_decode_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
+    "cgc_kernel_times": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "cgc_launch_count": (c_int64, [c_void_p]),
     "cgc_decode_errors": (c_int, [c_void_p, POINTER(c_int)]),
     "cgc_cov_size": (c_int64, [c_void_p]),
@@ -276,6 +277,13 @@ class Context:
         off = np.ascontiguousarray(atoms_offset, dtype=np.int64)
         self._check(self._lib.cgc_decode_device(self._h, _ptr(d_text), int(text_bytes), _ptr(off), int(n_frames),
                                                 _ptr(d_xyz), c_void_p(int(stream))))
+
+    def kernel_times(self, reset: bool = False):
+        """{kernel: (ms, launches)} accumulated since option "profile" was switched on (CUDA events on the launch stream)."""
+        ms = np.zeros(4, np.float64)
+        n = np.zeros(4, np.int64)
+        self._check(self._lib.cgc_kernel_times(self._h, _ptr(ms), _ptr(n), 1 if reset else 0))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("decode", "cdc", "finish", "cov"))}
 
     @property
     def launch_count(self) -> int:

@@ -94,6 +94,14 @@ struct cgc_context {
   int* d_err = nullptr;
   int64_t launches = 0;
 
+  // optional per-kernel timing (option "profile"): event pairs around each launch of the hot path
+  bool profile = false;
+  struct Timed { cudaEvent_t a, b; int kind; };
+  std::vector<Timed> timed;            // recorded, not yet read
+  std::vector<cudaEvent_t> ev_pool;    // recycled events
+  double kernel_ms[4] = {0, 0, 0, 0};  // K1 decode, K2 cdc, finish, K3 cov
+  int64_t kernel_n[4] = {0, 0, 0, 0};
+
   // Correlate
   double* d_cov = nullptr;
   bool cov_bound = false;
@@ -159,6 +167,8 @@ cgc_context::~cgc_context() {
   free_pipeline(this);
   free_static(this);
   if (device >= 0) {
+    for (auto& t : timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto& e : ev_pool) cudaEventDestroy(e);
     if (st_copy) cudaStreamDestroy(st_copy);
     if (st_comp) cudaStreamDestroy(st_comp);
     if (d_err) cudaFree(d_err);
@@ -394,13 +404,65 @@ void parallel_copy(char* dst, const char* src, int64_t n) {
   for (auto& t : th) t.join();
 }
 
+cudaEvent_t take_event(cgc_context* c) {
+  if (!c->ev_pool.empty()) {
+    cudaEvent_t e = c->ev_pool.back();
+    c->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  CUDA_OK(cudaEventCreate(&e));
+  return e;
+}
+
+struct ScopedKernelTimer {
+  cgc_context* c;
+  cudaStream_t st;
+  cgc_context::Timed t{};
+  bool on;
+  ScopedKernelTimer(cgc_context* c_, int kind, cudaStream_t st_) : c(c_), st(st_), on(c_->profile) {
+    if (!on) return;
+    t.a = take_event(c);
+    t.b = take_event(c);
+    t.kind = kind;
+    cudaEventRecord(t.a, st);
+  }
+  ~ScopedKernelTimer() {
+    if (!on) return;
+    cudaEventRecord(t.b, st);
+    c->timed.push_back(t);
+  }
+};
+
+void collect_kernel_times(cgc_context* c) {
+  for (auto& t : c->timed) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+      c->kernel_ms[t.kind] += ms;
+      c->kernel_n[t.kind]++;
+    }
+    c->ev_pool.push_back(t.a);
+    c->ev_pool.push_back(t.b);
+  }
+  c->timed.clear();
+}
+
 // K1 -> K2 -> finish (-> K3) for one batch whose text is already in d_text; everything on `st`
 void enqueue_compute(cgc_context* c, const char* d_text, int64_t text_bytes, const int64_t* d_off, int n_frames,
                      float* d_xyz8, float4* d_sites, double* d_acc, float* d_dE, bool accumulate, cudaStream_t st) {
   const DeviceSystem& sys = c->sys;
-  launch_decode(sys, d_text, text_bytes, d_off, n_frames, d_xyz8, d_sites, c->d_err, st);
-  launch_cdc(sys, d_xyz8, d_sites, d_acc, n_frames, c->sm_count, st);
-  launch_finish(d_acc, d_dE, (int64_t)n_frames * sys.n_sites * sys.num_tot, st);
+  {
+    ScopedKernelTimer t(c, 0, st);
+    launch_decode(sys, d_text, text_bytes, d_off, n_frames, d_xyz8, d_sites, c->d_err, st);
+  }
+  {
+    ScopedKernelTimer t(c, 1, st);
+    launch_cdc(sys, d_xyz8, d_sites, d_acc, n_frames, c->sm_count, st);
+  }
+  {
+    ScopedKernelTimer t(c, 2, st);
+    launch_finish(d_acc, d_dE, (int64_t)n_frames * sys.n_sites * sys.num_tot, st);
+  }
   c->launches += 3;
   if (accumulate && c->d_cov) {
     if (!c->shift_set) {
@@ -408,7 +470,10 @@ void enqueue_compute(cgc_context* c, const char* d_text, int64_t text_bytes, con
       c->shift_set = true;
       c->launches++;
     }
-    launch_cov_accumulate(d_dE, n_frames, c->d_cov, c->d_compat, sys.n_sites, sys.num_tot, st);
+    {
+      ScopedKernelTimer t(c, 3, st);
+      launch_cov_accumulate(d_dE, n_frames, c->d_cov, c->d_compat, sys.n_sites, sys.num_tot, st);
+    }
     c->launches += 2;
   }
   CUDA_OK(cudaGetLastError());
@@ -604,6 +669,8 @@ int cgc_set_option(cgc_context* ctx, const char* key, double value) {
       }
     } else if (k == "covariance") {
       ctx->cov_opt = value != 0.0 ? 1 : 0;
+    } else if (k == "profile") {
+      ctx->profile = value != 0.0;
     } else if (k == "batch_frames") {
       if (value < 1 || value > 65535) throw std::invalid_argument("batch_frames must be within 1..65535");
       ctx->batch_frames = (int)value;
@@ -626,6 +693,23 @@ double cgc_get_option(const cgc_context* ctx, const char* key) {
 }
 
 int64_t cgc_launch_count(const cgc_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int cgc_kernel_times(cgc_context* ctx, double* ms, int64_t* launches, int reset) {
+  if (!ctx || !ms || !launches) return fail(ctx, CGC_ERR_ARG, "null argument");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    collect_kernel_times(ctx);
+    for (int i = 0; i < 4; i++) {
+      ms[i] = ctx->kernel_ms[i];
+      launches[i] = ctx->kernel_n[i];
+      if (reset) {
+        ctx->kernel_ms[i] = 0;
+        ctx->kernel_n[i] = 0;
+      }
+    }
+    return CGC_OK;
+  });
+}
 
 int cgc_decode_errors(cgc_context* ctx, int* flags) {
   if (!ctx || !flags) return fail(ctx, CGC_ERR_ARG, "null argument");
@@ -849,7 +933,10 @@ int cgc_cov_accumulate_device(cgc_context* ctx, const float* d_dE_kcal, int n_fr
       ctx->shift_set = true;
       ctx->launches++;
     }
-    launch_cov_accumulate(d_dE_kcal, n_frames, ctx->d_cov, ctx->d_compat, ctx->sys.n_sites, ctx->sys.num_tot, st);
+    {
+      ScopedKernelTimer t(ctx, 3, st);
+      launch_cov_accumulate(d_dE_kcal, n_frames, ctx->d_cov, ctx->d_compat, ctx->sys.n_sites, ctx->sys.num_tot, st);
+    }
     ctx->launches += 2;
     CUDA_OK(cudaGetLastError());
     return CGC_OK;

@@ -90,6 +90,7 @@ int64_t cgc_frame_atoms_offset(cgc_context *ctx, int64_t frame);
  *                src/FMOparse.cpp:133)
  * "covariance"   0/1: accumulate n, sum(x-c), sum (x-c)(x-c)^T per site while running (default 1 when it fits)
  * "batch_frames" frames per device batch (default: sized from the frame text size)
+ * "profile"      0/1: time every hot-path kernel with CUDA events (see cgc_kernel_times)
  * Must be set after cgc_open and before the first cgc_run. */
 int cgc_set_option(cgc_context *ctx, const char *key, double value);
 double cgc_get_option(const cgc_context *ctx, const char *key);
@@ -112,6 +113,10 @@ int cgc_run_device(cgc_context *ctx, const void *d_text, int64_t text_bytes, con
 int cgc_decode_device(cgc_context *ctx, const void *d_text, int64_t text_bytes, const int64_t *atoms_offset,
                       int n_frames, float *d_xyz, void *stream);
 
+ /* With option "profile" = 1 every hot-path kernel launch is bracketed by CUDA events on its own stream; this returns the
+ * accumulated device time in ms and the launch count per kernel: [0] K1 decode, [1] K2 CDC pair sum, [2] FP64 bins ->
+ * float32 rows, [3] K3 Correlate.  Synchronises on the recorded events.  reset != 0 clears the totals. */
+int cgc_kernel_times(cgc_context *ctx, double *ms4, int64_t *launches4, int reset);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t cgc_launch_count(const cgc_context *ctx);
 /* device-side decode error flags accumulated so far (0 = every coordinate field was well-formed) */

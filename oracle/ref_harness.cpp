@@ -11,9 +11,12 @@
 //   <out>.x0.f32       float32[3*natoms]    coordinates of frame 0
 //   <out>.q.f32        float32[nchromo][natoms]  AtomDataLookup_v2 charges per excited site (frame 0)
 //   <out>.dE.f32       float32[frames][nchromo][numtot]  ComputeCDC_v1 output (kcal/mol), raw bits
-//   <out>.timing.txt   "read_s lookup_s cdc_s total_s frames" wall-clock of the frame loop (no start-up)
+//   <out>.timing.txt   "read_s lookup_s cdc_s total_s frames topo_s sites" wall-clock of the frame loop (no start-up)
+//   <out>.frames.txt   one line per frame: "read_s lookup_s cdc_s"
 //
-// Usage: ref_harness traj top itp out num_frames [first_frame_to_time_from]
+// Usage: ref_harness traj top itp out num_frames [max_sites [dump]]
+//   max_sites > 0 evaluates only sites 1..max_sites of every frame (a bounded sample for CPU timing: sites are
+//   independent and equally expensive); dump = 0 skips the binary dumps.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -47,6 +50,8 @@ int main(int argc, char** argv) {
   }
   std::string traj = argv[1], top = argv[2], itp = argv[3], out = argv[4];
   int num_frames = atoi(argv[5]);
+  int max_sites = argc > 6 ? atoi(argv[6]) : 0;
+  bool do_dump = argc > 7 ? atoi(argv[7]) != 0 : true;
 
   std::vector<std::string> names;
   std::vector<float> masses, charges;
@@ -60,6 +65,8 @@ int main(int argc, char** argv) {
   double t_read = 0, t_lookup = 0, t_cdc = 0;
   int nchromo = 0, ngroups = 0, numtot = 0, natoms = 0, done = 0;
   dump<float>(out + ".dE.f32", nullptr, 0, "wb");
+  std::ofstream per_frame(out + ".frames.txt");
+  int sites_done = 0;
   double t_loop0 = now_s();
   for (int t = 0; t < num_frames; t++) {
     std::vector<float> Xi;
@@ -69,30 +76,35 @@ int main(int argc, char** argv) {
     double t0 = now_s();
     ReadOneTimeGrom2Atom(have_pos ? &cur : 0, next, Xi, types, groups, box, traj);
     cur = next; have_pos = true;
-    t_read += now_s() - t0;
+    double f_read = now_s() - t0, f_lookup = 0, f_cdc = 0;
+    t_read += f_read;
     if (groups.empty()) break;  // ran off the end of the file (the stock CLI segfaults here)
     ngroups = *std::max_element(groups.begin(), groups.end());
     nchromo = std::abs(*std::min_element(groups.begin(), groups.end()));
     numtot = ngroups + nchromo;
     natoms = (int)groups.size();
-    if (t == 0) {
+    if (t == 0 && do_dump) {
       dump<int>(out + ".groups.i32", groups.data(), groups.size(), "wb");
       dump<float>(out + ".x0.f32", Xi.data(), Xi.size(), "wb");
       std::ofstream k(out + ".keys.txt");
       for (auto& s : types) k << s << "\n";
       dump<float>(out + ".q.f32", nullptr, 0, "wb");
     }
-    for (int site = 1; site <= nchromo; site++) {
+    sites_done = (max_sites > 0 && max_sites < nchromo) ? max_sites : nchromo;
+    for (int site = 1; site <= sites_done; site++) {
       std::vector<float> m, sz, q, ground, cdc;
       t0 = now_s();
       AtomDataLookup_v2(types, m, sz, q, groups, site, ground, names, masses, charges);
-      t_lookup += now_s() - t0;
-      if (t == 0) dump<float>(out + ".q.f32", q.data(), q.size(), "ab");
+      f_lookup += now_s() - t0;
+      if (t == 0 && do_dump) dump<float>(out + ".q.f32", q.data(), q.size(), "ab");
       t0 = now_s();
       ComputeCDC_v1(site, cdc, Xi, q, groups, ground);
-      t_cdc += now_s() - t0;
-      dump<float>(out + ".dE.f32", cdc.data(), cdc.size(), "ab");
+      f_cdc += now_s() - t0;
+      if (do_dump) dump<float>(out + ".dE.f32", cdc.data(), cdc.size(), "ab");
     }
+    t_lookup += f_lookup;
+    t_cdc += f_cdc;
+    per_frame << f_read << " " << f_lookup << " " << f_cdc << "\n";
     done++;
   }
   double t_loop = now_s() - t_loop0;
@@ -100,7 +112,8 @@ int main(int argc, char** argv) {
     std::ofstream m(out + ".meta.txt");
     m << natoms << " " << nchromo << " " << ngroups << " " << numtot << " " << done << "\n";
     std::ofstream tm(out + ".timing.txt");
-    tm << t_read << " " << t_lookup << " " << t_cdc << " " << t_loop << " " << done << " " << t_topo << "\n";
+    tm << t_read << " " << t_lookup << " " << t_cdc << " " << t_loop << " " << done << " " << t_topo << " " << sites_done
+       << "\n";
   }
   return 0;
 }

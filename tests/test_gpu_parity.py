@@ -1,0 +1,378 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C-ABI (cgromcorrfmo_b200/capi.py ->
+libcgromcorr.so); the oracle (oracle/) is only the checker.
+
+Tolerances (BASELINE.json north_star, made precise in SURVEY.md section 8c):
+  * group ids, columns, frame counts, decoded coordinates: bit-exact;
+  * dE: |dE_gpu - dE_exact| <= 1e-6 * max(|dE_exact|, sum over pairs of |term|) per entry, dE_exact = the float64
+    restatement fed the same float32 inputs; per-site totals within 1e-6 of the same scale;
+  * covariance: 1e-9 relative to max(|C_ij|, sqrt(C_ii C_jj)) against float64 on the identical dE matrix.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import scaled_err, sha
+
+pytestmark = pytest.mark.gpu
+
+DE_TOL = 1e-6
+COV_TOL = 1e-9
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "the gpu tests need a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def capi_mod():
+    from cgromcorrfmo_b200 import capi
+    capi.load()
+    return capi
+
+
+def _device_text(torch, path):
+    text = np.fromfile(path, dtype=np.uint8)
+    padded = np.concatenate([text, np.zeros(((-text.size) % 16) + 16, np.uint8)])
+    return torch.from_numpy(padded).cuda(), text.size
+
+
+@pytest.mark.parametrize("tag", ["tiny", "permol", "nosolv"])
+def test_dE_against_oracle(tag, small_inputs, oracle_mod, capi_mod):
+    O, capi = oracle_mod, capi_mod
+    traj, top, itp, frames = small_inputs(tag)
+    ref = O.run(traj, top, itp, frames)
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        assert np.array_equal(c.groups(), ref["groups"])
+        dE, done, rc = c.run(0, frames)
+        assert rc == capi.CGC_OK and done == frames == ref["frames"]
+        assert dE.shape == ref["dE_f64"].shape
+        e, z = scaled_err(dE, ref["dE_f64"], ref["scale"])
+        assert e <= DE_TOL, "max scaled error %g" % e
+        assert z == 0.0                                    # the own-site column (and any empty column) stays exactly 0
+        tot_err = np.abs(dE.astype(np.float64).sum(-1) - ref["dE_f64"].sum(-1))
+        assert np.all(tot_err <= DE_TOL * np.maximum(np.abs(ref["dE_f64"].sum(-1)), ref["scale"].sum(-1)))
+        # not worse than the reference's own float32 noise by more than a small factor
+        e_ref, _ = scaled_err(ref["dE_f32"], ref["dE_f64"], ref["scale"])
+        assert e <= max(4 * e_ref, 2e-7)
+        assert c.decode_errors() == 0
+        assert c.launch_count >= 3
+
+
+def test_dE_against_reference_golden(small_inputs, capi_mod, oracle_mod):
+    """Against raw float32 rows dumped by the unmodified reference (tests/golden/golden7.npz).  Both sides carry their own
+    float32 rounding relative to exact arithmetic (the reference's is <= ~2e-7 of the cancellation scale, SURVEY.md
+    section 8c), so the bound is 1e-6 + that, on the scale sum|term| which the oracle supplies."""
+    capi, O = capi_mod, oracle_mod
+    g = np.load(os.path.join(GOLD, "golden7.npz"))
+    traj, top, itp, frames = small_inputs("golden7")
+    if [sha(traj), sha(top), sha(itp)] != list(g["sha"]):
+        pytest.skip("synthetic generator produced different bytes than when the golden file was made")
+    scale = O.run(traj, top, itp, frames)["scale"]
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        assert np.array_equal(c.groups(), g["groups"])
+        dE, done, _ = c.run(0, frames)
+    ref = g["dE_f32"].astype(np.float64)
+    scale = np.maximum(scale, np.abs(ref))
+    assert np.all(np.abs(dE - ref) <= 1.2e-6 * scale)
+    assert np.all(dE[scale == 0] == 0)
+    # the .time text the stock CLI wrote for sites 1..7: 6 printed digits (half a unit in the 6th place) on top of that
+    rows = np.array([[float(v) for v in ln.split(",")] for ln in str(g["time_text"]).strip().split("\n")])
+    ours = (dE[:, :7].reshape(-1, dE.shape[-1]).astype(np.float64) * 349.7)
+    sc = scale[:, :7].reshape(-1, dE.shape[-1]) * 349.7
+    assert np.all(np.abs(ours - rows) <= 1.2e-6 * sc + 6e-6 * np.abs(rows))
+
+
+def test_reference_fixture_on_gpu(ref_fixture, oracle_mod, capi_mod):
+    """The reference's own test inputs: 6383 atoms, 7 BCL, 2 frames (reference src/test/)."""
+    O, capi = oracle_mod, capi_mod
+    traj, top, itp = ref_fixture
+    ref = O.run(traj, top, itp, 2)
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        assert c.dims() == (6383, 7, 350, 357)
+        dE, done, rc = c.run(0, 2)
+    e, z = scaled_err(dE, ref["dE_f64"], ref["scale"])
+    assert e <= DE_TOL and z == 0.0
+    tot = (dE[0].astype(np.float64) * 349.7).sum(-1)      # BASELINE.md section 2 smoke values
+    assert np.allclose(tot, [383.37, 132.194, -175.118, -276.294, -347.642, -104.302, -76.3561], rtol=2e-5)
+
+
+@pytest.mark.parametrize("tag", ["tiny", "permol"])
+def test_decode_bit_exact(tag, small_inputs, oracle_mod, capi_mod, torch_cuda):
+    """K1 against (float)atof of the tokens (reference src/grom2atomFMO.cpp:448-450), every frame, bit for bit."""
+    O, capi, torch = oracle_mod, capi_mod, torch_cuda
+    traj, top, itp, frames = small_inputs(tag)
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        d_text, nbytes = _device_text(torch, traj)
+        offs = [c.frame_atoms_offset(f) for f in range(frames)]
+        xyz = torch.empty((frames, c.n_atoms, 3), dtype=torch.float32, device="cuda")
+        c.decode_device(d_text.data_ptr(), nbytes, offs, frames, xyz.data_ptr())
+        torch.cuda.synchronize()
+        assert c.decode_errors() == 0
+        got = xyz.cpu().numpy()
+    pos = None
+    for f in range(frames):
+        pos, Xi, _, _, _ = O.read_frame(traj, pos)
+        assert np.array_equal(got[f].reshape(-1).view(np.uint32), Xi.view(np.uint32))
+
+
+def test_decode_negative_and_edge_values(tmp_path, capi_mod, torch_cuda, small_inputs):
+    """Negative coordinates, -0.000, the largest field value, every digit position."""
+    capi, torch = capi_mod, torch_cuda
+    _, top, itp, _ = small_inputs("tiny")
+    from cgromcorrfmo_b200 import synth
+    names = synth.bcl_atom_names()
+    vals = [-0.0, -0.001, 0.0, 0.001, -999.999, 9999.999, 1234.567, -12.345, 0.5, 8.415, 16777.215 % 10000, 0.009]
+    rng = np.random.default_rng(3)
+    lines = []
+    for i in range(140):
+        x, y, z = (vals[(i + k) % len(vals)] if i < 36 else float(np.round(rng.uniform(-999, 9999), 3)) for k in range(3))
+        lines.append("%5d%-5s%5s%5d%8.3f%8.3f%8.3f\n" % (1, "BCL", names[i], i + 1, x, y, z))
+    text = "edge t= 0.0\n  140\n" + "".join(lines) + "   1.0   1.0   1.0\n"
+    p = tmp_path / "edge.gro"
+    p.write_text(text)
+    with capi.Context(top, itp, 0) as c:
+        c.open(str(p))
+        d_text, nbytes = _device_text(torch, str(p))
+        xyz = torch.empty((1, 140, 3), dtype=torch.float32, device="cuda")
+        c.decode_device(d_text.data_ptr(), nbytes, [c.frame_atoms_offset(0)], 1, xyz.data_ptr())
+        torch.cuda.synchronize()
+        got = xyz.cpu().numpy().reshape(-1)
+    expect = np.array([np.float32(float(ln[20 + 8 * k: 28 + 8 * k])) for ln in lines for k in range(3)], np.float32)
+    assert np.array_equal(got.view(np.uint32), expect.view(np.uint32))      # includes the sign bit of -0.000
+
+
+def test_decode_flags_malformed_text(tmp_path, capi_mod, small_inputs):
+    """A coordinate field damaged in a LATER frame is caught on the device and surfaces as InputFileMalformed."""
+    capi = capi_mod
+    traj, top, itp, frames = small_inputs("tiny")
+    data = bytearray(open(traj, "rb").read())
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        off = c.frame_atoms_offset(1)
+    data[off + 45 * 10 + 23] = ord("x")
+    bad = tmp_path / "bad.gro"
+    bad.write_bytes(bytes(data))
+    with capi.Context(top, itp, 0) as c:
+        c.open(str(bad))
+        with pytest.raises(capi.CgcError) as e:
+            c.run(0, frames)
+        assert e.value.code == capi.CGC_ERR_INPUT_MALFORMED
+
+
+def test_device_and_host_paths_agree_and_frames_are_independent(small_inputs, capi_mod, torch_cuda):
+    capi, torch = capi_mod, torch_cuda
+    traj, top, itp, frames = small_inputs("tiny")
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        full, done, _ = c.run(0, frames)
+        d_text, nbytes = _device_text(torch, traj)
+        offs = [c.frame_atoms_offset(f) for f in range(frames)]
+        dEd = torch.empty((frames, c.n_sites, c.num_tot), dtype=torch.float32, device="cuda")
+        c.run_device(d_text.data_ptr(), nbytes, offs, frames, dEd.data_ptr())
+        torch.cuda.synchronize()
+        dev = dEd.cpu().numpy()
+        # a frame's row does not depend on which batch it travels in (sharding across ranks relies on this)
+        c.set_option("batch_frames", 1)
+        one_by_one, _, _ = c.run(0, frames)
+        tail, done_tail, _ = c.run(1, frames - 1)
+    s = np.abs(full).max()
+    assert np.abs(dev - full).max() <= 1e-6 * s
+    assert np.abs(one_by_one - full).max() <= 1e-6 * s
+    assert done_tail == frames - 1 and np.abs(tail - full[1:]).max() <= 1e-6 * s
+
+
+def test_eof_is_clean(small_inputs, capi_mod):
+    """Asking for more frames than the file holds returns CGC_EOF with the frames that exist
+    (the reference segfaults, reference README.md:31)."""
+    capi = capi_mod
+    traj, top, itp, frames = small_inputs("tiny")
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        dE, done, rc = c.run(0, frames + 5)
+        assert rc == capi.CGC_EOF and done == frames and dE.shape[0] == frames
+        dE2, done2, rc2 = c.run(frames, 2)
+        assert rc2 == capi.CGC_EOF and done2 == 0
+
+
+def test_sites_option_matches_reference_seven(small_inputs, oracle_mod, capi_mod):
+    """--sites 7 reproduces the stock program's site loop (reference src/FMOparse.cpp:133) on an 8-BCL system."""
+    O, capi = oracle_mod, capi_mod
+    traj, top, itp, frames = small_inputs("tiny")
+    ref = O.run(traj, top, itp, frames, n_sites=7)
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        c.set_option("sites", 7)
+        dE, done, _ = c.run(0, frames)
+    assert dE.shape[1] == 7
+    e, z = scaled_err(dE, ref["dE_f64"], ref["scale"])
+    assert e <= DE_TOL and z == 0.0
+
+
+@pytest.mark.parametrize("tag", ["tiny", "permol"])
+def test_covariance(tag, small_inputs, oracle_mod, capi_mod):
+    O, capi = oracle_mod, capi_mod
+    traj, top, itp, frames = small_inputs(tag)
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        c.set_option("batch_frames", 2)                   # more than one batch: sums carry across launches
+        dE, done, _ = c.run(0, frames)
+        for ddof in (0, 1):
+            if frames - ddof <= 0:
+                continue
+            mean, cov = c.cov_finalize(ddof)
+            m64, c64 = O.cov_f64(dE, ddof)
+            scale = np.maximum(np.abs(c64), np.sqrt(np.einsum("sii,sjj->sij", c64, c64)))
+            ok = scale > 0
+            assert np.all(np.abs(cov - c64)[ok] <= COV_TOL * scale[ok])
+            assert np.all(cov[~ok] == 0) if (~ok).any() else True
+            assert np.allclose(mean, m64, rtol=1e-12, atol=1e-300)
+            assert np.array_equal(cov, np.swapaxes(cov, 1, 2))          # exactly symmetric
+        part = c.cov_partials()
+        assert part[0] == frames
+
+
+def test_covariance_long_random_rows(capi_mod, torch_cuda, small_inputs):
+    """K3 alone on many frames of synthetic rows with a large mean (the cancellation the shift is there for)."""
+    capi, torch = capi_mod, torch_cuda
+    traj, top, itp, frames = small_inputs("tiny")
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        S, G = c.n_sites, c.num_tot
+        rng = np.random.default_rng(11)
+        T = 3000
+        X = (rng.normal(size=(T, S, G)) * 0.05 + rng.normal(size=(1, S, G)) * 50.0).astype(np.float32)
+        d = torch.from_numpy(X).cuda()
+        c.cov_reset()
+        for t0 in range(0, T, 700):
+            n = min(700, T - t0)
+            c.cov_accumulate_device(d[t0:t0 + n].contiguous().data_ptr(), n)
+        torch.cuda.synchronize()
+        mean, cov = c.cov_finalize(1)
+    X64 = X.astype(np.float64)
+    for k in range(S):
+        ref = np.cov(X64[:, k, :], rowvar=False, ddof=1)      # depca's np.cov (sidechain_corr.py:67)
+        scale = np.maximum(np.abs(ref), np.sqrt(np.outer(np.diag(ref), np.diag(ref))))
+        assert np.all(np.abs(cov[k] - ref) <= COV_TOL * scale)
+        assert np.allclose(mean[k], X64[:, k, :].mean(0), rtol=1e-12)
+
+
+def test_writers_match_reference_format(small_inputs, oracle_mod, capi_mod, tmp_path):
+    """.time and the compat .mtx are byte-identical to the reference's formatting of the same float32 rows."""
+    O, capi = oracle_mod, capi_mod
+    traj, top, itp, frames = small_inputs("tiny")
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        dE, done, _ = c.run(0, frames)
+        capi.write_time(str(tmp_path / "o.time"), dE)
+        assert open(tmp_path / "o.time").read() == O.format_time_rows(dE.reshape(-1, dE.shape[-1]))
+        c.write_mtx(str(tmp_path / "o_compat.mtx"), compat=True)
+        assert open(tmp_path / "o_compat.mtx").read() == O.format_mtx(O.mtx_compat_f32(dE))
+        c.write_mtx(str(tmp_path / "o.mtx"), compat=False)
+        _, c64 = O.cov_f64(dE, 0)
+        assert open(tmp_path / "o.mtx").read() == O.format_mtx(c64.astype(np.float32))
+
+
+def test_cli_drop_in(small_inputs, oracle_mod, capi_mod, tmp_path):
+    """The CLI driver with the reference's five positionals: exit codes, .time/.mtx shapes, parity with the stock binary
+    (when oracle/_ref travelled to this box) to the 6 printed digits."""
+    import subprocess
+    from cgromcorrfmo_b200 import build
+    O = oracle_mod
+    traj, top, itp, frames = small_inputs("golden7")
+    exe = build.CLI
+    assert os.path.exists(exe)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "Order of args" in r.stdout                      # reference src/FMOparse.cpp:325-329
+    out = str(tmp_path / "out")
+    r = subprocess.run([exe, traj, top, itp, out, str(frames), "--mtx-compat"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = [ln.split(",") for ln in open(out + ".time").read().strip().split("\n")]
+    assert len(rows) == frames * 7 and all(len(x) == len(rows[0]) for x in rows)
+    G = len(rows[0])
+    mtx = open(out + ".mtx").read().strip().split("\n")
+    assert len(mtx) == 7 * G and all(len(x.split(",")) == G for x in mtx)
+    g = np.load(os.path.join(GOLD, "golden7.npz"))
+    if [sha(traj), sha(top), sha(itp)] == list(g["sha"]):
+        scale = O.run(traj, top, itp, frames)["scale"][:, :7].reshape(-1, G) * 349.7
+        ref_rows = np.array([[float(v) for v in ln.split(",")] for ln in str(g["time_text"]).strip().split("\n")])
+        ours = np.array(rows, dtype=np.float64)
+        # both files print 6 significant digits
+        assert np.all(np.abs(ours - ref_rows) <= 1.2e-6 * scale + 1.2e-5 * np.abs(ref_rows))
+        ref_m = np.array([[float(v) for v in ln.split(",")] for ln in str(g["mtx_text"]).strip().split("\n")])
+        ours_m = np.array([[float(v) for v in ln.split(",")] for ln in mtx])
+        assert np.all(np.abs(ours_m - ref_m) <= 1e-4 * np.abs(ref_m).max())
+    # more frames than the file holds: clean stop, exit 0, .time holds what exists
+    r = subprocess.run([exe, traj, top, itp, out + "2", str(frames + 4)], capture_output=True, text=True)
+    assert r.returncode == 0 and "ended after" in r.stderr
+    assert len(open(out + "2.time").read().strip().split("\n")) == frames * 7
+    # malformed input: the reference dies with SIGABRT (134) on InputFileMalformed
+    r = subprocess.run([exe, traj, str(tmp_path / "missing.top"), itp, out + "3", "1"], capture_output=True, text=True)
+    assert r.returncode == 134 and "InputFileMalformed" in r.stderr
+
+
+def test_full_size_properties(capi_mod, torch_cuda):
+    """BASELINE.json's C2 shape (100k atoms, 24 sites): properties that need no CPU oracle.
+      (a) per-site totals equal an independent float64 evaluation of the same double sum in torch on the GPU;
+      (b) splitting one group into two leaves every other column unchanged and the two halves add up to the original."""
+    capi, torch = capi_mod, torch_cuda
+    from cgromcorrfmo_b200 import synth
+    import tempfile
+    s = synth.named_system("C2")
+    prefix = synth._static_prefix(s)
+    with tempfile.TemporaryDirectory() as d:
+        top, itp = os.path.join(d, "t.top"), os.path.join(d, "b.itp")
+        synth.write_top(top, s)
+        synth.write_itp(itp, s)
+        blob = synth.frame_bytes(s, prefix, 0) + synth.frame_bytes(s, prefix, 1)
+        with capi.Context(top, itp, 0) as c:
+            c.open_memory(blob)
+            n_atoms, n_chromo, n_groups, G = c.dims()
+            assert (n_atoms, n_chromo) == (100000, 24)
+            dE, done, _ = c.run(0, 2)
+            assert done == 2
+            groups = c.groups()
+            x = torch.tensor(synth.frame_milli(s, 0), dtype=torch.float64, device="cuda") / 1000.0
+            x = x.to(torch.float32).to(torch.float64)     # the float32 values the decoder produces
+            tot = np.zeros(n_chromo)
+            absum = np.zeros(n_chromo)
+            for site in range(1, n_chromo + 1):
+                q = torch.tensor(c.site_charges(site), dtype=torch.float64, device="cuda")
+                sel = torch.tensor(groups == -site, device="cuda")
+                dq = q[sel]
+                nz = dq != 0
+                xc, dq = x[sel][nz], dq[nz]
+                env = ~sel
+                r = torch.cdist(x[env], xc)
+                terms = (float(np.float32(33.2)) * q[env])[:, None] * dq[None, :] / r
+                tot[site - 1] = terms.sum().item()
+                absum[site - 1] = terms.abs().sum().item()
+            ours = dE[0].astype(np.float64).sum(-1)
+            assert np.all(np.abs(ours - tot) <= DE_TOL * np.maximum(np.abs(tot), absum))
+        # (b) re-number the second half of one protein residue: its column splits in two
+        a0 = int(np.nonzero(groups == 5)[0][0])
+        n5 = int((groups == 5).sum())
+        assert n5 >= 4
+        resnr2 = s.resnr.copy()
+        resnr2[a0 + n5 // 2: a0 + n5] = 99999                # a number no neighbour uses
+        import dataclasses
+        s2 = dataclasses.replace(s, resnr=resnr2)
+        top2 = os.path.join(d, "t2.top")
+        synth.write_top(top2, s2)
+        blob2 = synth.frame_bytes(s2, synth._static_prefix(s2), 0)
+        with capi.Context(top2, itp, 0) as c2:
+            c2.open_memory(blob2)
+            assert c2.num_tot == G + 1
+            dE2, _, _ = c2.run(0, 1)
+        col = n_chromo + 5 - 1
+        merged = np.concatenate([dE2[0][:, :col], (dE2[0][:, col] + dE2[0][:, col + 1])[:, None], dE2[0][:, col + 2:]], axis=1)
+        yard = np.abs(dE[0]).max()
+        assert np.abs(merged - dE[0]).max() <= 2e-6 * yard
