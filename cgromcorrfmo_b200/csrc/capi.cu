@@ -269,7 +269,7 @@ void build_static(cgc_context* c) {
   for (int s = 0; s < sys.n_sites; s++) P = std::max(P, count[s]);
   sys.site_cap = P;
   if (cdc_smem_bytes(sys) > 200 * 1024) {
-    throw Unsupported("site block (sites x dQ atoms x 32 B, double buffered) exceeds shared memory; lower the \"sites\" option");
+    throw Unsupported("site block (sites x dQ atoms x 16 B, double buffered) exceeds shared memory; lower the \"sites\" option");
   }
   std::vector<float> slot_dq((size_t)sys.n_sites * P, 0.f);
   std::fill(count.begin(), count.end(), 0);
@@ -356,7 +356,7 @@ void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_ho
     CUDA_OK(cudaMalloc(&s.d_off, sizeof(int64_t) * batch));
     CUDA_OK(cudaHostAlloc(&s.h_off, sizeof(int64_t) * batch, cudaHostAllocDefault));
     CUDA_OK(cudaMalloc(&s.d_xyz8, sizeof(float) * 3 * (size_t)sys.n_pad * batch));
-    CUDA_OK(cudaMalloc(&s.d_sites, (size_t)32 * sys.n_sites * sys.site_cap * batch));
+    CUDA_OK(cudaMalloc(&s.d_sites, (size_t)16 * sys.n_sites * sys.site_cap * batch));
     CUDA_OK(cudaMalloc(&s.d_acc, sizeof(double) * sg * batch));
     CUDA_OK(cudaMemset(s.d_acc, 0, sizeof(double) * sg * batch));
     CUDA_OK(cudaMalloc(&s.d_dE, sizeof(float) * sg * batch));

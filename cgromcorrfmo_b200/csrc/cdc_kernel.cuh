@@ -1,0 +1,212 @@
+// K2 — the CDC pair kernel (replaces ComputeCDC_v1, reference src/grom2atomFMO.cpp:625-739), sm_100a.
+//
+// Work item = (frame, tile of kTileAtoms consecutive atoms, chunk of sites).  Persistent CTAs stride over the items;
+// the site loop is cut into chunks so that a launch has many more items than resident CTAs (small tail) and a
+// single frame still fills the machine.  Each thread keeps
+// E = 8 consecutive atoms in registers as 4 packed pairs (loaded as 64-bit values straight from the blocked SoA layout
+// K1 writes); the frame's site block (S x P entries of 16 B: -x,-y,-z,dQ) arrives in shared memory by one bulk TMA copy,
+// double-buffered so the next item's block lands while this one is computed.  For every site s and site atom c, all
+// threads read the same 16 B (one broadcast LDS.128) and evaluate 8 pairs:
+//   dx = x - xc (FADD2 x3), r2 = dx*dx + dy*dy + dz*dz (FMUL2 + 2 FFMA2), rinv = MUFU.RSQ (x2), V += dQ*rinv (FFMA2)
+// i.e. 7 packed FP32 instructions + 2 MUFU per 2 pairs: the XU pipe (16 rsqrt/clk/SM) is the ceiling, the FP32 pipe
+// runs at 7/8 of it.  V_s(a) = sum_c dQ_c / r_ac is FP32 over <= P terms; everything after that is FP64:
+// w = V * (33.2f * q_a), summed per residue group (atoms of a group are consecutive in the file, so a thread's 8 atoms
+// form a few runs at most), warp-shuffle reduced when the whole warp sits in one group, added to the FP64 bin
+// acc[frame][site][column].
+//
+// Template knobs (chosen by measurement, scripts/k2_variants.cu):
+//   kMinBlocks  CTAs per SM promised to ptxas (register cap 65536 / (256 * kMinBlocks))
+//   kUnroll     unroll factor of the site-atom loop
+//   kPipelined  software-pipelined loop: the rsqrt of iteration c-1 is issued while r2 of iteration c is formed
+#pragma once
+#include "kernels.cuh"
+#include "ptx_helpers.cuh"
+
+namespace cgc {
+
+constexpr int kCdcMinBlocks = 2;
+constexpr int kCdcUnroll = 4;
+constexpr bool kCdcPipelined = true;
+
+// sa = (-xc, -yc, -zc, dQ) of one site atom.  pack2(v, v) is folded by ptxas into the scalar-broadcast operand form of
+// the packed instruction (SASS "FADD2 R, R.F32x2.HI_LO, R.F32"), so the broadcast costs no instruction.
+__device__ __forceinline__ f32x2 pair_r2(f32x2 x, f32x2 y, f32x2 z, const float4& sa) {
+  const f32x2 dx = fadd2(x, pack2(sa.x, sa.x)), dy = fadd2(y, pack2(sa.y, sa.y)), dz = fadd2(z, pack2(sa.z, sa.z));
+  f32x2 r2 = fmul2(dx, dx);
+  r2 = ffma2(dy, dy, r2);
+  return ffma2(dz, dz, r2);
+}
+
+__device__ __forceinline__ f32x2 rsqrt2(f32x2 r2) {
+  float a, b;
+  unpack2(r2, a, b);
+  return pack2(rsqrt_approx(a), rsqrt_approx(b));
+}
+
+template <int kMinBlocks, int kUnroll, bool kPipelined, int kDebug = 0>
+__global__ void __launch_bounds__(kTileThreads, kMinBlocks)
+cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, const double* __restrict__ kq_all,
+           const int32_t* __restrict__ col_all, double* __restrict__ acc, int n_pad, int tiles_per_frame, int n_items,
+           int S, int P, int G, int n_chunks, int chunk_sites) {
+  extern __shared__ __align__(128) unsigned char sm_raw[];
+  __shared__ __align__(8) uint64_t bars[2];
+  const uint32_t buf_bytes = (uint32_t)chunk_sites * P * 16u;   // one buffer: the dQ atoms of up to chunk_sites sites
+  // item -> (frame, tile, chunk of sites); the chunk index varies fastest so that neighbouring CTAs share atoms in L2
+  auto decode_item = [&](int it, int& f, int& tile, int& s0, int& ns) {
+    const int ft = it / n_chunks;
+    const int ch = it - ft * n_chunks;
+    f = ft / tiles_per_frame;
+    tile = ft - f * tiles_per_frame;
+    s0 = ch * chunk_sites;
+    ns = min(chunk_sites, S - s0);
+  };
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  int item = blockIdx.x;
+  if (item >= n_items) return;
+  if (threadIdx.x == 0) {
+    int f0, t0, s0, ns;
+    decode_item(item, f0, t0, s0, ns);
+    mbar_expect_tx(&bars[0], (uint32_t)ns * P * 16u);
+    tma_bulk_g2s(sm_raw, sites + ((size_t)f0 * S + s0) * P, (uint32_t)ns * P * 16u, &bars[0]);
+  }
+  uint32_t phase_bits = 0;  // bit b = parity to wait for on bars[b]
+  int cur = 0;
+  const int lane = threadIdx.x & 31;
+
+  for (; item < n_items; item += gridDim.x) {
+    int f, tile, s_begin, n_s;
+    decode_item(item, f, tile, s_begin, n_s);
+    const int next = item + gridDim.x;
+    if (threadIdx.x == 0 && next < n_items) {
+      // buf[cur^1] was last read in the previous iteration; the __syncthreads at its end orders that
+      int fn, tn, sn, nn;
+      decode_item(next, fn, tn, sn, nn);
+      mbar_expect_tx(&bars[cur ^ 1], (uint32_t)nn * P * 16u);
+      tma_bulk_g2s(sm_raw + (cur ^ 1) * buf_bytes, sites + ((size_t)fn * S + sn) * P, (uint32_t)nn * P * 16u, &bars[cur ^ 1]);
+    }
+
+    // ---- this thread's 8 atoms
+    const int a0 = tile * kTileAtoms + threadIdx.x * kAtomsPerThread;
+    const ulonglong2* ap = reinterpret_cast<const ulonglong2*>(xyz8 + ((size_t)f * n_pad + a0) * 3);
+    f32x2 X[4], Y[4], Z[4];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const ulonglong2 vx = __ldg(ap + j), vy = __ldg(ap + 2 + j), vz = __ldg(ap + 4 + j);
+      X[2 * j] = vx.x; X[2 * j + 1] = vx.y;
+      Y[2 * j] = vy.x; Y[2 * j + 1] = vy.y;
+      Z[2 * j] = vz.x; Z[2 * j + 1] = vz.y;
+    }
+    int cols[8];
+    {
+      const int4 c0 = __ldg(reinterpret_cast<const int4*>(col_all + a0));
+      const int4 c1 = __ldg(reinterpret_cast<const int4*>(col_all + a0 + 4));
+      cols[0] = c0.x; cols[1] = c0.y; cols[2] = c0.z; cols[3] = c0.w;
+      cols[4] = c1.x; cols[5] = c1.y; cols[6] = c1.z; cols[7] = c1.w;
+    }
+    double kq[8];
+    {
+      const double2* kp = reinterpret_cast<const double2*>(kq_all + a0);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double2 v = __ldg(kp + j);
+        kq[2 * j] = v.x;
+        kq[2 * j + 1] = v.y;
+      }
+    }
+    bool same = true;
+#pragma unroll
+    for (int e = 1; e < 8; e++) same = same && (cols[e] == cols[0]);
+    const int c_lane0 = __shfl_sync(0xffffffffu, cols[0], 0);
+    // whole warp inside one environment group (columns < 0 are padding; chromophore columns never fill a warp)
+    const bool warp_uniform = __all_sync(0xffffffffu, same && cols[0] == c_lane0) && c_lane0 >= 0;
+
+    mbar_wait(&bars[cur], (phase_bits >> cur) & 1u);
+    phase_bits ^= 1u << cur;
+    const float4* sblk = reinterpret_cast<const float4*>(sm_raw + cur * buf_bytes);
+    double* acc_frame = acc + (size_t)f * S * G;
+
+    for (int sl = 0; sl < n_s; sl++) {
+      const int s = s_begin + sl;
+      f32x2 V[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) V[j] = 0ull;
+      const float4* sp = sblk + (size_t)sl * P;
+      if constexpr (!kPipelined) {
+#pragma unroll kUnroll
+        for (int c = 0; c < P; c++) {
+          const float4 sa = sp[c];  // one broadcast LDS.128: (-xc, -yc, -zc, dQ)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const f32x2 ri = rsqrt2(pair_r2(X[j], Y[j], Z[j], sa));
+            V[j] = ffma2(pack2(sa.w, sa.w), ri, V[j]);
+          }
+        }
+      } else {
+        f32x2 R[4];
+        float dq_prev;
+        {
+          const float4 sa = sp[0];
+#pragma unroll
+          for (int j = 0; j < 4; j++) R[j] = pair_r2(X[j], Y[j], Z[j], sa);
+          dq_prev = sa.w;
+        }
+#pragma unroll kUnroll
+        for (int c = 1; c < P; c++) {
+          const float4 sa = sp[c];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const f32x2 ri = rsqrt2(R[j]);                  // iteration c-1
+            R[j] = pair_r2(X[j], Y[j], Z[j], sa);           // iteration c, independent of ri
+            V[j] = ffma2(pack2(dq_prev, dq_prev), ri, V[j]);
+          }
+          dq_prev = sa.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) V[j] = ffma2(pack2(dq_prev, dq_prev), rsqrt2(R[j]), V[j]);
+      }
+      float Vf[8];
+#pragma unroll
+      for (int j = 0; j < 4; j++) unpack2(V[j], Vf[2 * j], Vf[2 * j + 1]);
+
+      // ---- FP64 from here: w_e = V_e * 33.2f * q_e, binned per column
+      double* acc_row = acc_frame + (size_t)s * G;
+      if constexpr (kDebug == 1) {  // measurement only: no binning
+        float t = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; e++) t += Vf[e];
+        if (t == 123.456f) atomicAdd(acc_row, (double)t);
+      } else if (warp_uniform) {
+        double t = 0.0;
+#pragma unroll
+        for (int e = 0; e < 8; e++) t += (double)Vf[e] * kq[e];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) atomicAdd(acc_row + c_lane0, t);
+      } else {
+        double run = 0.0;
+        int cc = cols[0];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          if (cols[e] != cc) {
+            if (cc >= 0 && cc != s) atomicAdd(acc_row + cc, run);
+            cc = cols[e];
+            run = 0.0;
+          }
+          run += (double)Vf[e] * kq[e];
+        }
+        if (cc >= 0 && cc != s) atomicAdd(acc_row + cc, run);
+      }
+    }
+    __syncthreads();  // everyone is done with buf[cur] before it is refilled
+    cur ^= 1;
+  }
+}
+
+}  // namespace cgc

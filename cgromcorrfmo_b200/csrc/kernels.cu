@@ -9,73 +9,12 @@
 //   K3  cov_* kernels     n, sum(x-c), sum (x-c)(x-c)^T per site on FP64 tensor cores (DMMA)
 //                         (replaces the Correlate block, reference src/FMOparse.cpp:168-178, 188-206)
 #include "kernels.cuh"
+#include "ptx_helpers.cuh"
+#include "cdc_kernel.cuh"
 
 #include <cstdio>
 
 namespace cgc {
-
-// ---------------------------------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + 1-D bulk TMA (cp.async.bulk -> SASS UBLKCP), packed FP32 (FFMA2/FADD2/FMUL2), MUFU.RSQ
-// ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_addr(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-// global -> shared bulk copy through the TMA unit; bytes % 16 == 0, both addresses 16-byte aligned
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_addr(dst)),
-               "l"(src), "r"(bytes), "r"(smem_addr(bar))
-               : "memory");
-}
-
-// Packed FP32 pairs live in 64-bit registers for their whole life (so ptxas never re-packs them with MOVs).
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ float rsqrt_approx(float x) {
-  float y;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 // The neutral padding entry of a site block: dQ = 0 at a far-away point (stored negated), so it adds exactly 0.
 #define CGC_PAD_NEG_COORD 1.0e6f
@@ -153,11 +92,8 @@ decode_kernel(const char* __restrict__ text, int64_t text_bytes, const int64_t* 
     if (err) atomicOr(err_flags, err);
     const int sl = slot[a];
     if (sl >= 0) {
-      // site block entry, laid out for the packed pair loop: (-x,-x,-y,-y) (-z,-z,dq,dq)
-      const float dq = slot_dq[sl];
-      float4* dst = sites + (size_t)f * sites_stride + (size_t)sl * 2;
-      dst[0] = make_float4(-out.x, -out.x, -out.y, -out.y);
-      dst[1] = make_float4(-out.z, -out.z, dq, dq);
+      // site block entry for the pair loop: negated coordinates (so dx = x + (-xc) is one FADD2) and dQ
+      sites[(size_t)f * sites_stride + sl] = make_float4(-out.x, -out.y, -out.z, slot_dq[sl]);
     }
   } else {
     out = make_float3(0.f, 0.f, 0.f);  // tile padding: its kq is 0 and its column is -1
@@ -189,8 +125,7 @@ void launch_unblock(const DeviceSystem& sys, const float* xyz8, float* xyz, int 
 __global__ void init_sites_kernel(float4* sites, int64_t n_entries) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_entries) return;
-  sites[2 * i + 0] = make_float4(CGC_PAD_NEG_COORD, CGC_PAD_NEG_COORD, CGC_PAD_NEG_COORD, CGC_PAD_NEG_COORD);
-  sites[2 * i + 1] = make_float4(CGC_PAD_NEG_COORD, CGC_PAD_NEG_COORD, 0.f, 0.f);
+  sites[i] = make_float4(CGC_PAD_NEG_COORD, CGC_PAD_NEG_COORD, CGC_PAD_NEG_COORD, 0.f);
 }
 
 void launch_init_sites(const DeviceSystem& sys, float4* sites, int n_frames, cudaStream_t st) {
@@ -210,162 +145,51 @@ void launch_decode(const DeviceSystem& sys, const char* text, int64_t text_bytes
   }
   decode_kernel<<<grid, kDecodeThreads, smem, st>>>(text, text_bytes, atoms_off, sys.n_atoms, sys.n_pad, sys.line_bytes,
                                                     sys.x_col, sys.field_w, sys.ndec, sys.slot, sys.slot_dq,
-                                                    sys.n_sites * sys.site_cap * 2, xyz8, sites, err_flags);
+                                                    sys.n_sites * sys.site_cap, xyz8, sites, err_flags);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// K2  CDC pair kernel
+// K2  CDC pair kernel: see cdc_kernel.cuh
 // ---------------------------------------------------------------------------------------------------------------------
-// Work item = (frame, tile of kTileAtoms consecutive atoms).  Persistent CTAs stride over the items.  Each thread keeps
-// E = 8 consecutive atoms in registers as 4 packed pairs; the frame's site block (S x P entries of 32 B) arrives in
-// shared memory by one bulk TMA copy, double-buffered so the next item's block lands while this one is computed.
-// For every site s and site atom c, all threads read the same 32 B (broadcast LDS.128 x2) and evaluate 8 pairs:
-//   dx = x - xc (FADD2 x3), r2 = dx*dx + dy*dy + dz*dz (FMUL2 + 2 FFMA2), rinv = MUFU.RSQ (x2), V += dQ*rinv (FFMA2)
-// i.e. 7 packed FP32 instructions + 2 MUFU per 2 pairs.  V_s(a) = sum_c dQ_c / r_ac is FP32 over <= P terms; everything
-// after that is FP64: w = V * (33.2f * q_a), summed per residue group (atoms of a group are consecutive in the file,
-// so a thread's 8 atoms form at most a few runs), warp-shuffle reduced when the whole warp sits in one group, and
-// added to the FP64 bin acc[frame][site][column].
-__global__ void __launch_bounds__(kTileThreads, 2)
-cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, const double* __restrict__ kq_all,
-           const int32_t* __restrict__ col_all, double* __restrict__ acc, int n_pad, int tiles_per_frame, int n_items,
-           int S, int P, int G) {
-  extern __shared__ __align__(128) unsigned char sm_raw[];
-  __shared__ __align__(8) uint64_t bars[2];
-  const uint32_t block_bytes = (uint32_t)S * P * 32u;
-
-  if (threadIdx.x == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_fence_init();
+// Sites per work item: few enough that a launch has >= ~48 items per resident CTA (tail below ~2 %), never fewer than 2
+// sites per item (the per-item prologue — 8 atoms, columns, charges — is amortised over the site loop).
+static int cdc_chunk_sites(const DeviceSystem& sys, int n_frames, int resident_ctas) {
+  const int tiles = sys.n_pad / kTileAtoms;
+  int best = sys.n_sites;
+  for (int cs = sys.n_sites; cs >= 1; cs--) {
+    const int chunks = (sys.n_sites + cs - 1) / cs;
+    best = cs;
+    if ((long long)tiles * n_frames * chunks >= 48LL * resident_ctas) break;
+    if (cs <= 2) break;
   }
-  __syncthreads();
-
-  int item = blockIdx.x;
-  if (item >= n_items) return;
-  if (threadIdx.x == 0) {
-    const int f0 = item / tiles_per_frame;
-    mbar_expect_tx(&bars[0], block_bytes);
-    tma_bulk_g2s(sm_raw, sites + (size_t)f0 * S * P * 2, block_bytes, &bars[0]);
-  }
-  uint32_t phase_bits = 0;  // bit b = parity to wait for on bars[b]
-  int cur = 0;
-  const int lane = threadIdx.x & 31;
-
-  for (; item < n_items; item += gridDim.x) {
-    const int f = item / tiles_per_frame;
-    const int tile = item - f * tiles_per_frame;
-    const int next = item + gridDim.x;
-    if (threadIdx.x == 0 && next < n_items) {
-      // buf[cur^1] was last read two iterations ago; the __syncthreads at the end of the previous one orders that
-      const int fn = next / tiles_per_frame;
-      mbar_expect_tx(&bars[cur ^ 1], block_bytes);
-      tma_bulk_g2s(sm_raw + (cur ^ 1) * block_bytes, sites + (size_t)fn * S * P * 2, block_bytes, &bars[cur ^ 1]);
-    }
-
-    // ---- this thread's 8 atoms
-    const int a0 = tile * kTileAtoms + threadIdx.x * kAtomsPerThread;
-    const ulonglong2* ap = reinterpret_cast<const ulonglong2*>(xyz8 + ((size_t)f * n_pad + a0) * 3);
-    f32x2 X[4], Y[4], Z[4];
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-      const ulonglong2 vx = __ldg(ap + j), vy = __ldg(ap + 2 + j), vz = __ldg(ap + 4 + j);
-      X[2 * j] = vx.x; X[2 * j + 1] = vx.y;
-      Y[2 * j] = vy.x; Y[2 * j + 1] = vy.y;
-      Z[2 * j] = vz.x; Z[2 * j + 1] = vz.y;
-    }
-    int cols[8];
-    {
-      const int4 c0 = __ldg(reinterpret_cast<const int4*>(col_all + a0));
-      const int4 c1 = __ldg(reinterpret_cast<const int4*>(col_all + a0 + 4));
-      cols[0] = c0.x; cols[1] = c0.y; cols[2] = c0.z; cols[3] = c0.w;
-      cols[4] = c1.x; cols[5] = c1.y; cols[6] = c1.z; cols[7] = c1.w;
-    }
-    bool same = true;
-#pragma unroll
-    for (int e = 1; e < 8; e++) same = same && (cols[e] == cols[0]);
-    const int c_lane0 = __shfl_sync(0xffffffffu, cols[0], 0);
-    // whole warp inside one environment group (columns < 0 are padding; chromophore columns never fill a warp)
-    const bool warp_uniform = __all_sync(0xffffffffu, same && cols[0] == c_lane0) && c_lane0 >= 0;
-
-    mbar_wait(&bars[cur], (phase_bits >> cur) & 1u);
-    phase_bits ^= 1u << cur;
-    const ulonglong2* sblk = reinterpret_cast<const ulonglong2*>(sm_raw + cur * block_bytes);
-    double* acc_frame = acc + (size_t)f * S * G;
-
-    for (int s = 0; s < S; s++) {
-      f32x2 V[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) V[j] = 0ull;
-      const ulonglong2* sp = sblk + (size_t)s * P * 2;
-#pragma unroll 2
-      for (int c = 0; c < P; c++) {
-        const ulonglong2 A = sp[2 * c];      // (-x,-x) (-y,-y)
-        const ulonglong2 B = sp[2 * c + 1];  // (-z,-z) (dq,dq)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const f32x2 dx = fadd2(X[j], A.x), dy = fadd2(Y[j], A.y), dz = fadd2(Z[j], B.x);
-          f32x2 r2 = fmul2(dx, dx);
-          r2 = ffma2(dy, dy, r2);
-          r2 = ffma2(dz, dz, r2);
-          float r2a, r2b;
-          unpack2(r2, r2a, r2b);
-          const f32x2 ri = pack2(rsqrt_approx(r2a), rsqrt_approx(r2b));
-          V[j] = ffma2(B.y, ri, V[j]);
-        }
-      }
-      float Vf[8];
-#pragma unroll
-      for (int j = 0; j < 4; j++) unpack2(V[j], Vf[2 * j], Vf[2 * j + 1]);
-      // ---- FP64 from here: w_e = V_e * 33.2f * q_e, binned per column
-      const double* kq = kq_all + a0;
-      double* acc_row = acc_frame + (size_t)s * G;
-      if (warp_uniform) {
-        double t = 0.0;
-#pragma unroll
-        for (int e = 0; e < 8; e++) t += (double)Vf[e] * __ldg(kq + e);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) atomicAdd(acc_row + c_lane0, t);
-      } else {
-        double run = 0.0;
-        int cc = cols[0];
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-          if (cols[e] != cc) {
-            if (cc >= 0 && cc != s) atomicAdd(acc_row + cc, run);
-            cc = cols[e];
-            run = 0.0;
-          }
-          run += (double)Vf[e] * __ldg(kq + e);
-        }
-        if (cc >= 0 && cc != s) atomicAdd(acc_row + cc, run);
-      }
-    }
-    __syncthreads();  // everyone is done with buf[cur] before it is refilled
-    cur ^= 1;
-  }
+  return best;
 }
 
-size_t cdc_smem_bytes(const DeviceSystem& sys) { return (size_t)2 * sys.n_sites * sys.site_cap * 32; }
+size_t cdc_smem_bytes(const DeviceSystem& sys) { return (size_t)2 * sys.n_sites * sys.site_cap * 16; }
 
 void launch_cdc(const DeviceSystem& sys, const float* xyz8, const float4* sites, double* acc, int n_frames,
                 int sm_count, cudaStream_t st) {
   const int tiles = sys.n_pad / kTileAtoms;
-  const int n_items = tiles * n_frames;
-  if (n_items == 0) return;
-  size_t smem = cdc_smem_bytes(sys);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(cdc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
+  if (tiles * n_frames == 0) return;
+  auto kern = cdc_kernel<kCdcMinBlocks, kCdcUnroll, kCdcPipelined>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
   }
-  int per_sm = 2;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cdc_kernel, kTileThreads, smem);
+  int per_sm = kCdcMinBlocks;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, cdc_smem_bytes(sys));
   if (per_sm < 1) per_sm = 1;
+  const int chunk_sites = cdc_chunk_sites(sys, n_frames, sm_count * per_sm);
+  const int n_chunks = (sys.n_sites + chunk_sites - 1) / chunk_sites;
+  const size_t smem = (size_t)2 * chunk_sites * sys.site_cap * 16;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem);
+  if (per_sm < 1) per_sm = 1;
+  const int n_items = tiles * n_frames * n_chunks;
   int grid = sm_count * per_sm;
   if (grid > n_items) grid = n_items;
-  cdc_kernel<<<grid, kTileThreads, smem, st>>>(xyz8, sites, sys.kq, sys.col, acc, sys.n_pad, tiles, n_items, sys.n_sites,
-                                               sys.site_cap, sys.num_tot);
+  kern<<<grid, kTileThreads, smem, st>>>(xyz8, sites, sys.kq, sys.col, acc, sys.n_pad, tiles, n_items, sys.n_sites,
+                                         sys.site_cap, sys.num_tot, n_chunks, chunk_sites);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
