@@ -211,7 +211,7 @@ def run_reference_arm(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from cgromcorrfmo_b200 import capi
+    from cgromcorrfmo_b200 import capi, dist as cdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -265,7 +265,6 @@ def run_ours(args):
         if world > 1:
             dist.broadcast(row0, 0)
         ctx.cov_set_shift_device(row0.data_ptr(), stream)
-        shift_backup = cov[1:1 + S * G].clone()
 
         def step_device():
             ctx.run_device(d_text.data_ptr(), n_text, offs, F, d_dE.data_ptr(), stream)
@@ -273,8 +272,7 @@ def run_ours(args):
 
         def combine():
             if world > 1:
-                dist.all_reduce(cov)                                   # ONE collective: n, sum(x-c), sum (x-c)(x-c)^T
-                cov[1:1 + S * G] = shift_backup                        # the shift block is identical on all ranks
+                cdist.allreduce_partials(cov, S, G)                    # ONE collective: n, sum(x-c), sum (x-c)(x-c)^T
 
         def barrier():
             torch.cuda.synchronize()

@@ -1,0 +1,78 @@
+"""traj2dEcsv as a Python call, one process per GPU (launch with torchrun for more than one):
+
+    python -m cgromcorrfmo_b200.run traj_in topology excited_itp csv_out num_frames [--sites N] [--mtx-compat]
+
+Same five positionals and the same two output files as the reference program (reference README.md:25-31); with R ranks
+every rank streams its frame range, writes csv_out.time.part<r>, and the Correlate sums are combined by one NCCL
+all-reduce before rank 0 writes csv_out.mtx and joins the parts."""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import numpy as np
+
+from . import capi, dist as cdist
+
+
+def traj2dEcsv(traj, top, itp, out, num_frames, sites=0, mtx_compat=False, chunk_frames=0, device=None):
+    import torch
+    import torch.distributed as tdist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0")) if device is None else device
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: the hot path is CUDA-only (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1 and not tdist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    with capi.Context(top, itp, local) as c:
+        c.open(traj)
+        if sites:
+            c.set_option("sites", sites)
+        total = min(int(num_frames), c.frame_count())          # stops cleanly where the reference would overrun
+        first, count = cdist.frame_range(rank, world, total)
+        S, G = c.n_sites, c.num_tot
+        cov = None
+        if c.cov_size():
+            cov = torch.zeros(c.cov_size(), dtype=torch.float64, device="cuda")
+            c.cov_bind(cov.data_ptr())
+        part = out + (".time.part%d" % rank if world > 1 else ".time")
+        capi.write_time(part, np.empty((0, G), np.float32), truncate=True)
+        step = chunk_frames or 4 * int(c.get_option("batch_frames"))
+        done = 0
+        while done < count:
+            n = min(step, count - done)
+            dE, got, rc = c.run(first + done, n)
+            capi.write_time(part, dE, truncate=False)
+            done += got
+            if rc == capi.CGC_EOF:
+                break
+        if world > 1:
+            if cov is not None:
+                cdist.allreduce_partials(cov, S, G)
+            tdist.barrier()
+        if rank == 0:
+            if world > 1:
+                cdist.concat_time_parts(out, world)
+            if cov is not None and total > 0:
+                c.write_mtx(out + ".mtx", compat=mtx_compat)
+        return total
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(prog="cgromcorrfmo_b200.run")
+    for name in ("traj_in", "topology", "excited_itp", "csv_out"):
+        ap.add_argument(name)
+    ap.add_argument("num_frames", type=int)
+    ap.add_argument("--sites", type=int, default=0)
+    ap.add_argument("--mtx-compat", action="store_true")
+    a = ap.parse_args(argv)
+    traj2dEcsv(a.traj_in, a.topology, a.excited_itp, a.csv_out, a.num_frames, a.sites, a.mtx_compat)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
