@@ -43,7 +43,7 @@ __device__ __forceinline__ f32x2 rsqrt2(f32x2 r2) {
   return pack2(rsqrt_approx(a), rsqrt_approx(b));
 }
 
-template <int kMinBlocks, int kUnroll, bool kPipelined, int kDebug = 0>
+template <int kMinBlocks, int kUnroll, bool kPipelined, int kDebug = 0, int kPk = 4>
 __global__ void __launch_bounds__(kTileThreads, kMinBlocks)
 cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, const double* __restrict__ kq_all,
            const int32_t* __restrict__ col_all, double* __restrict__ acc, int n_pad, int tiles_per_frame, int n_items,
@@ -92,26 +92,29 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
       tma_bulk_g2s(sm_raw + (cur ^ 1) * buf_bytes, sites + ((size_t)fn * S + sn) * P, (uint32_t)nn * P * 16u, &bars[cur ^ 1]);
     }
 
-    // ---- this thread's 8 atoms
-    const int a0 = tile * kTileAtoms + threadIdx.x * kAtomsPerThread;
-    const ulonglong2* ap = reinterpret_cast<const ulonglong2*>(xyz8 + ((size_t)f * n_pad + a0) * 3);
-    f32x2 X[4], Y[4], Z[4];
+    // ---- this thread's E = 2*kPk consecutive atoms (kPk/4 blocks of 8)
+    constexpr int E = 2 * kPk;
+    const int a0 = (tile * kTileThreads + threadIdx.x) * E;
+    f32x2 X[kPk], Y[kPk], Z[kPk];
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-      const ulonglong2 vx = __ldg(ap + j), vy = __ldg(ap + 2 + j), vz = __ldg(ap + 4 + j);
-      X[2 * j] = vx.x; X[2 * j + 1] = vx.y;
-      Y[2 * j] = vy.x; Y[2 * j + 1] = vy.y;
-      Z[2 * j] = vz.x; Z[2 * j + 1] = vz.y;
+    for (int b = 0; b < kPk / 4; b++) {
+      const ulonglong2* ap = reinterpret_cast<const ulonglong2*>(xyz8 + ((size_t)f * n_pad + a0 + 8 * b) * 3);
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const ulonglong2 vx = __ldg(ap + j), vy = __ldg(ap + 2 + j), vz = __ldg(ap + 4 + j);
+        X[4 * b + 2 * j] = vx.x; X[4 * b + 2 * j + 1] = vx.y;
+        Y[4 * b + 2 * j] = vy.x; Y[4 * b + 2 * j + 1] = vy.y;
+        Z[4 * b + 2 * j] = vz.x; Z[4 * b + 2 * j + 1] = vz.y;
+      }
     }
-    int cols[8];
-    {
-      const int4 c0 = __ldg(reinterpret_cast<const int4*>(col_all + a0));
-      const int4 c1 = __ldg(reinterpret_cast<const int4*>(col_all + a0 + 4));
-      cols[0] = c0.x; cols[1] = c0.y; cols[2] = c0.z; cols[3] = c0.w;
-      cols[4] = c1.x; cols[5] = c1.y; cols[6] = c1.z; cols[7] = c1.w;
+    int cols[E];
+#pragma unroll
+    for (int b = 0; b < E / 4; b++) {
+      const int4 c0 = __ldg(reinterpret_cast<const int4*>(col_all + a0) + b);
+      cols[4 * b] = c0.x; cols[4 * b + 1] = c0.y; cols[4 * b + 2] = c0.z; cols[4 * b + 3] = c0.w;
     }
-    double kq[8];
-    {
+    double kq[kPk == 4 ? E : 1];
+    if constexpr (kPk == 4) {
       const double2* kp = reinterpret_cast<const double2*>(kq_all + a0);
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -120,9 +123,10 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
         kq[2 * j + 1] = v.y;
       }
     }
+    auto kq_of = [&](int e) -> double { if constexpr (kPk == 4) return kq[e]; else return __ldg(kq_all + a0 + e); };
     bool same = true;
 #pragma unroll
-    for (int e = 1; e < 8; e++) same = same && (cols[e] == cols[0]);
+    for (int e = 1; e < E; e++) same = same && (cols[e] == cols[0]);
     const int c_lane0 = __shfl_sync(0xffffffffu, cols[0], 0);
     // whole warp inside one environment group (columns < 0 are padding; chromophore columns never fill a warp)
     const bool warp_uniform = __all_sync(0xffffffffu, same && cols[0] == c_lane0) && c_lane0 >= 0;
@@ -134,34 +138,34 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
 
     for (int sl = 0; sl < n_s; sl++) {
       const int s = s_begin + sl;
-      f32x2 V[4];
+      f32x2 V[kPk];
 #pragma unroll
-      for (int j = 0; j < 4; j++) V[j] = 0ull;
+      for (int j = 0; j < kPk; j++) V[j] = 0ull;
       const float4* sp = sblk + (size_t)sl * P;
       if constexpr (!kPipelined) {
 #pragma unroll kUnroll
         for (int c = 0; c < P; c++) {
           const float4 sa = sp[c];  // one broadcast LDS.128: (-xc, -yc, -zc, dQ)
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
+          for (int j = 0; j < kPk; j++) {
             const f32x2 ri = rsqrt2(pair_r2(X[j], Y[j], Z[j], sa));
             V[j] = ffma2(pack2(sa.w, sa.w), ri, V[j]);
           }
         }
       } else {
-        f32x2 R[4];
+        f32x2 R[kPk];
         float dq_prev;
         {
           const float4 sa = sp[0];
 #pragma unroll
-          for (int j = 0; j < 4; j++) R[j] = pair_r2(X[j], Y[j], Z[j], sa);
+          for (int j = 0; j < kPk; j++) R[j] = pair_r2(X[j], Y[j], Z[j], sa);
           dq_prev = sa.w;
         }
 #pragma unroll kUnroll
         for (int c = 1; c < P; c++) {
           const float4 sa = sp[c];
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
+          for (int j = 0; j < kPk; j++) {
             const f32x2 ri = rsqrt2(R[j]);                  // iteration c-1
             R[j] = pair_r2(X[j], Y[j], Z[j], sa);           // iteration c, independent of ri
             V[j] = ffma2(pack2(dq_prev, dq_prev), ri, V[j]);
@@ -169,23 +173,23 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
           dq_prev = sa.w;
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) V[j] = ffma2(pack2(dq_prev, dq_prev), rsqrt2(R[j]), V[j]);
+        for (int j = 0; j < kPk; j++) V[j] = ffma2(pack2(dq_prev, dq_prev), rsqrt2(R[j]), V[j]);
       }
-      float Vf[8];
+      float Vf[E];
 #pragma unroll
-      for (int j = 0; j < 4; j++) unpack2(V[j], Vf[2 * j], Vf[2 * j + 1]);
+      for (int j = 0; j < kPk; j++) unpack2(V[j], Vf[2 * j], Vf[2 * j + 1]);
 
       // ---- FP64 from here: w_e = V_e * 33.2f * q_e, binned per column
       double* acc_row = acc_frame + (size_t)s * G;
       if constexpr (kDebug == 1) {  // measurement only: no binning
         float t = 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; e++) t += Vf[e];
+        for (int e = 0; e < E; e++) t += Vf[e];
         if (t == 123.456f) atomicAdd(acc_row, (double)t);
       } else if (warp_uniform) {
         double t = 0.0;
 #pragma unroll
-        for (int e = 0; e < 8; e++) t += (double)Vf[e] * kq[e];
+        for (int e = 0; e < E; e++) t += (double)Vf[e] * kq_of(e);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
         if (lane == 0) atomicAdd(acc_row + c_lane0, t);
@@ -193,13 +197,13 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
         double run = 0.0;
         int cc = cols[0];
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
+        for (int e = 0; e < E; e++) {
           if (cols[e] != cc) {
             if (cc >= 0 && cc != s) atomicAdd(acc_row + cc, run);
             cc = cols[e];
             run = 0.0;
           }
-          run += (double)Vf[e] * kq[e];
+          run += (double)Vf[e] * kq_of(e);
         }
         if (cc >= 0 && cc != s) atomicAdd(acc_row + cc, run);
       }

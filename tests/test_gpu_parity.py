@@ -377,3 +377,64 @@ def test_full_size_properties(capi_mod, torch_cuda):
         merged = np.concatenate([dE2[0][:, :col], (dE2[0][:, col] + dE2[0][:, col + 1])[:, None], dE2[0][:, col + 2:]], axis=1)
         yard = np.abs(dE[0]).max()
         assert np.abs(merged - dE[0]).max() <= 2e-6 * yard
+
+
+def test_more_chromophores_than_groups(tmp_path, oracle_mod, capi_mod):
+    """The reference's outer loop runs over 1..nGroups (reference src/grom2atomFMO.cpp:669), so with nChromo > nGroups
+    the columns of the last chromophores stay 0.  Kept, checked against the oracle."""
+    O, capi = oracle_mod, capi_mod
+    from cgromcorrfmo_b200 import synth
+    s = synth.make_system(3 * 140 + 9, 3, 21, "none")          # one 9-atom residue + 3 BCL
+    traj, top, itp = synth.write_inputs(str(tmp_path), s, 2)
+    ref = O.run(traj, top, itp, 2)
+    assert ref["n_chromo"] == 3 and ref["n_groups"] < 3
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        dE, done, _ = c.run(0, 2)
+    e, z = scaled_err(dE, ref["dE_f64"], ref["scale"])
+    assert e <= DE_TOL and z == 0.0
+    assert np.all(dE[:, :, ref["n_groups"]:3] == 0)
+
+
+def test_zero_frames_and_reopen(small_inputs, capi_mod):
+    capi = capi_mod
+    traj, top, itp, frames = small_inputs("tiny")
+    traj2, top2, itp2, frames2 = small_inputs("nosolv")
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        dE, done, rc = c.run(0, 0)
+        assert rc == capi.CGC_OK and done == 0 and dE.shape[0] == 0
+        a, _, _ = c.run(0, frames)
+        c.open(traj)                                          # re-opening resets the Correlate sums and options
+        b, _, _ = c.run(0, frames)
+        assert np.array_equal(a, b) or np.abs(a - b).max() <= 1e-6 * np.abs(a).max()
+        assert c.cov_partials()[0] == frames
+    with capi.Context(top2, itp2, 0) as c:
+        c.open(traj2)
+        assert c.run(0, 1)[1] == 1
+
+
+def test_wide_coordinate_fields(tmp_path, capi_mod, torch_cuda, small_inputs):
+    """%10.5f coordinates (GROMACS writes them with trjconv -ndec 5): the decoder takes the double-precision division
+    path; still bit-exact with (float)atof."""
+    capi, torch = capi_mod, torch_cuda
+    _, top, itp, _ = small_inputs("tiny")
+    from cgromcorrfmo_b200 import synth
+    names = synth.bcl_atom_names()
+    rng = np.random.default_rng(9)
+    lines = []
+    for i in range(140):
+        x, y, z = (float(np.round(rng.uniform(-99, 999), 5)) for _ in range(3))
+        lines.append("%5d%-5s%5s%5d%10.5f%10.5f%10.5f\n" % (1, "BCL", names[i], i + 1, x, y, z))
+    p = tmp_path / "wide.gro"
+    p.write_text("wide t= 0.0\n  140\n" + "".join(lines) + "   1.0   1.0   1.0\n")
+    with capi.Context(top, itp, 0) as c:
+        c.open(str(p))
+        assert c.layout() == dict(line_bytes=51, x_col=20, field_width=10, decimals=5)
+        d_text, nbytes = _device_text(torch, str(p))
+        xyz = torch.empty((1, 140, 3), dtype=torch.float32, device="cuda")
+        c.decode_device(d_text.data_ptr(), nbytes, [c.frame_atoms_offset(0)], 1, xyz.data_ptr())
+        torch.cuda.synchronize()
+        got = xyz.cpu().numpy().reshape(-1)
+    expect = np.array([np.float32(float(ln[20 + 10 * k: 30 + 10 * k])) for ln in lines for k in range(3)], np.float32)
+    assert np.array_equal(got.view(np.uint32), expect.view(np.uint32))
