@@ -2,22 +2,28 @@
 //
 // Work item = (frame, tile of kTileAtoms consecutive atoms, chunk of sites).  Persistent CTAs stride over the items;
 // the site loop is cut into chunks so that a launch has many more items than resident CTAs (small tail) and a
-// single frame still fills the machine.  Each thread keeps
-// E = 8 consecutive atoms in registers as 4 packed pairs (loaded as 64-bit values straight from the blocked SoA layout
-// K1 writes); the frame's site block (S x P entries of 16 B: -x,-y,-z,dQ) arrives in shared memory by one bulk TMA copy,
-// double-buffered so the next item's block lands while this one is computed.  For every site s and site atom c, all
-// threads read the same 16 B (one broadcast LDS.128) and evaluate 8 pairs:
+// single frame still fills the machine.  Each thread keeps 8 consecutive atoms in registers as 4 packed pairs (loaded
+// as 64-bit values straight from the blocked SoA layout K1 writes); the chunk's site block (sites x P entries of 16 B:
+// -x,-y,-z,dQ) arrives in shared memory by one bulk TMA copy, double-buffered so the next item's block lands while this
+// one is computed.  For every site s and site atom c, all threads read the same 16 B (one broadcast LDS.128) and
+// evaluate 8 pairs:
 //   dx = x - xc (FADD2 x3), r2 = dx*dx + dy*dy + dz*dz (FMUL2 + 2 FFMA2), rinv = MUFU.RSQ (x2), V += dQ*rinv (FFMA2)
 // i.e. 7 packed FP32 instructions + 2 MUFU per 2 pairs: the XU pipe (16 rsqrt/clk/SM) is the ceiling, the FP32 pipe
-// runs at 7/8 of it.  V_s(a) = sum_c dQ_c / r_ac is FP32 over <= P terms; everything after that is FP64:
-// w = V * (33.2f * q_a), summed per residue group (atoms of a group are consecutive in the file, so a thread's 8 atoms
-// form a few runs at most), warp-shuffle reduced when the whole warp sits in one group, added to the FP64 bin
-// acc[frame][site][column].
+// runs at 7/8 of it.  The loop is software-pipelined in three stages (r2 of atom c, rsqrt of atom c-1, accumulate
+// atom c-2) so that ptxas can spread the MUFUs between the packed FP32 instructions.
+// V_s(a) = sum_c dQ_c / r_ac is FP32 over <= P terms; everything after that is FP64: w = V * (33.2f * q_a), summed per
+// residue group.  Atoms of a group are consecutive in the file, so a thread's 8 atoms form a few runs at most:
+//   * warp entirely inside one environment group (the solvent): each lane parks its FP64 partial in shared memory and
+//     moves on; the 32 lane values of every (warp, site) are added after the item's site loop (no shuffle tree, and no
+//     dependent chain, in the site loop);
+//   * otherwise: in-thread runs, one fire-and-forget atomicAdd(double) per run (the own-site column is skipped here,
+//     reference src/grom2atomFMO.cpp:674).
 //
-// Template knobs (chosen by measurement, scripts/k2_variants.cu):
+// Template knobs (chosen by measurement, scripts/k2_variants.cu; logs under profiles/):
 //   kMinBlocks  CTAs per SM promised to ptxas (register cap 65536 / (256 * kMinBlocks))
 //   kUnroll     unroll factor of the site-atom loop
-//   kPipelined  software-pipelined loop: the rsqrt of iteration c-1 is issued while r2 of iteration c is formed
+//   kStages     2 or 3 software-pipeline stages
+//   kFlags      measurement only: bit 0 = skip the epilogue, bit 1 = warp-shuffle tree instead of the deferred reduction
 #pragma once
 #include "kernels.cuh"
 #include "ptx_helpers.cuh"
@@ -25,8 +31,10 @@
 namespace cgc {
 
 constexpr int kCdcMinBlocks = 2;
-constexpr int kCdcUnroll = 4;
-constexpr bool kCdcPipelined = true;
+constexpr int kCdcUnroll = 7;
+constexpr int kCdcStages = 3;
+constexpr int kCdcMaxChunkSites = 8;   // bounds the shared memory of the deferred reduction
+constexpr int kCdcWarps = kTileThreads / 32;
 
 // sa = (-xc, -yc, -zc, dQ) of one site atom.  pack2(v, v) is folded by ptxas into the scalar-broadcast operand form of
 // the packed instruction (SASS "FADD2 R, R.F32x2.HI_LO, R.F32"), so the broadcast costs no instruction.
@@ -43,7 +51,19 @@ __device__ __forceinline__ f32x2 rsqrt2(f32x2 r2) {
   return pack2(rsqrt_approx(a), rsqrt_approx(b));
 }
 
-template <int kMinBlocks, int kUnroll, bool kPipelined, int kDebug = 0, int kPk = 4>
+// dynamic shared memory of one CTA: two site-block buffers + two reduction buffers + per-warp columns
+__host__ __device__ inline int cdc_red_stride(int chunk_sites) { return kCdcWarps * chunk_sites + 1; }
+__host__ __device__ inline size_t cdc_smem_layout(int chunk_sites, int P, size_t* red_off, size_t* wcol_off) {
+  size_t off = (size_t)2 * chunk_sites * P * 16;
+  off = (off + 15) & ~(size_t)15;
+  if (red_off) *red_off = off;
+  off += (size_t)2 * 32 * cdc_red_stride(chunk_sites) * sizeof(double);
+  if (wcol_off) *wcol_off = off;
+  off += (size_t)2 * kCdcWarps * sizeof(int);
+  return off;
+}
+
+template <int kMinBlocks, int kUnroll, int kStages, int kFlags = 0>
 __global__ void __launch_bounds__(kTileThreads, kMinBlocks)
 cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, const double* __restrict__ kq_all,
            const int32_t* __restrict__ col_all, double* __restrict__ acc, int n_pad, int tiles_per_frame, int n_items,
@@ -51,6 +71,11 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
   extern __shared__ __align__(128) unsigned char sm_raw[];
   __shared__ __align__(8) uint64_t bars[2];
   const uint32_t buf_bytes = (uint32_t)chunk_sites * P * 16u;   // one buffer: the dQ atoms of up to chunk_sites sites
+  size_t red_off, wcol_off;
+  cdc_smem_layout(chunk_sites, P, &red_off, &wcol_off);
+  double* red = reinterpret_cast<double*>(sm_raw + red_off);     // [2][32 lanes][red_stride]
+  int* wcol = reinterpret_cast<int*>(sm_raw + wcol_off);         // [2][warps]: column of a single-group warp, else -1
+  const int red_stride = cdc_red_stride(chunk_sites);
   // item -> (frame, tile, chunk of sites); the chunk index varies fastest so that neighbouring CTAs share atoms in L2
   auto decode_item = [&](int it, int& f, int& tile, int& s0, int& ns) {
     const int ft = it / n_chunks;
@@ -79,6 +104,7 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
   uint32_t phase_bits = 0;  // bit b = parity to wait for on bars[b]
   int cur = 0;
   const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
 
   for (; item < n_items; item += gridDim.x) {
     int f, tile, s_begin, n_s;
@@ -92,29 +118,28 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
       tma_bulk_g2s(sm_raw + (cur ^ 1) * buf_bytes, sites + ((size_t)fn * S + sn) * P, (uint32_t)nn * P * 16u, &bars[cur ^ 1]);
     }
 
-    // ---- this thread's E = 2*kPk consecutive atoms (kPk/4 blocks of 8)
-    constexpr int E = 2 * kPk;
-    const int a0 = (tile * kTileThreads + threadIdx.x) * E;
-    f32x2 X[kPk], Y[kPk], Z[kPk];
-#pragma unroll
-    for (int b = 0; b < kPk / 4; b++) {
-      const ulonglong2* ap = reinterpret_cast<const ulonglong2*>(xyz8 + ((size_t)f * n_pad + a0 + 8 * b) * 3);
+    // ---- this thread's 8 consecutive atoms (one block of the xyz8 layout)
+    const int a0 = tile * kTileAtoms + threadIdx.x * kAtomsPerThread;
+    f32x2 X[4], Y[4], Z[4];
+    {
+      const ulonglong2* ap = reinterpret_cast<const ulonglong2*>(xyz8 + ((size_t)f * n_pad + a0) * 3);
 #pragma unroll
       for (int j = 0; j < 2; j++) {
         const ulonglong2 vx = __ldg(ap + j), vy = __ldg(ap + 2 + j), vz = __ldg(ap + 4 + j);
-        X[4 * b + 2 * j] = vx.x; X[4 * b + 2 * j + 1] = vx.y;
-        Y[4 * b + 2 * j] = vy.x; Y[4 * b + 2 * j + 1] = vy.y;
-        Z[4 * b + 2 * j] = vz.x; Z[4 * b + 2 * j + 1] = vz.y;
+        X[2 * j] = vx.x; X[2 * j + 1] = vx.y;
+        Y[2 * j] = vy.x; Y[2 * j + 1] = vy.y;
+        Z[2 * j] = vz.x; Z[2 * j + 1] = vz.y;
       }
     }
-    int cols[E];
-#pragma unroll
-    for (int b = 0; b < E / 4; b++) {
-      const int4 c0 = __ldg(reinterpret_cast<const int4*>(col_all + a0) + b);
-      cols[4 * b] = c0.x; cols[4 * b + 1] = c0.y; cols[4 * b + 2] = c0.z; cols[4 * b + 3] = c0.w;
+    int cols[8];
+    {
+      const int4 c0 = __ldg(reinterpret_cast<const int4*>(col_all + a0));
+      const int4 c1 = __ldg(reinterpret_cast<const int4*>(col_all + a0 + 4));
+      cols[0] = c0.x; cols[1] = c0.y; cols[2] = c0.z; cols[3] = c0.w;
+      cols[4] = c1.x; cols[5] = c1.y; cols[6] = c1.z; cols[7] = c1.w;
     }
-    double kq[kPk == 4 ? E : 1];
-    if constexpr (kPk == 4) {
+    double kq[8];
+    {
       const double2* kp = reinterpret_cast<const double2*>(kq_all + a0);
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -123,13 +148,14 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
         kq[2 * j + 1] = v.y;
       }
     }
-    auto kq_of = [&](int e) -> double { if constexpr (kPk == 4) return kq[e]; else return __ldg(kq_all + a0 + e); };
     bool same = true;
 #pragma unroll
-    for (int e = 1; e < E; e++) same = same && (cols[e] == cols[0]);
+    for (int e = 1; e < 8; e++) same = same && (cols[e] == cols[0]);
     const int c_lane0 = __shfl_sync(0xffffffffu, cols[0], 0);
     // whole warp inside one environment group (columns < 0 are padding; chromophore columns never fill a warp)
     const bool warp_uniform = __all_sync(0xffffffffu, same && cols[0] == c_lane0) && c_lane0 >= 0;
+    double* red_cur = red + (size_t)cur * 32 * red_stride;
+    if (lane == 0) wcol[cur * kCdcWarps + warp] = warp_uniform ? c_lane0 : -1;
 
     mbar_wait(&bars[cur], (phase_bits >> cur) & 1u);
     phase_bits ^= 1u << cur;
@@ -138,77 +164,129 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
 
     for (int sl = 0; sl < n_s; sl++) {
       const int s = s_begin + sl;
-      f32x2 V[kPk];
+      f32x2 V[4];
 #pragma unroll
-      for (int j = 0; j < kPk; j++) V[j] = 0ull;
+      for (int j = 0; j < 4; j++) V[j] = 0ull;
       const float4* sp = sblk + (size_t)sl * P;
-      if constexpr (!kPipelined) {
+      if constexpr (kStages == 3) {
+        // three stages: r2 of atom c, rsqrt of atom c-1, accumulate atom c-2   (P >= 2; pads have dQ = 0)
+        f32x2 R[4], RI[4];
+        float dq1, dq2;
+        {
+          const float4 s0 = sp[0], s1 = sp[P > 1 ? 1 : 0];
+#pragma unroll
+          for (int j = 0; j < 4; j++) RI[j] = rsqrt2(pair_r2(X[j], Y[j], Z[j], s0));
+#pragma unroll
+          for (int j = 0; j < 4; j++) R[j] = pair_r2(X[j], Y[j], Z[j], s1);
+          dq2 = s0.w;
+          dq1 = P > 1 ? s1.w : 0.f;
+        }
 #pragma unroll kUnroll
-        for (int c = 0; c < P; c++) {
+        for (int c = 2; c < P; c++) {
           const float4 sa = sp[c];  // one broadcast LDS.128: (-xc, -yc, -zc, dQ)
 #pragma unroll
-          for (int j = 0; j < kPk; j++) {
-            const f32x2 ri = rsqrt2(pair_r2(X[j], Y[j], Z[j], sa));
-            V[j] = ffma2(pack2(sa.w, sa.w), ri, V[j]);
+          for (int j = 0; j < 4; j++) {
+            V[j] = ffma2(pack2(dq2, dq2), RI[j], V[j]);      // atom c-2
+            RI[j] = rsqrt2(R[j]);                            // atom c-1
+            R[j] = pair_r2(X[j], Y[j], Z[j], sa);            // atom c
           }
+          dq2 = dq1;
+          dq1 = sa.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          V[j] = ffma2(pack2(dq2, dq2), RI[j], V[j]);
+          V[j] = ffma2(pack2(dq1, dq1), rsqrt2(R[j]), V[j]);
         }
       } else {
-        f32x2 R[kPk];
+        f32x2 R[4];
         float dq_prev;
         {
           const float4 sa = sp[0];
 #pragma unroll
-          for (int j = 0; j < kPk; j++) R[j] = pair_r2(X[j], Y[j], Z[j], sa);
+          for (int j = 0; j < 4; j++) R[j] = pair_r2(X[j], Y[j], Z[j], sa);
           dq_prev = sa.w;
         }
 #pragma unroll kUnroll
         for (int c = 1; c < P; c++) {
           const float4 sa = sp[c];
 #pragma unroll
-          for (int j = 0; j < kPk; j++) {
-            const f32x2 ri = rsqrt2(R[j]);                  // iteration c-1
-            R[j] = pair_r2(X[j], Y[j], Z[j], sa);           // iteration c, independent of ri
+          for (int j = 0; j < 4; j++) {
+            const f32x2 ri = rsqrt2(R[j]);                  // atom c-1
+            R[j] = pair_r2(X[j], Y[j], Z[j], sa);           // atom c, independent of ri
             V[j] = ffma2(pack2(dq_prev, dq_prev), ri, V[j]);
           }
           dq_prev = sa.w;
         }
 #pragma unroll
-        for (int j = 0; j < kPk; j++) V[j] = ffma2(pack2(dq_prev, dq_prev), rsqrt2(R[j]), V[j]);
+        for (int j = 0; j < 4; j++) V[j] = ffma2(pack2(dq_prev, dq_prev), rsqrt2(R[j]), V[j]);
       }
-      float Vf[E];
+      float Vf[8];
 #pragma unroll
-      for (int j = 0; j < kPk; j++) unpack2(V[j], Vf[2 * j], Vf[2 * j + 1]);
+      for (int j = 0; j < 4; j++) unpack2(V[j], Vf[2 * j], Vf[2 * j + 1]);
 
       // ---- FP64 from here: w_e = V_e * 33.2f * q_e, binned per column
       double* acc_row = acc_frame + (size_t)s * G;
-      if constexpr (kDebug == 1) {  // measurement only: no binning
+      if constexpr ((kFlags & 1) != 0) {  // measurement only: no binning
         float t = 0.f;
 #pragma unroll
-        for (int e = 0; e < E; e++) t += Vf[e];
+        for (int e = 0; e < 8; e++) t += Vf[e];
         if (t == 123.456f) atomicAdd(acc_row, (double)t);
       } else if (warp_uniform) {
-        double t = 0.0;
+        // two independent chains of four
+        double t0 = (double)Vf[0] * kq[0], t1 = (double)Vf[1] * kq[1];
 #pragma unroll
-        for (int e = 0; e < E; e++) t += (double)Vf[e] * kq_of(e);
+        for (int e = 2; e < 8; e += 2) {
+          t0 += (double)Vf[e] * kq[e];
+          t1 += (double)Vf[e + 1] * kq[e + 1];
+        }
+        double t = t0 + t1;
+        if constexpr ((kFlags & 2) != 0) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) atomicAdd(acc_row + c_lane0, t);
+          for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (lane == 0) atomicAdd(acc_row + c_lane0, t);
+        } else {
+          red_cur[lane * red_stride + warp * chunk_sites + sl] = t;   // summed over lanes after the site loop
+        }
       } else {
         double run = 0.0;
         int cc = cols[0];
 #pragma unroll
-        for (int e = 0; e < E; e++) {
+        for (int e = 0; e < 8; e++) {
           if (cols[e] != cc) {
             if (cc >= 0 && cc != s) atomicAdd(acc_row + cc, run);
             cc = cols[e];
             run = 0.0;
           }
-          run += (double)Vf[e] * kq_of(e);
+          run += (double)Vf[e] * kq[e];
         }
         if (cc >= 0 && cc != s) atomicAdd(acc_row + cc, run);
       }
     }
-    __syncthreads();  // everyone is done with buf[cur] before it is refilled
+    __syncthreads();  // everyone is done with buf[cur]; all lane partials of this item are in red[cur]
+    if constexpr ((kFlags & 3) == 0) {
+      // deferred lane reduction: 4 threads per (warp, site) row, 8 lane values each, then two shuffle steps.
+      // red[cur] is rewritten two items from now, after the next __syncthreads — which every thread reaches only after
+      // it has finished this pass.
+      const int rows = kCdcWarps * chunk_sites;
+      for (int task = threadIdx.x; task < ((4 * rows + 31) & ~31); task += kTileThreads) {
+        const int r = task >> 2, q = task & 3;
+        const int w = r / chunk_sites, sl = r - w * chunk_sites;
+        double t = 0.0;
+        int c = -1;
+        if (r < rows && sl < n_s) {
+          c = wcol[cur * kCdcWarps + w];
+          if (c >= 0) {
+            const double* p = red_cur + (size_t)(q * 8) * red_stride + r;
+#pragma unroll
+            for (int l = 0; l < 8; l++) t += p[(size_t)l * red_stride];
+          }
+        }
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        if (q == 0 && c >= 0) atomicAdd(acc_frame + (size_t)(s_begin + sl) * G + c, t);
+      }
+    }
     cur ^= 1;
   }
 }

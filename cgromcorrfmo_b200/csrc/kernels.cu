@@ -12,6 +12,7 @@
 #include "ptx_helpers.cuh"
 #include "cdc_kernel.cuh"
 
+#include <algorithm>
 #include <cstdio>
 
 namespace cgc {
@@ -152,11 +153,12 @@ void launch_decode(const DeviceSystem& sys, const char* text, int64_t text_bytes
 // K2  CDC pair kernel: see cdc_kernel.cuh
 // ---------------------------------------------------------------------------------------------------------------------
 // Sites per work item: few enough that a launch has >= ~48 items per resident CTA (tail below ~2 %), never fewer than 2
-// sites per item (the per-item prologue — 8 atoms, columns, charges — is amortised over the site loop).
+// sites per item (the per-item prologue — 8 atoms, columns, charges — is amortised over the site loop), never more than
+// kCdcMaxChunkSites (shared memory of the deferred lane reduction).
 static int cdc_chunk_sites(const DeviceSystem& sys, int n_frames, int resident_ctas) {
   const int tiles = sys.n_pad / kTileAtoms;
-  int best = sys.n_sites;
-  for (int cs = sys.n_sites; cs >= 1; cs--) {
+  int best = std::min(sys.n_sites, kCdcMaxChunkSites);
+  for (int cs = best; cs >= 1; cs--) {
     const int chunks = (sys.n_sites + cs - 1) / cs;
     best = cs;
     if ((long long)tiles * n_frames * chunks >= 48LL * resident_ctas) break;
@@ -165,13 +167,15 @@ static int cdc_chunk_sites(const DeviceSystem& sys, int n_frames, int resident_c
   return best;
 }
 
-size_t cdc_smem_bytes(const DeviceSystem& sys) { return (size_t)2 * sys.n_sites * sys.site_cap * 16; }
+size_t cdc_smem_bytes(const DeviceSystem& sys) {
+  return cdc_smem_layout(std::min(sys.n_sites, kCdcMaxChunkSites), sys.site_cap, nullptr, nullptr);
+}
 
 void launch_cdc(const DeviceSystem& sys, const float* xyz8, const float4* sites, double* acc, int n_frames,
                 int sm_count, cudaStream_t st) {
   const int tiles = sys.n_pad / kTileAtoms;
   if (tiles * n_frames == 0) return;
-  auto kern = cdc_kernel<kCdcMinBlocks, kCdcUnroll, kCdcPipelined>;
+  auto kern = cdc_kernel<kCdcMinBlocks, kCdcUnroll, kCdcStages>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -182,7 +186,7 @@ void launch_cdc(const DeviceSystem& sys, const float* xyz8, const float4* sites,
   if (per_sm < 1) per_sm = 1;
   const int chunk_sites = cdc_chunk_sites(sys, n_frames, sm_count * per_sm);
   const int n_chunks = (sys.n_sites + chunk_sites - 1) / chunk_sites;
-  const size_t smem = (size_t)2 * chunk_sites * sys.site_cap * 16;
+  const size_t smem = cdc_smem_layout(chunk_sites, sys.site_cap, nullptr, nullptr);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem);
   if (per_sm < 1) per_sm = 1;
   const int n_items = tiles * n_frames * n_chunks;

@@ -15,16 +15,16 @@ struct Data {
   float* xyz8; float4* sites; double* kq; int* col; double* acc;
 };
 
-template <int MB, int UN, bool SW, int DBG = 0, int PK = 4>
+template <int MB, int UN, int ST, int FL = 0>
 double run(const Data& d, const char* name, int sm_count, double* checksum, int chunk_sites = 24) {
-  auto kern = cdc_kernel<MB, UN, SW, DBG, PK>;
-  size_t smem = (size_t)2 * chunk_sites * d.P * 16;
+  auto kern = cdc_kernel<MB, UN, ST, FL>;
+  size_t smem = cdc_smem_layout(chunk_sites, d.P, nullptr, nullptr);
   int n_chunks = (d.S + chunk_sites - 1) / chunk_sites;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem));
   cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
-  int tiles = d.n_pad / (kTileThreads * 2 * PK), items = tiles * d.F * n_chunks;
+  int tiles = d.n_pad / kTileAtoms, items = tiles * d.F * n_chunks;
   int grid = std::min(items, sm_count * per_sm);
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaMemset(d.acc, 0, sizeof(double) * (size_t)d.F * d.S * d.G));
@@ -49,7 +49,7 @@ double run(const Data& d, const char* name, int sm_count, double* checksum, int 
 
 int main(int argc, char** argv) {
   Data d; d.F = argc > 1 ? atoi(argv[1]) : 64;
-  d.n_pad = (d.N + 4095) / 4096 * 4096;
+  d.n_pad = (d.N + 2047) / 2048 * 2048;
   std::mt19937 rng(1);
   std::uniform_real_distribution<float> U(0.f, 10.f);
   std::normal_distribution<float> Nq(0.f, 0.4f);
@@ -83,15 +83,11 @@ int main(int argc, char** argv) {
   double cs_;
   int sm = prop.multiProcessorCount;
 #define RUN(MB, UN, SW) run<MB, UN, SW>(d, "minb" #MB " unroll" #UN " swp" #SW, sm, &cs)
-  for (int cs : {24, 8}) {
-    run<2, 4, true>(d, "E8  minb2 unroll4 swp", sm, &cs_, cs);
-    run<1, 2, false, 0, 8>(d, "E16 minb1 unroll2", sm, &cs_, cs);
-    run<1, 4, false, 0, 8>(d, "E16 minb1 unroll4", sm, &cs_, cs);
-    run<1, 2, true, 0, 8>(d, "E16 minb1 unroll2 swp", sm, &cs_, cs);
-    run<1, 4, true, 0, 8>(d, "E16 minb1 unroll4 swp", sm, &cs_, cs);
-    run<2, 2, false, 0, 8>(d, "E16 minb2 unroll2", sm, &cs_, cs);
-    run<2, 2, true, 0, 8>(d, "E16 minb2 unroll2 swp", sm, &cs_, cs);
-    run<2, 1, true, 0, 8>(d, "E16 minb2 unroll1 swp", sm, &cs_, cs);
+  for (int cs : {8}) {
+    run<2, 21, 3, 0>(d, "swp3 unroll21 deferred", sm, &cs_, cs);
+    run<2, 7, 3, 0>(d, "swp3 unroll7 deferred", sm, &cs_, cs);
+    run<2, 14, 3, 0>(d, "swp3 unroll14 deferred", sm, &cs_, cs);
+    run<2, 21, 3, 1>(d, "swp3 unroll21 NO-EPILOGUE", sm, &cs_, cs);
   }
   return 0;
 }
