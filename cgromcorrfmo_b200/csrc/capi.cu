@@ -107,6 +107,8 @@ struct cgc_context {
   bool cov_bound = false;
   bool shift_set = false;
   float* d_compat = nullptr;  // float32 [2][S*G]
+  double* d_centred = nullptr;  // scratch: centred FP64 rows of the batch being accumulated
+  int64_t centred_frames = 0;
 
   ~cgc_context();
 };
@@ -157,6 +159,9 @@ void free_static(cgc_context* c) {
   c->cov_bound = false;
   if (c->d_compat) cudaFree(c->d_compat);
   c->d_compat = nullptr;
+  if (c->d_centred) cudaFree(c->d_centred);
+  c->d_centred = nullptr;
+  c->centred_frames = 0;
   c->shift_set = false;
   c->dev_static = false;
 }
@@ -447,6 +452,17 @@ void collect_kernel_times(cgc_context* c) {
   c->timed.clear();
 }
 
+double* centred_scratch(cgc_context* c, int n_frames) {
+  if (c->centred_frames < n_frames) {
+    if (c->d_centred) CUDA_OK(cudaFree(c->d_centred));  // synchronises: nothing in flight still reads it
+    c->d_centred = nullptr;
+    const int64_t want = std::max<int64_t>(n_frames, 64);
+    CUDA_OK(cudaMalloc(&c->d_centred, sizeof(double) * (size_t)want * c->sys.n_sites * c->sys.num_tot));
+    c->centred_frames = want;
+  }
+  return c->d_centred;
+}
+
 // K1 -> K2 -> finish (-> K3) for one batch whose text is already in d_text; everything on `st`
 void enqueue_compute(cgc_context* c, const char* d_text, int64_t text_bytes, const int64_t* d_off, int n_frames,
                      float* d_xyz8, float4* d_sites, double* d_acc, float* d_dE, bool accumulate, cudaStream_t st) {
@@ -472,7 +488,7 @@ void enqueue_compute(cgc_context* c, const char* d_text, int64_t text_bytes, con
     }
     {
       ScopedKernelTimer t(c, 3, st);
-      launch_cov_accumulate(d_dE, n_frames, c->d_cov, c->d_compat, sys.n_sites, sys.num_tot, st);
+      launch_cov_accumulate(d_dE, n_frames, c->d_cov, c->d_compat, centred_scratch(c, n_frames), sys.n_sites, sys.num_tot, st);
     }
     c->launches += 2;
   }
@@ -935,7 +951,8 @@ int cgc_cov_accumulate_device(cgc_context* ctx, const float* d_dE_kcal, int n_fr
     }
     {
       ScopedKernelTimer t(ctx, 3, st);
-      launch_cov_accumulate(d_dE_kcal, n_frames, ctx->d_cov, ctx->d_compat, ctx->sys.n_sites, ctx->sys.num_tot, st);
+      launch_cov_accumulate(d_dE_kcal, n_frames, ctx->d_cov, ctx->d_compat, centred_scratch(ctx, n_frames), ctx->sys.n_sites,
+                            ctx->sys.num_tot, st);
     }
     ctx->launches += 2;
     CUDA_OK(cudaGetLastError());

@@ -268,7 +268,7 @@ void launch_finish(double* acc, float* dE, int64_t n, cudaStream_t st) {
 // blocks; only blocks with bi <= bj are computed (finalize mirrors them).  One CTA of 4 warps owns one block of one
 // site for the whole batch; each warp owns a 32 x 32 quarter = 4 x 4 DMMA m8n8k4 tiles (32 FP64 accumulators/thread).
 constexpr int kCovBlk = 64;
-constexpr int kCovChunk = 32;   // frames staged in shared memory per step
+constexpr int kCovChunk = 16;   // frames staged in shared memory per step (two stages in flight)
 constexpr int kCovLd = 68;      // row stride in doubles: 136 words == 8 (mod 32) -> conflict-free DMMA fragment loads
 
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
@@ -287,10 +287,11 @@ void launch_cov_set_shift(const float* dE_row0, double* buf, int S, int G, cudaS
   cov_set_shift_kernel<<<(n + 255) / 256, 256, 0, st>>>(dE_row0, buf, n);
 }
 
-// Also keeps the two float32 running sums the reference's literal .mtx arithmetic needs (src/FMOparse.cpp:173-175 with
-// the zero stride of :193,202): sum_t x_i and sum_t x_0 x_j, added frame by frame in order like the reference does.
+// cov_sum_kernel: n, sum(x-c), the centred rows D = x - c in FP64 (scratch, consumed by the SYRK), and the two float32
+// running sums the reference's literal .mtx arithmetic needs (src/FMOparse.cpp:173-175 with the zero stride of :193,202):
+// sum_t x_i and sum_t x_0 x_j, added frame by frame in order like the reference does.
 __global__ void cov_sum_kernel(const float* __restrict__ dE, int n_frames, double* __restrict__ buf, int SG, int G,
-                               float* __restrict__ compat /* [2][SG] or null */) {
+                               float* __restrict__ compat /* [2][SG] or null */, double* __restrict__ centred) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) buf[0] += (double)n_frames;
   if (i >= SG) return;
@@ -300,7 +301,9 @@ __global__ void cov_sum_kernel(const float* __restrict__ dE, int n_frames, doubl
   float m32 = compat ? compat[i] : 0.f, p32 = compat ? compat[SG + i] : 0.f;
   for (int t = 0; t < n_frames; t++) {
     const float x = dE[(size_t)t * SG + i];
-    s += (double)x - c;
+    const double d = (double)x - c;
+    centred[(size_t)t * SG + i] = d;
+    s += d;
     m32 += x;
     p32 += __fmul_rn(dE[(size_t)t * SG + i0], x);
   }
@@ -308,17 +311,26 @@ __global__ void cov_sum_kernel(const float* __restrict__ dE, int n_frames, doubl
   if (compat) { compat[i] = m32; compat[SG + i] = p32; }
 }
 
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc, bool valid) {
+  const int n = valid ? 8 : 0;   // src-size 0 -> the 8 bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_addr(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// sumsq_s += D_s^T D_s.  D (FP64, centred) is staged with cp.async (LDGSTS) into a double-buffered shared-memory tile:
+// the copy of chunk k+1 runs under the DMMAs of chunk k.
 __global__ void __launch_bounds__(128)
-cov_syrk_kernel(const float* __restrict__ dE, int n_frames, double* __restrict__ buf, int S, int G, int nblk) {
-  __shared__ double Ai[kCovChunk][kCovLd];
-  __shared__ double Aj[kCovChunk][kCovLd];
+cov_syrk_kernel(const double* __restrict__ D, int n_frames, double* __restrict__ buf, int S, int G, int nblk) {
+  __shared__ __align__(16) double Ai[2][kCovChunk][kCovLd];
+  __shared__ __align__(16) double Aj[2][kCovChunk][kCovLd];
   // upper-triangular block index -> (bi, bj)
   int b = blockIdx.x, bi = 0;
   while (b >= nblk - bi) { b -= nblk - bi; bi++; }
   const int bj = bi + b;
   const int s = blockIdx.y;
   const int SG = S * G;
-  const double* shift = buf + 1 + (size_t)s * G;
   double* sumsq = buf + 1 + 2 * (size_t)SG + (size_t)s * G * G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wi = (warp >> 1) * 32, wj = (warp & 1) * 32;  // this warp's quarter of the block
@@ -329,35 +341,42 @@ cov_syrk_kernel(const float* __restrict__ dE, int n_frames, double* __restrict__
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  for (int t0 = 0; t0 < n_frames; t0 += kCovChunk) {
-    // stage (x - c) for both column blocks; zero beyond G or beyond the batch
+  auto stage = [&](int buf_i, int t0) {
     for (int idx = threadIdx.x; idx < kCovChunk * kCovBlk; idx += 128) {
       const int k = idx / kCovBlk, cidx = idx - k * kCovBlk;
       const int t = t0 + k;
       const int gi = bi * kCovBlk + cidx, gj = bj * kCovBlk + cidx;
-      double vi = 0.0, vj = 0.0;
-      if (t < n_frames) {
-        const float* row = dE + (size_t)t * SG + (size_t)s * G;
-        if (gi < G) vi = (double)row[gi] - shift[gi];
-        if (gj < G) vj = (double)row[gj] - shift[gj];
-      }
-      Ai[k][cidx] = vi;
-      Aj[k][cidx] = vj;
+      const double* row = D + (size_t)(t < n_frames ? t : 0) * SG + (size_t)s * G;
+      cp_async_8(&Ai[buf_i][k][cidx], row + (gi < G ? gi : 0), t < n_frames && gi < G);
+      cp_async_8(&Aj[buf_i][k][cidx], row + (gj < G ? gj : 0), t < n_frames && gj < G);
+    }
+    cp_async_commit();
+  };
+
+  const int n_chunks = (n_frames + kCovChunk - 1) / kCovChunk;
+  stage(0, 0);
+  for (int ch = 0; ch < n_chunks; ch++) {
+    const int cb = ch & 1;
+    if (ch + 1 < n_chunks) {
+      stage(cb ^ 1, (ch + 1) * kCovChunk);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
 #pragma unroll
     for (int k0 = 0; k0 < kCovChunk; k0 += 4) {
       double a[4], bb[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++) a[i] = Ai[k0 + tig][wi + i * 8 + gid];
+      for (int i = 0; i < 4; i++) a[i] = Ai[cb][k0 + tig][wi + i * 8 + gid];
 #pragma unroll
-      for (int j = 0; j < 4; j++) bb[j] = Aj[k0 + tig][wj + j * 8 + gid];
+      for (int j = 0; j < 4; j++) bb[j] = Aj[cb][k0 + tig][wj + j * 8 + gid];
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
     }
-    __syncthreads();
+    __syncthreads();  // the tile is free before the copy two chunks ahead overwrites it
   }
 #pragma unroll
   for (int i = 0; i < 4; i++)
@@ -372,13 +391,14 @@ cov_syrk_kernel(const float* __restrict__ dE, int n_frames, double* __restrict__
     }
 }
 
-void launch_cov_accumulate(const float* dE, int n_frames, double* buf, float* compat, int S, int G, cudaStream_t st) {
+void launch_cov_accumulate(const float* dE, int n_frames, double* buf, float* compat, double* centred_scratch, int S,
+                           int G, cudaStream_t st) {
   if (n_frames <= 0) return;
   const int SG = S * G;
   const int nblk = (G + kCovBlk - 1) / kCovBlk;
+  cov_sum_kernel<<<(SG + 255) / 256, 256, 0, st>>>(dE, n_frames, buf, SG, G, compat, centred_scratch);
   dim3 grid(nblk * (nblk + 1) / 2, S);
-  cov_syrk_kernel<<<grid, 128, 0, st>>>(dE, n_frames, buf, S, G, nblk);
-  cov_sum_kernel<<<(SG + 255) / 256, 256, 0, st>>>(dE, n_frames, buf, SG, G, compat);
+  cov_syrk_kernel<<<grid, 128, 0, st>>>(centred_scratch, n_frames, buf, S, G, nblk);
 }
 
 // mean = c + sum/n ; cov_ij = (sumsq_ij - sum_i sum_j / n) / (n - ddof), upper blocks mirrored

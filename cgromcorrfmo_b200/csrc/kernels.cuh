@@ -51,8 +51,9 @@ void launch_finish(double* acc, float* dE, int64_t n, cudaStream_t st);
 
 // K3: per-site shifted sums.  buf = [ n | c (S*G) | sum (S*G) | sumsq (S*G*G) ]
 void launch_cov_set_shift(const float* dE_row0, double* buf, int S, int G, cudaStream_t st);
+// centred_scratch: n_frames * S * G doubles (the centred rows the SYRK consumes)
 void launch_cov_accumulate(const float* dE, int n_frames, double* buf, float* compat /* float32 [2][S*G] or null */,
-                           int S, int G, cudaStream_t st);
+                           double* centred_scratch, int S, int G, cudaStream_t st);
 void launch_cov_finalize(const double* buf, int S, int G, int ddof, double* mean, double* cov, cudaStream_t st);
 
 }  // namespace cgc
