@@ -780,7 +780,9 @@ int cgc_run(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_k
     auto drain = [&](Slot& s) {
       if (!s.busy) return;
       CUDA_OK(cudaEventSynchronize(s.ev_done));
-      if (dE_kcal) memcpy(dE_kcal + s.out_frame * sg, s.h_dE, sizeof(float) * (size_t)(sg * s.frames));
+      if (dE_kcal) {
+        parallel_copy((char*)(dE_kcal + s.out_frame * sg), (const char*)s.h_dE, (int64_t)sizeof(float) * sg * s.frames);
+      }
       if (frames_done) *frames_done += s.frames;
       s.busy = false;
     };

@@ -1,0 +1,88 @@
+"""ctypes shim for the pyPCA / depca post-processing scripts (reference scripts/depca, scripts/2014-06-csv2hdf5.py).
+
+Those scripts only ever consume `csv_out.time`: the text is parsed back into a
+(frames, 7, 357) array (scripts/2014-06-csv2hdf5.py:56-74), split per site (scripts/depca/depca/dedata.py:96-120), and
+reduced with np.cov + mean per site (scripts/depca/depca/sidechain_corr.py:50-72) before eigh and projection.  This module
+hands them the same arrays straight from the GPU path, with depca's names, shapes, units and return order, so the text
+round trip disappears.  Everything numerical that is on the hot path (dE rows, mean, covariance) comes from the C-ABI;
+what follows it (eigen-decomposition, projection) is plain numpy, as in depca.
+
+    E_t_ia               = load_E_t_ia(traj, top, itp, num_frames)            # float32 (T, Nsites, Ncoarse), cm^-1
+    Corr_i_ab, AvgEia    = AvgAndCorrelateSidechains_gpu(traj, top, itp, T)   # depca's return order
+    vi, wi, impact_i     = ComputeModes(Corr_i_ab)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import capi
+
+CM_PER_KCAL = 349.7   # reference src/FMOparse.cpp:151
+
+
+def _run(traj, top, itp, num_frames, sites, device, want_rows):
+    with capi.Context(top, itp, device) as c:
+        c.open(traj)
+        if sites:
+            c.set_option("sites", sites)
+        dE, done, _ = c.run(0, num_frames, want_dE=want_rows)
+        mean = cov = None
+        if c.cov_size() and done > 1:
+            mean, cov = c.cov_finalize(ddof=1)     # np.cov's default, as depca uses it (sidechain_corr.py:67)
+        return dE, done, mean, cov
+
+
+def load_E_t_ia(traj, top, itp, num_frames, sites=7, device=0, units="cm-1"):
+    """The array depca calls E_t_ia: (frames, Nsites, Ncoarse).  `.time` holds cm^-1 (x349.7 of the kcal/mol rows), and so
+    does this by default; the conversion is the reference's own: float(double(kcal) * 349.7) (src/FMOparse.cpp:151-154).
+    sites=7 is the stock program's site count (src/FMOparse.cpp:133); 0 = every chromophore."""
+    dE, done, _, _ = _run(traj, top, itp, num_frames, sites, device, True)
+    if units == "kcal":
+        return dE
+    return (dE.astype(np.float64) * CM_PER_KCAL).astype(np.float32)
+
+
+def AvgAndCorrelateSidechains_gpu(traj, top, itp, num_frames, sites=7, device=0, units="cm-1"):
+    """depca.sidechain_corr.AvgAndCorrelateSidechains (sidechain_corr.py:36-72) without materialising the time series on
+    the host: returns (Corr_i_ab [Nsites, Ncoarse, Ncoarse], AvgEia [Nsites, Ncoarse]) — np.cov(rowvar=0) (ddof 1) and the
+    mean per site, computed by the Correlate kernels on the float32 rows."""
+    _, done, mean, cov = _run(traj, top, itp, num_frames, sites, device, False)
+    if cov is None:
+        raise ValueError("covariance is unavailable (fewer than two frames, or numTot too large for the partial sums)")
+    if units == "kcal":
+        return cov, mean
+    # the rows are scaled by 349.7 before np.cov in depca's pipeline (they come from the .time text)
+    return cov * (CM_PER_KCAL * CM_PER_KCAL), mean * CM_PER_KCAL
+
+
+def AvgAndCorrelateSidechains(E_t_ia):
+    """Same reduction for an array that is already on the host (numpy), per site: np.cov(X, rowvar=0) and the mean
+    (sidechain_corr.py:50-72).  Post-processing, not the hot path."""
+    E = np.asarray(E_t_ia, dtype=np.float64)
+    corr = np.stack([np.cov(E[:, i, :], rowvar=False) for i in range(E.shape[1])])
+    return corr, E.mean(axis=0)
+
+
+def ComputeModes(corr, sort=True):
+    """depca.sidechain_corr.ComputeModes (sidechain_corr.py:74-129): eigh per site, eigenvectors as rows, sign chosen so that
+    the component sum has the sign of the eigenvalue, modes sorted by eigenvalue x impact^2 (ascending, like the script)."""
+    corr = np.asarray(corr)
+    vi, wi, imp = [], [], []
+    for c in corr:
+        v, w = np.linalg.eigh(c)
+        w = w.T.copy()
+        n = w.sum(axis=1)
+        flip = ((v < 0) & (n > 0)) | ((v > 0) & (n < 0))
+        w[flip] *= -1
+        n[flip] *= -1
+        if sort:
+            order = np.argsort(v * n * n, kind="stable")
+            v, w, n = v[order], w[order], n[order]
+        vi.append(v); wi.append(w); imp.append(n)
+    return np.array(vi), np.array(wi), np.array(imp)
+
+
+def ApplyPCA(E_t_ia, AvgEia, wi):
+    """depca.convert.ApplyPCA_hdf5 (convert.py:84-125) in memory: (E - mean) projected on the modes, per site."""
+    E = np.asarray(E_t_ia, dtype=np.float64)
+    return np.stack([np.inner(E[:, i, :] - AvgEia[i], wi[i]) for i in range(E.shape[1])], axis=1)

@@ -1,0 +1,39 @@
+"""Developer check: the C4 shape (350k atoms, every solvent molecule its own group, numTot ~1e5, covariance off)."""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from cgromcorrfmo_b200 import capi, synth
+from oracle import oracle as O
+
+t0 = time.time()
+s = synth.named_system("C4")
+d = "/tmp/dev_c4"; os.makedirs(d, exist_ok=True)
+frames = 8
+prefix = synth._static_prefix(s)
+top, itp = d + "/topol.top", d + "/bcx.itp"
+synth.write_top(top, s); synth.write_itp(itp, s)
+blob = b"".join(synth.frame_bytes(s, prefix, f) for f in range(frames))
+print("generated in %.1fs, %.2f MB/frame" % (time.time() - t0, len(blob) / frames / 1e6), flush=True)
+text = np.frombuffer(blob, dtype=np.uint8)
+host = torch.from_numpy(np.concatenate([text, np.zeros(64, np.uint8)])).pin_memory()
+with capi.Context(top, itp, 0) as c:
+    t0 = time.time()
+    c.open_memory((host.data_ptr(), text.size))
+    print("open %.2fs dims %s cov_size %d batch %d" % (time.time() - t0, c.dims(), c.cov_size(), c.get_option("batch_frames")), flush=True)
+    c.set_option("profile", 1)
+    dE, done, rc = c.run(0, frames)
+    t0 = time.time()
+    dE, done, rc = c.run(0, frames)
+    dt = time.time() - t0
+    kt = c.kernel_times(reset=True)
+    print("e2e %.1f ms per %d frames -> %.1f frames/s ; kernel ms %s" % (dt * 1e3, frames, frames / dt, {k: round(v[0] / 2, 3) for k, v in kt.items()}), flush=True)
+    S, G = c.n_sites, c.num_tot
+    pairs = frames * S * int(c.get_option("site_cap")) * (c.n_atoms - 140)
+    print("K2: %.1f Gpairs/s -> %.3f of ceiling" % (pairs / (kt["cdc"][0] / 2) / 1e6, pairs / (kt["cdc"][0] / 2) / 1e6 / 4653.1))
+open(d + "/one.gro", "wb").write(blob[: len(blob) // frames])
+t0 = time.time()
+ref = O.run(d + "/one.gro", top, itp, 1, n_sites=3)
+print("oracle 3 sites: %.1fs" % (time.time() - t0))
+r64 = ref["dE_f64"][0]; dd = np.abs(dE[0, :3].astype(np.float64) - r64); sc = np.maximum(np.abs(r64), ref["scale"][0]); m = sc > 0
+print("C4 frame0 sites 1-3 max scaled err %.3g ; zero cols max %.3g" % ((dd[m] / sc[m]).max(), np.abs(dE[0, :3][~m]).max() if (~m).any() else 0))

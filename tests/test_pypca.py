@@ -1,0 +1,55 @@
+"""The pyPCA/depca shim (cgromcorrfmo_b200/pypca.py): host-side post-processing against a line-by-line restatement of the
+reference scripts, and (gpu) the device-computed reduction against numpy on the rows the same run returns."""
+import numpy as np
+import pytest
+
+from cgromcorrfmo_b200 import pypca
+
+
+def _compute_modes_reference(corr):
+    """reference scripts/depca/depca/sidechain_corr.py:91-129, restated without the py2 idioms."""
+    vi, wi, imp = [], [], []
+    for c in corr:
+        v, w = np.linalg.eigh(c)
+        w = w.transpose().copy()
+        n = []
+        for k in range(len(v)):
+            nf = sum(w[k])
+            if (v[k] < 0 and nf > 0) or (v[k] > 0 and nf < 0):
+                w[k] *= -1
+                nf *= -1
+            n.append(nf)
+        tup = sorted(zip(v, n, [x.copy() for x in w]), key=lambda x: x[0] * x[1] * x[1])
+        vi.append([t[0] for t in tup]); imp.append([t[1] for t in tup]); wi.append([t[2] for t in tup])
+    return np.array(vi), np.array(wi), np.array(imp)
+
+
+def test_host_post_processing_matches_depca():
+    rng = np.random.default_rng(90210)                     # the seed of the reference's own script (old/test__pyPCA.py:9)
+    E = (rng.normal(size=(1000, 2, 6)) @ np.diag([3, 2, 1, 0.5, 0.2, 0.1]) + 7.0).astype(np.float32)
+    corr, avg = pypca.AvgAndCorrelateSidechains(E)
+    for i in range(2):
+        assert np.allclose(corr[i], np.cov(E[:, i, :].astype(np.float64), rowvar=False))
+    vi, wi, imp = pypca.ComputeModes(corr)
+    rv, rw, ri = _compute_modes_reference(corr)
+    assert np.allclose(vi, rv) and np.allclose(wi, rw) and np.allclose(imp, ri)
+    assert np.all(np.diff(vi * imp * imp, axis=1) >= -1e-12)
+    proj = pypca.ApplyPCA(E, avg, wi)
+    assert proj.shape == (1000, 2, 6)
+    for i in range(2):
+        assert np.allclose(np.cov(proj[:, i, :], rowvar=False), np.diag(vi[i]), atol=1e-8)   # modes diagonalise the covariance
+
+
+@pytest.mark.gpu
+def test_gpu_reduction_matches_numpy(small_inputs):
+    traj, top, itp, frames = small_inputs("tiny")
+    E = pypca.load_E_t_ia(traj, top, itp, frames, sites=7)
+    assert E.shape[:2] == (frames, 7) and E.dtype == np.float32
+    Ek = pypca.load_E_t_ia(traj, top, itp, frames, sites=7, units="kcal")
+    assert np.array_equal(E, (Ek.astype(np.float64) * 349.7).astype(np.float32))
+    corr, avg = pypca.AvgAndCorrelateSidechains_gpu(traj, top, itp, frames, sites=7, units="kcal")
+    rc, ra = pypca.AvgAndCorrelateSidechains(Ek)
+    scale = np.maximum(np.abs(rc), np.sqrt(np.einsum("sii,sjj->sij", rc, rc)))
+    ok = scale > 0
+    assert np.all(np.abs(corr - rc)[ok] <= 1e-9 * scale[ok])
+    assert np.allclose(avg, ra, rtol=1e-12, atol=1e-300)
