@@ -52,6 +52,35 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
 
 
+def k2_traffic_per_frame():
+    """dram__bytes_read.sum + dram__bytes_write.sum of cdc_kernel per frame of the C2 workload, from the committed
+    `ncu --set full` capture (profiles/r01_k2_traffic.json); None when that file is absent."""
+    p = os.path.join(ROOT, "profiles", "r01_k2_traffic.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["dram_bytes_per_frame"])
+        except Exception:
+            return None
+    return None
+
+
+def calibrate_fp64_tensor(torch, dev):
+    """Yard-stick for K3 only (MEASURED_PEAKS.json has no FP64 figure): cuBLAS DGEMM 4096^3, best of 5, TFLOP/s."""
+    n = 4096
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
 def cores_available() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -331,6 +360,7 @@ def run_ours(args):
         e2e_ktimes = ctx.kernel_times(reset=True)
         same = float(np.abs(out_host - d_dE.cpu().numpy()).max())
         ctx.close()
+        fp64_peak = calibrate_fp64_tensor(torch, dev) if rank == 0 else None
 
     if rank != 0:
         if world > 1:
@@ -354,7 +384,9 @@ def run_ours(args):
     roofline = {
         "kernel": "cdc_kernel (K2, CDC pair sums)", "bound": "fp32+mufu issue (16 pairs/clk/SM)",
         "achieved": achieved, "peak": peak, "unit": "Gpairs/s", "frac": achieved / peak if peak else None,
-        "traffic": None,
+        "traffic": (k2_traffic_per_frame() * F) if k2_traffic_per_frame() else None,
+        "traffic_source": "profiles/r01_k2_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per frame) x frames per launch",
+        "algorithmic_bytes_per_launch": F * (n_atoms * 12 + S * ndq * 16),
         "peak_source": "16 pairs/clk/SM x %d SMs x %.0f MHz (sm_max_mhz, %s MEASURED_PEAKS.json)" % (SM_COUNT, peaks["sm_max_mhz"], peaks["source"]),
         "algorithmic_pairs_per_launch": pairs_per_launch, "avg_launch_ms": k2_avg_s * 1e3,
         "share_of_kernel_time": k2_ms / kern_total if kern_total else None,
@@ -366,7 +398,9 @@ def run_ours(args):
          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (k1_bytes / k1_avg_s / 1e9 / peaks["hbm_gbs"]) if k1_avg_s else None,
          "algorithmic_bytes_per_launch": k1_bytes, "avg_launch_ms": k1_avg_s * 1e3, "share_of_kernel_time": k1_ms / kern_total if kern_total else None},
         {"kernel": "cov_syrk_kernel+cov_sum_kernel (K3)", "bound": "fp64 tensor (DMMA)", "achieved": k3_flop / k3_avg_s / 1e12 if k3_avg_s else 0.0,
-         "peak": None, "unit": "TFLOP/s", "frac": None, "algorithmic_flop_per_launch": k3_flop, "avg_launch_ms": k3_avg_s * 1e3,
+         "peak": fp64_peak, "unit": "TFLOP/s", "frac": (k3_flop / k3_avg_s / 1e12 / fp64_peak) if (k3_avg_s and fp64_peak) else None,
+         "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)",
+         "algorithmic_flop_per_launch": k3_flop, "avg_launch_ms": k3_avg_s * 1e3,
          "share_of_kernel_time": k3_ms / kern_total if kern_total else None},
     ]
 

@@ -16,6 +16,7 @@
 #include <thread>
 #include <vector>
 
+#include "fmt_g.h"
 #include "host_parse.h"
 #include "kernels.cuh"
 
@@ -1003,7 +1004,7 @@ int cgc_cov_finalize(cgc_context* ctx, int ddof, double* mean, double* cov) {
 namespace {
 
 // "%g" of a float, as std::ostream << float prints it (precision 6)
-inline int fmt_g(char* p, float v) { return snprintf(p, 32, "%g", (double)v); }
+inline int fmt_g(char* p, float v) { return fmt_g6(p, v); }
 
 // format rows [r0, r1) of a float matrix into `out`
 void format_rows(const float* m, int64_t r0, int64_t r1, int ncol, bool to_cm, std::string& out) {

@@ -170,3 +170,27 @@ def test_fixed_column_extension_five_digit_serials(tmp_path, small_inputs):
         a.open(traj)
         b.open(wide)
         assert np.array_equal(a.groups(), b.groups()) and a.keys() == b.keys()
+
+
+def test_time_writer_is_byte_identical_to_printf_g(tmp_path):
+    """cgc_write_time formats with a fast "%g" (csrc/fmt_g.h); it must print exactly what std::ostream << float /
+    printf("%g") prints (reference src/FMOparse.cpp:151-165).  Python's '%g' is the same correctly-rounded conversion."""
+    rng = np.random.default_rng(2)
+    n = 400_000
+    x = (rng.choice([-1.0, 1.0], n) * 10.0 ** rng.uniform(-14, 7, n) * rng.uniform(0.1, 1, n)).astype(np.float32)
+    special = np.array([0.0, -0.0, 1.0, 0.5, 123456.5 / 349.7, 1e-5, 9.999995e-5, 999999.5, 0.1, 1e5, 1e6, 12345.65,
+                        2.5e-7, 1e-38, 1e30, 2.8596e-3, 100000.0 / 349.7, 1000000.0 / 349.7, np.inf, -np.inf, np.nan],
+                       np.float32)
+    x[:special.size] = special
+    # values whose 7th digit is exactly 5 (rounding ties of the decimal expansion) and exact powers of ten
+    ties = np.array([(k * 10 + 5) / 64.0 for k in range(100000, 100400)], np.float32)
+    x[100:100 + ties.size] = ties / np.float32(349.7)
+    x = x.reshape(-1, 500)
+    path = str(tmp_path / "w.time")
+    capi.write_time(path, x)
+    with np.errstate(over="ignore", invalid="ignore"):
+        cm = (x.astype(np.float64) * 349.7).astype(np.float32)
+    expect = "".join(",".join("%g" % float(v) for v in row) + "\n" for row in cm)
+    assert open(path).read() == expect
+    capi.write_time(path, x[:2], truncate=False)          # append mode (the reference re-opens in append mode per row)
+    assert open(path).read() == expect + expect[: len("".join(expect.splitlines(True)[:2]))]
