@@ -68,6 +68,7 @@ struct cgc_context {
   const char* text = nullptr;
   int64_t nbytes = 0;
   bool mapped = false;
+  int fd = -1;              // the trajectory file, kept open for threaded pread() into the pinned staging buffers
   bool registered = false;  // text is page-locked for the device (cudaHostRegister): H2D straight from it
   FrameLayout L;
   std::vector<FrameSpan> frames;  // frames located so far
@@ -120,6 +121,8 @@ void release_text(cgc_context* c) {
   if (c->registered && c->text) cudaHostUnregister((void*)c->text);
   c->registered = false;
   if (c->mapped && c->text) munmap((void*)c->text, (size_t)c->nbytes);
+  if (c->fd >= 0) close(c->fd);
+  c->fd = -1;
   c->text = nullptr;
   c->nbytes = 0;
   c->mapped = false;
@@ -393,6 +396,30 @@ int64_t index_upto(cgc_context* c, int64_t upto) {
   return (int64_t)c->frames.size();
 }
 
+void parallel_pread(int fd, char* dst, int64_t offset, int64_t n) {
+  const int64_t kMin = 4 << 20;
+  int nt = (int)std::min<int64_t>(std::max(1u, std::min(16u, std::thread::hardware_concurrency())), std::max<int64_t>(1, n / kMin));
+  auto work = [=](int64_t b, int64_t e) {
+    while (b < e) {
+      ssize_t got = pread(fd, dst + b, (size_t)(e - b), (off_t)(offset + b));
+      if (got <= 0) break;  // short file: the frame index never points past the end, so this is an I/O error
+      b += got;
+    }
+  };
+  if (nt <= 1) {
+    work(0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const int64_t chunk = ((n + nt - 1) / nt + 4095) & ~(int64_t)4095;
+  for (int i = 0; i < nt; i++) {
+    int64_t b = (int64_t)i * chunk, e = std::min(n, b + chunk);
+    if (b >= e) break;
+    th.emplace_back(work, b, e);
+  }
+  for (auto& t : th) t.join();
+}
+
 void parallel_copy(char* dst, const char* src, int64_t n) {
   const int64_t kMin = 8 << 20;
   int nt = (int)std::min<int64_t>(std::max(1u, std::min(8u, std::thread::hardware_concurrency())), std::max<int64_t>(1, n / kMin));
@@ -579,12 +606,16 @@ int cgc_open(cgc_context* ctx, const char* traj_path) {
       throw ReadError("trajectory file is empty or cannot be stat'ed");
     }
     void* p = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
-    close(fd);
-    if (p == MAP_FAILED) throw ReadError("mmap of the trajectory failed");
-    madvise(p, (size_t)sb.st_size, MADV_SEQUENTIAL);
+    if (p == MAP_FAILED) {
+      close(fd);
+      throw ReadError("mmap of the trajectory failed");
+    }
+    // the mapping serves the frame-0 pass and the frame index (a few bytes per frame); the bulk text is pread() by several
+    // threads straight into the pinned staging buffers, which avoids one page fault per 4 KiB of trajectory
     ctx->text = (const char*)p;
     ctx->nbytes = sb.st_size;
     ctx->mapped = true;
+    ctx->fd = fd;
     open_common(ctx);
     return CGC_OK;
   });
@@ -812,7 +843,9 @@ int cgc_run(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_k
       for (int i = 0; i < want; i++) s.h_off[i] = ctx->frames[(size_t)(f_begin + i)].atoms - b0;
       const char* src = ctx->text + b0;
       if (!direct) {
-        parallel_copy(s.h_text, src, nb);  // page cache / pageable memory -> pinned
+        // page cache / pageable memory -> pinned
+        if (ctx->mapped && ctx->fd >= 0) parallel_pread(ctx->fd, s.h_text, b0, nb);
+        else parallel_copy(s.h_text, src, nb);
         src = s.h_text;
       }
       CUDA_OK(cudaMemcpyAsync(s.d_text, src, (size_t)nb, cudaMemcpyHostToDevice, ctx->st_copy));
@@ -1025,12 +1058,12 @@ void format_rows(const float* m, int64_t r0, int64_t r1, int ncol, bool to_cm, s
 }
 
 int write_matrix_text(const char* path, bool truncate, const float* m, int64_t rows, int ncol, bool to_cm) {
-  FILE* f = fopen(path, truncate ? "wb" : "ab");
-  if (!f) return -1;
+  int fd = open(path, O_WRONLY | O_CREAT | (truncate ? O_TRUNC : O_APPEND), 0644);
+  if (fd < 0) return -1;
   const int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-  const int64_t per = std::max<int64_t>(1, (((int64_t)4 << 20) / std::max(1, ncol * 9)));  // ~4 MB of text per task
-  for (int64_t base = 0; base < rows; base += per * nt) {
-    std::vector<std::string> parts((size_t)nt);
+  const int64_t per = std::max<int64_t>(1, (((int64_t)2 << 20) / std::max(1, ncol * 9)));  // ~2 MB of text per task
+  // groups of nt tasks; group g+1 is formatted by the pool while this thread writes group g
+  auto format_group = [&](int64_t base, std::vector<std::string>& parts) {
     std::vector<std::thread> th;
     for (int i = 0; i < nt; i++) {
       int64_t r0 = base + i * per, r1 = std::min(rows, r0 + per);
@@ -1038,13 +1071,29 @@ int write_matrix_text(const char* path, bool truncate, const float* m, int64_t r
       th.emplace_back([&, i, r0, r1] { format_rows(m, r0, r1, ncol, to_cm, parts[(size_t)i]); });
     }
     for (auto& t : th) t.join();
-    for (auto& p : parts)
-      if (!p.empty() && fwrite(p.data(), 1, p.size(), f) != p.size()) {
-        fclose(f);
-        return -1;
+  };
+  std::vector<std::string> cur((size_t)nt), nxt((size_t)nt);
+  bool ok = true;
+  if (rows > 0) format_group(0, cur);
+  for (int64_t base = 0; base < rows && ok; base += per * nt) {
+    const int64_t next_base = base + per * nt;
+    std::thread ahead;
+    if (next_base < rows) ahead = std::thread([&] { format_group(next_base, nxt); });
+    for (auto& p : cur) {
+      size_t off = 0;
+      while (off < p.size()) {
+        ssize_t w = write(fd, p.data() + off, p.size() - off);
+        if (w <= 0) { ok = false; break; }
+        off += (size_t)w;
       }
+      p.clear();
+      if (!ok) break;
+    }
+    if (ahead.joinable()) ahead.join();
+    std::swap(cur, nxt);
   }
-  return fclose(f) == 0 ? 0 : -1;
+  if (close(fd) != 0) ok = false;
+  return ok ? 0 : -1;
 }
 
 }  // namespace

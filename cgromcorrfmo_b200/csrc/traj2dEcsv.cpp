@@ -12,6 +12,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <csignal>
 #include <cstdio>
 #include <cstdlib>
@@ -28,6 +29,10 @@ static void on_sigint(int) {
   ssize_t r = write(2, msg, sizeof(msg) - 1);
   (void)r;
   g_keep_running = 0;
+}
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 static int die(cgc_context* ctx, int rc, const char* what) {
@@ -53,7 +58,7 @@ int main(int argc, char** argv) {
   const long long num_frames = atoll(argv[5]);
   int sites = 0, device = 0, batch = 0;
   long long first = 0;
-  bool compat = false, no_mtx = false, verbose = false;
+  bool compat = false, no_mtx = false, verbose = false, timing = false;
   for (int i = 6; i < argc; i++) {
     std::string a = argv[i];
     auto val = [&](const char* name) -> const char* {
@@ -70,6 +75,7 @@ int main(int argc, char** argv) {
     else if (a == "--mtx-compat") compat = true;
     else if (a == "--no-mtx") no_mtx = true;
     else if (a == "--verbose") verbose = true;
+    else if (a == "--timing") timing = true;
     else {
       fprintf(stderr, "traj2dEcsv: unknown flag %s\n", a.c_str());
       return EXIT_FAILURE;
@@ -77,6 +83,7 @@ int main(int argc, char** argv) {
   }
   if (const char* e = getenv("CGC_SITES")) if (!sites) sites = atoi(e);
 
+  const double t_start = now_s();
   cgc_context* ctx = nullptr;
   int rc = cgc_create(top.c_str(), itp.c_str(), device, &ctx);
   if (rc != CGC_OK) return die(nullptr, rc, "reading the topology");
@@ -84,6 +91,7 @@ int main(int argc, char** argv) {
     printf("Minor issues found with the topology input (%d conflicting duplicate entries; first entry kept)\n",
            cgc_topology_warnings(ctx));
   }
+  const double t_created = now_s();
   rc = cgc_open(ctx, traj.c_str());
   if (rc != CGC_OK) return die(ctx, rc, "opening the trajectory");
   if (sites > 0 && (rc = cgc_set_option(ctx, "sites", sites)) != CGC_OK) return die(ctx, rc, "setting --sites");
@@ -105,6 +113,9 @@ int main(int argc, char** argv) {
     return EXIT_FAILURE;
   }
   signal(SIGINT, on_sigint);
+  const double t_opened = now_s();
+  double t_run = 0, t_wait_writer = 0, t_best_chunk = 1e30;
+  long long best_chunk_frames = 0;
 
   const long long chunk = 4LL * (long long)cgc_get_option(ctx, "batch_frames");
   const size_t row = (size_t)S * num_tot;
@@ -118,13 +129,22 @@ int main(int argc, char** argv) {
     const long long n = std::min(chunk, num_frames - done_total);
     buf[which].resize((size_t)n * row);
     int64_t done = 0;
+    double t0 = now_s();
     rc = cgc_run(ctx, first + done_total, n, buf[which].data(), &done);
+    const double t_chunk = now_s() - t0;
+    t_run += t_chunk;
+    if (done == n && t_chunk / (double)n < t_best_chunk / (double)std::max<long long>(1, best_chunk_frames)) {
+      t_best_chunk = t_chunk;
+      best_chunk_frames = n;
+    }
+    t0 = now_s();
     if (rc != CGC_OK && rc != CGC_EOF) {
       if (writer.joinable()) writer.join();
       return die(ctx, rc, "processing frames");
     }
     eof = rc == CGC_EOF;
     if (writer.joinable()) writer.join();
+    t_wait_writer += now_s() - t0;
     if (wrc != CGC_OK) break;
     const float* data = buf[which].data();
     const long long base = done_total;
@@ -145,7 +165,9 @@ int main(int argc, char** argv) {
     done_total += done;
     which ^= 1;
   }
+  const double t_loop_end = now_s();
   if (writer.joinable()) writer.join();
+  const double t_written = now_s();
   if (wrc != CGC_OK) {
     fprintf(stderr, "traj2dEcsv: cannot write %s\n", time_path.c_str());
     cgc_destroy(ctx);
@@ -159,6 +181,15 @@ int main(int argc, char** argv) {
     rc = cgc_write_mtx(ctx, (out + ".mtx").c_str(), compat ? 1 : 0);
     if (rc != CGC_OK) return die(ctx, rc, "writing the .mtx file");
   }
+  const double t_mtx = now_s();
   cgc_destroy(ctx);
+  if (timing) {
+    fprintf(stderr,
+            "timing: tables+cuda init %.3f s | open (frame-0 pass, device tables) %.3f s | frame loop %.3f s (cgc_run %.3f, "
+            "waiting for the .time writer %.3f) | last .time chunk %.3f s | .mtx %.3f s | teardown %.3f s | frames %lld | best chunk: %lld frames in %.3f s = %.0f frames/s\n",
+            t_created - t_start, t_opened - t_created, t_loop_end - t_opened, t_run, t_wait_writer, t_written - t_loop_end,
+            t_mtx - t_written, now_s() - t_mtx, done_total, best_chunk_frames, t_best_chunk,
+            best_chunk_frames / t_best_chunk);
+  }
   return 0;
 }

@@ -438,3 +438,41 @@ def test_wide_coordinate_fields(tmp_path, capi_mod, torch_cuda, small_inputs):
         got = xyz.cpu().numpy().reshape(-1)
     expect = np.array([np.float32(float(ln[20 + 10 * k: 30 + 10 * k])) for ln in lines for k in range(3)], np.float32)
     assert np.array_equal(got.view(np.uint32), expect.view(np.uint32))
+
+
+def test_two_rank_sharding_emulated_on_one_gpu(small_inputs, oracle_mod, capi_mod):
+    """Frame-range sharding as the multi-GPU driver does it (cgromcorrfmo_b200/run.py), with both "ranks" as separate
+    contexts on one GPU: each streams its range, the partial sums are added element-wise with the shift block restored
+    (what dist.allreduce_partials does over NCCL), and the merged sums finalise to the covariance of ALL rows.
+    Rank 1 does not start at frame 0, so it evaluates frame 0 only to obtain the common shift."""
+    O, capi = oracle_mod, capi_mod
+    from cgromcorrfmo_b200 import dist as cdist
+    traj, top, itp, frames = small_inputs("tiny")
+    parts, rows = [], []
+    for rank in range(2):
+        lo, n = cdist.frame_range(rank, 2, frames)
+        with capi.Context(top, itp, 0) as c:
+            c.open(traj)
+            dE, done, _ = c.run(lo, n)
+            assert done == n
+            rows.append(dE)
+            parts.append(c.cov_partials())
+            S, G = c.n_sites, c.num_tot
+    lay = cdist.partials_layout(S, G)
+    assert np.array_equal(parts[0][lay["shift"]:lay["sum"]], parts[1][lay["shift"]:lay["sum"]])   # same shift on both
+    allrows = np.concatenate(rows)
+    assert np.array_equal(parts[0][lay["shift"]:lay["sum"]], allrows[0].astype(np.float64).reshape(-1))  # = row of frame 0
+    merged = parts[0] + parts[1]
+    merged[lay["shift"]:lay["sum"]] = parts[0][lay["shift"]:lay["sum"]]
+    n = merged[0]
+    assert n == frames
+    s = merged[lay["sum"]:lay["sumsq"]].reshape(S, G)
+    ss = merged[lay["sumsq"]:].reshape(S, G, G)
+    iu = np.triu_indices(G)
+    cov = (ss - np.einsum("si,sj->sij", s, s) / n) / n
+    _, c64 = O.cov_f64(allrows, 0)
+    scale = np.maximum(np.abs(c64), np.sqrt(np.einsum("sii,sjj->sij", c64, c64)))
+    for k in range(S):
+        # the device stores the upper block-triangle (64x64 blocks); G < 64 here, so the whole matrix is one block
+        ok = scale[k] > 0
+        assert np.all(np.abs(cov[k] - c64[k])[ok] <= COV_TOL * scale[k][ok])
