@@ -197,17 +197,17 @@ void launch_decode(const DeviceSystem& sys, const char* text, int64_t text_bytes
 // ---------------------------------------------------------------------------------------------------------------------
 // K2  CDC pair kernel: see cdc_kernel.cuh
 // ---------------------------------------------------------------------------------------------------------------------
-// Sites per work item: few enough that a launch has >= ~48 items per resident CTA (tail below ~2 %), never fewer than 2
-// sites per item (the per-item prologue — 8 atoms, columns, charges — is amortised over the site loop), never more than
-// kCdcMaxChunkSites (shared memory of the deferred lane reduction).
-static int cdc_chunk_sites(const DeviceSystem& sys, int n_frames, int resident_ctas) {
+// Sites per work item.  All sites in one item when the launch has plenty of items (the thread's atoms, columns and
+// charges are then loaded once per frame and tile); fewer — down to 2 — when a launch is small, so that even a single
+// frame fills the machine.  Inside an item the sites go through shared memory in chunks of kCdcMaxChunkSites.
+static int cdc_group_sites(const DeviceSystem& sys, int n_frames, int resident_ctas) {
   const int tiles = sys.n_pad / kTileAtoms;
-  int best = std::min(sys.n_sites, kCdcMaxChunkSites);
-  for (int cs = best; cs >= 1; cs--) {
-    const int chunks = (sys.n_sites + cs - 1) / cs;
-    best = cs;
-    if ((long long)tiles * n_frames * chunks >= 48LL * resident_ctas) break;
-    if (cs <= 2) break;
+  int best = sys.n_sites;
+  for (int gs = sys.n_sites; gs >= 1; gs--) {
+    const int groups = (sys.n_sites + gs - 1) / gs;
+    best = gs;
+    if ((long long)tiles * n_frames * groups >= 16LL * resident_ctas) break;
+    if (gs <= 2) break;
   }
   return best;
 }
@@ -229,16 +229,17 @@ void launch_cdc(const DeviceSystem& sys, const float* xyz8, const float4* sites,
   int per_sm = kCdcMinBlocks;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, cdc_smem_bytes(sys));
   if (per_sm < 1) per_sm = 1;
-  const int chunk_sites = cdc_chunk_sites(sys, n_frames, sm_count * per_sm);
-  const int n_chunks = (sys.n_sites + chunk_sites - 1) / chunk_sites;
+  const int group_sites = cdc_group_sites(sys, n_frames, sm_count * per_sm);
+  const int n_groups = (sys.n_sites + group_sites - 1) / group_sites;
+  const int chunk_sites = std::min(group_sites, kCdcMaxChunkSites);
   const size_t smem = cdc_smem_layout(chunk_sites, sys.site_cap, nullptr, nullptr);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem);
   if (per_sm < 1) per_sm = 1;
-  const int n_items = tiles * n_frames * n_chunks;
+  const int n_items = tiles * n_frames * n_groups;
   int grid = sm_count * per_sm;
   if (grid > n_items) grid = n_items;
   kern<<<grid, kTileThreads, smem, st>>>(xyz8, sites, sys.kq, sys.col, acc, sys.n_pad, tiles, n_items, sys.n_sites,
-                                         sys.site_cap, sys.num_tot, n_chunks, chunk_sites);
+                                         sys.site_cap, sys.num_tot, n_groups, group_sites, chunk_sites);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -16,24 +16,24 @@ struct Data {
 };
 
 template <int MB, int UN, int ST, int FL = 0>
-double run(const Data& d, const char* name, int sm_count, double* checksum, int chunk_sites = 24) {
+double run(const Data& d, const char* name, int sm_count, double* checksum, int group_sites = 24, int chunk_sites = 8) {
   auto kern = cdc_kernel<MB, UN, ST, FL>;
   size_t smem = cdc_smem_layout(chunk_sites, d.P, nullptr, nullptr);
-  int n_chunks = (d.S + chunk_sites - 1) / chunk_sites;
+  int n_groups = (d.S + group_sites - 1) / group_sites;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem));
   cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
-  int tiles = d.n_pad / kTileAtoms, items = tiles * d.F * n_chunks;
+  int tiles = d.n_pad / kTileAtoms, items = tiles * d.F * n_groups;
   int grid = std::min(items, sm_count * per_sm);
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaMemset(d.acc, 0, sizeof(double) * (size_t)d.F * d.S * d.G));
-  for (int i = 0; i < 2; i++) kern<<<grid, kTileThreads, smem>>>(d.xyz8, d.sites, d.kq, d.col, d.acc, d.n_pad, tiles, items, d.S, d.P, d.G, n_chunks, chunk_sites);
+  for (int i = 0; i < 2; i++) kern<<<grid, kTileThreads, smem>>>(d.xyz8, d.sites, d.kq, d.col, d.acc, d.n_pad, tiles, items, d.S, d.P, d.G, n_groups, group_sites, chunk_sites);
   CK(cudaDeviceSynchronize());
   CK(cudaMemset(d.acc, 0, sizeof(double) * (size_t)d.F * d.S * d.G));
   const int reps = 5;
   CK(cudaEventRecord(e0));
-  for (int i = 0; i < reps; i++) kern<<<grid, kTileThreads, smem>>>(d.xyz8, d.sites, d.kq, d.col, d.acc, d.n_pad, tiles, items, d.S, d.P, d.G, n_chunks, chunk_sites);
+  for (int i = 0; i < reps; i++) kern<<<grid, kTileThreads, smem>>>(d.xyz8, d.sites, d.kq, d.col, d.acc, d.n_pad, tiles, items, d.S, d.P, d.G, n_groups, group_sites, chunk_sites);
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
@@ -43,7 +43,7 @@ double run(const Data& d, const char* name, int sm_count, double* checksum, int 
   *checksum = cs / reps;
   double pairs = (double)d.F * d.S * d.P * (d.N - 140);
   double gp = pairs / ms / 1e6;
-  printf("chunk %2d %-28s regs %3d occ %d grid %4d  %8.3f ms  %8.1f Gpairs/s  frac(16/clk@1.965) %.3f  checksum %.9e\n", chunk_sites, name, fa.numRegs, per_sm, grid, ms, gp, gp / 4653.1, *checksum);
+  printf("group %2d chunk %2d %-28s regs %3d occ %d grid %4d  %8.3f ms  %8.1f Gpairs/s  frac(16/clk@1.965) %.3f  checksum %.9e\n", group_sites, chunk_sites, name, fa.numRegs, per_sm, grid, ms, gp, gp / 4653.1, *checksum);
   return ms;
 }
 
@@ -83,11 +83,12 @@ int main(int argc, char** argv) {
   double cs_;
   int sm = prop.multiProcessorCount;
 #define RUN(MB, UN, SW) run<MB, UN, SW>(d, "minb" #MB " unroll" #UN " swp" #SW, sm, &cs)
-  for (int cs : {8}) {
-    run<2, 21, 3, 0>(d, "swp3 unroll21 deferred", sm, &cs_, cs);
-    run<2, 7, 3, 0>(d, "swp3 unroll7 deferred", sm, &cs_, cs);
-    run<2, 14, 3, 0>(d, "swp3 unroll14 deferred", sm, &cs_, cs);
-    run<2, 21, 3, 1>(d, "swp3 unroll21 NO-EPILOGUE", sm, &cs_, cs);
+  for (int gs : {24, 12, 8}) {
+    run<2, 7, 3, 0>(d, "swp3 unroll7 deferred", sm, &cs_, gs, 8);
+    run<2, 21, 3, 0>(d, "swp3 unroll21 deferred", sm, &cs_, gs, 8);
   }
+  run<2, 7, 3, 0>(d, "swp3 unroll7 deferred", sm, &cs_, 24, 6);
+  run<2, 7, 3, 0>(d, "swp3 unroll7 deferred", sm, &cs_, 24, 4);
+  run<2, 7, 3, 1>(d, "swp3 unroll7 NO-EPILOGUE", sm, &cs_, 24, 8);
   return 0;
 }
