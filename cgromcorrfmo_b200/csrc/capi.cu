@@ -69,7 +69,6 @@ struct cgc_context {
   int64_t nbytes = 0;
   bool mapped = false;
   int fd = -1;              // the trajectory file, kept open for threaded pread() into the pinned staging buffers
-  bool registered = false;  // text is page-locked for the device (cudaHostRegister): H2D straight from it
   FrameLayout L;
   std::vector<FrameSpan> frames;  // frames located so far
   bool index_complete = false;
@@ -118,8 +117,6 @@ struct cgc_context {
 namespace {
 
 void release_text(cgc_context* c) {
-  if (c->registered && c->text) cudaHostUnregister((void*)c->text);
-  c->registered = false;
   if (c->mapped && c->text) munmap((void*)c->text, (size_t)c->nbytes);
   if (c->fd >= 0) close(c->fd);
   c->fd = -1;

@@ -17,6 +17,18 @@
 
 namespace cgc {
 
+// cudaFuncSetAttribute is per device: remember, per device, the largest dynamic shared memory size already granted.
+template <typename K>
+static void ensure_dynamic_smem(K kernel, size_t bytes, size_t* granted /* [16] */) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 15;
+  if (bytes > 48 * 1024 && bytes > granted[dev]) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    granted[dev] = bytes;
+  }
+}
+
 // The neutral padding entry of a site block: dQ = 0 at a far-away point (stored negated), so it adds exactly 0.
 #define CGC_PAD_NEG_COORD 1.0e6f
 
@@ -184,11 +196,8 @@ void launch_decode(const DeviceSystem& sys, const char* text, int64_t text_bytes
   size_t smem = (size_t)kDecodeThreads * sys.line_bytes + 32;
   const bool std_layout = sys.field_w == 8 && sys.ndec == 3;
   auto kern = std_layout ? decode_kernel<true> : decode_kernel<false>;
-  static size_t configured[2] = {0, 0};
-  if (smem > 48 * 1024 && smem > configured[std_layout]) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured[std_layout] = smem;
-  }
+  static size_t granted[2][16] = {};
+  ensure_dynamic_smem(kern, smem, granted[std_layout]);
   kern<<<grid, kDecodeThreads, smem, st>>>(text, text_bytes, atoms_off, sys.n_atoms, sys.n_pad, sys.line_bytes,
                                                     sys.x_col, sys.field_w, sys.ndec, sys.slot, sys.slot_dq,
                                                     sys.n_sites * sys.site_cap, xyz8, sites, err_flags);
@@ -221,11 +230,8 @@ void launch_cdc(const DeviceSystem& sys, const float* xyz8, const float4* sites,
   const int tiles = sys.n_pad / kTileAtoms;
   if (tiles * n_frames == 0) return;
   auto kern = cdc_kernel<kCdcMinBlocks, kCdcUnroll, kCdcStages>;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
-  }
+  static size_t granted[16] = {};
+  ensure_dynamic_smem(kern, 200 * 1024, granted);
   int per_sm = kCdcMinBlocks;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, cdc_smem_bytes(sys));
   if (per_sm < 1) per_sm = 1;

@@ -476,3 +476,40 @@ def test_two_rank_sharding_emulated_on_one_gpu(small_inputs, oracle_mod, capi_mo
         # the device stores the upper block-triangle (64x64 blocks); G < 64 here, so the whole matrix is one block
         ok = scale[k] > 0
         assert np.all(np.abs(cov[k] - c64[k])[ok] <= COV_TOL * scale[k][ok])
+
+
+def test_device_entry_points_reject_bad_arguments(small_inputs, capi_mod, torch_cuda):
+    capi, torch = capi_mod, torch_cuda
+    traj, top, itp, frames = small_inputs("tiny")
+    with capi.Context(top, itp, 0) as c:
+        d = torch.zeros(1024, dtype=torch.uint8, device="cuda")
+        out = torch.zeros(16, dtype=torch.float32, device="cuda")
+        with pytest.raises(capi.CgcError) as e:           # no trajectory opened yet
+            c.run_device(d.data_ptr(), 1024, [0], 1, out.data_ptr())
+        assert e.value.code == capi.CGC_ERR_STATE
+        c.open(traj)
+        with pytest.raises(capi.CgcError) as e:           # text pointer must be 16-byte aligned (bulk TMA source)
+            c.run_device(d.data_ptr() + 4, 1000, [0], 1, out.data_ptr())
+        assert e.value.code == capi.CGC_ERR_ARG
+        with pytest.raises(capi.CgcError) as e:
+            c.run_device(d.data_ptr(), 1024, [0], 0, out.data_ptr())
+        assert e.value.code == capi.CGC_ERR_ARG
+        with pytest.raises(capi.CgcError) as e:
+            c.run(-1, 2)
+        assert e.value.code == capi.CGC_ERR_ARG
+
+
+def test_kernel_timing_hook(small_inputs, capi_mod):
+    """Option "profile": CUDA events around every hot-path launch, as bench.py uses for the per-kernel rooflines."""
+    capi = capi_mod
+    traj, top, itp, frames = small_inputs("tiny")
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        c.set_option("profile", 1)
+        n0 = c.launch_count
+        c.run(0, frames)
+        kt = c.kernel_times(reset=True)
+        assert kt["decode"][1] == 1 and kt["cdc"][1] == 1 and kt["finish"][1] == 1 and kt["cov"][1] == 1
+        assert all(ms > 0 for ms, _ in kt.values())
+        assert c.launch_count - n0 >= 5
+        assert c.kernel_times()["cdc"] == (0.0, 0)
