@@ -513,3 +513,35 @@ def test_kernel_timing_hook(small_inputs, capi_mod):
         assert all(ms > 0 for ms, _ in kt.values())
         assert c.launch_count - n0 >= 5
         assert c.kernel_times()["cdc"] == (0.0, 0)
+
+
+def test_c1_shape_against_the_stock_reference_program(tmp_path, oracle_mod, capi_mod):
+    """BASELINE.json configs[0]: the monomer shape (30 000 atoms, 7 BCL) that the UNMODIFIED reference program can run as
+    is.  Its .time text (7 sites, 6 printed digits) against the CLI driver's, three frames; group ids bit-exact."""
+    import subprocess
+    from cgromcorrfmo_b200 import build, synth
+    O = oracle_mod
+    if not O.have_ref():
+        pytest.skip("oracle/_ref (the compiled reference) is not on this box")
+    s = synth.named_system("C1")
+    frames = 3
+    traj, top, itp = synth.write_inputs(str(tmp_path / "c1"), s, frames)
+    assert O.run_ref_cli(traj, top, itp, str(tmp_path / "ref"), frames, timeout=900) == 0
+    r = subprocess.run([build.CLI, traj, top, itp, str(tmp_path / "ours"), str(frames)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ref_rows = np.array([[float(v) for v in ln.split(",")] for ln in open(tmp_path / "ref.time").read().strip().split("\n")])
+    our_rows = np.array([[float(v) for v in ln.split(",")] for ln in open(tmp_path / "ours.time").read().strip().split("\n")])
+    assert ref_rows.shape == our_rows.shape == (frames * 7, ref_rows.shape[1])
+    # the cancellation scale of every entry, from the oracle (frame 0 only: one frame of 30k atoms x 7 sites is seconds)
+    one = str(tmp_path / "one.gro")
+    first = open(traj, "rb").read()
+    open(one, "wb").write(first[: len(first) // frames])
+    o = O.run(one, top, itp, 1)
+    with capi_mod.Context(top, itp, 0) as c:
+        c.open(traj)
+        assert np.array_equal(c.groups(), o["groups"])
+    scale = o["scale"][0] * 349.7
+    # both files print 6 significant digits; the reference's own float32 noise is ~1e-7 of the scale
+    tol = 1.3e-6 * np.tile(scale, (frames, 1)) * 1.5 + 1.2e-5 * np.abs(ref_rows)
+    assert np.all(np.abs(our_rows - ref_rows) <= tol)
+    assert np.all(our_rows[np.tile(scale, (frames, 1)) == 0] == 0)
