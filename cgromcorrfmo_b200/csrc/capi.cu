@@ -273,6 +273,7 @@ void build_static(cgc_context* c) {
   }
   int P = 1;
   for (int s = 0; s < sys.n_sites; s++) P = std::max(P, count[s]);
+  P = cdc_pad_site_cap(P);
   sys.site_cap = P;
   if (cdc_smem_bytes(sys) > 200 * 1024) {
     throw Unsupported("site block (sites x dQ atoms x 16 B, double buffered) exceeds shared memory; lower the \"sites\" option");

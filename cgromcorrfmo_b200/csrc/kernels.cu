@@ -206,46 +206,54 @@ void launch_decode(const DeviceSystem& sys, const char* text, int64_t text_bytes
 // ---------------------------------------------------------------------------------------------------------------------
 // K2  CDC pair kernel: see cdc_kernel.cuh
 // ---------------------------------------------------------------------------------------------------------------------
-// Sites per work item.  All sites in one item when the launch has plenty of items (the thread's atoms, columns and
-// charges are then loaded once per frame and tile); fewer — down to 2 — when a launch is small, so that even a single
-// frame fills the machine.  Inside an item the sites go through shared memory in chunks of kCdcMaxChunkSites.
-static int cdc_group_sites(const DeviceSystem& sys, int n_frames, int resident_ctas) {
-  const int tiles = sys.n_pad / kTileAtoms;
-  int best = sys.n_sites;
-  for (int gs = sys.n_sites; gs >= 1; gs--) {
-    const int groups = (sys.n_sites + gs - 1) / gs;
-    best = gs;
-    if ((long long)tiles * n_frames * groups >= 16LL * resident_ctas) break;
-    if (gs <= 2) break;
-  }
-  return best;
+// Sites per work unit (chunk): 8 when the launch has plenty of units, fewer — down to 1 — when it is small, so that even
+// a single frame gives every resident CTA a few units.
+static int cdc_chunk_sites(const DeviceSystem& sys, int n_frames, int resident_ctas) {
+  const long long items = (long long)(sys.n_pad / kTileAtoms) * n_frames;
+  int cs = std::min(sys.n_sites, kCdcMaxChunkSites);
+  while (cs > 1 && items * ((sys.n_sites + cs - 1) / cs) < 8LL * resident_ctas) cs--;
+  return cs;
 }
 
 size_t cdc_smem_bytes(const DeviceSystem& sys) {
-  return cdc_smem_layout(std::min(sys.n_sites, kCdcMaxChunkSites), sys.site_cap, nullptr, nullptr);
+  return cdc_smem_layout(std::min(sys.n_sites, kCdcMaxChunkSites), sys.site_cap, nullptr);
 }
 
-void launch_cdc(const DeviceSystem& sys, const float* xyz8, const float4* sites, double* acc, int n_frames,
-                int sm_count, cudaStream_t st) {
+// dQ atoms per site as the kernel wants them: at least 2 (the carried pipeline peels two entries), and P - 2 a multiple
+// of 7 so that the unrolled main loop covers every entry (pads are neutral: dQ = 0 at a far-away point).
+int cdc_pad_site_cap(int p) {
+  if (p < 2) p = 2;
+  return 2 + (p - 2 + 6) / 7 * 7;
+}
+
+template <int kUnroll>
+static void launch_cdc_t(const DeviceSystem& sys, const float* xyz8, const float4* sites, double* acc, int n_frames,
+                         int sm_count, cudaStream_t st) {
   const int tiles = sys.n_pad / kTileAtoms;
-  if (tiles * n_frames == 0) return;
-  auto kern = cdc_kernel<kCdcMinBlocks, kCdcUnroll, kCdcStages>;
+  auto kern = cdc_kernel<kCdcMinBlocks, kUnroll>;
   static size_t granted[16] = {};
   ensure_dynamic_smem(kern, 200 * 1024, granted);
   int per_sm = kCdcMinBlocks;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, cdc_smem_bytes(sys));
   if (per_sm < 1) per_sm = 1;
-  const int group_sites = cdc_group_sites(sys, n_frames, sm_count * per_sm);
-  const int n_groups = (sys.n_sites + group_sites - 1) / group_sites;
-  const int chunk_sites = std::min(group_sites, kCdcMaxChunkSites);
-  const size_t smem = cdc_smem_layout(chunk_sites, sys.site_cap, nullptr, nullptr);
+  const int chunk_sites = cdc_chunk_sites(sys, n_frames, sm_count * per_sm);
+  const int chunks_per_item = (sys.n_sites + chunk_sites - 1) / chunk_sites;
+  const size_t smem = cdc_smem_layout(chunk_sites, sys.site_cap, nullptr);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem);
   if (per_sm < 1) per_sm = 1;
-  const int n_items = tiles * n_frames * n_groups;
-  int grid = sm_count * per_sm;
-  if (grid > n_items) grid = n_items;
-  kern<<<grid, kTileThreads, smem, st>>>(xyz8, sites, sys.kq, sys.col, acc, sys.n_pad, tiles, n_items, sys.n_sites,
-                                         sys.site_cap, sys.num_tot, n_groups, group_sites, chunk_sites);
+  const long long n_units = (long long)tiles * n_frames * chunks_per_item;
+  long long grid = (long long)sm_count * per_sm;
+  if (grid > n_units) grid = n_units;
+  kern<<<(unsigned)grid, kTileThreads, smem, st>>>(xyz8, sites, sys.kq, sys.col, acc, sys.n_pad, tiles, n_units,
+                                                   sys.n_sites, sys.site_cap, sys.num_tot, chunk_sites, chunks_per_item);
+}
+
+void launch_cdc(const DeviceSystem& sys, const float* xyz8, const float4* sites, double* acc, int n_frames,
+                int sm_count, cudaStream_t st) {
+  if (sys.n_pad / kTileAtoms * n_frames == 0 || sys.n_sites == 0) return;
+  // 42 site atoms per trip when that divides P - 2 (the 44 dQ atoms of a BCL), else 7 (cdc_pad_site_cap)
+  if ((sys.site_cap - 2) % 42 == 0) launch_cdc_t<42>(sys, xyz8, sites, acc, n_frames, sm_count, st);
+  else launch_cdc_t<7>(sys, xyz8, sites, acc, n_frames, sm_count, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

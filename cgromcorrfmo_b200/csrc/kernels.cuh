@@ -45,6 +45,7 @@ void launch_init_sites(const DeviceSystem& sys, float4* sites, int n_frames, cud
 void launch_cdc(const DeviceSystem& sys, const float* xyz8, const float4* sites, double* acc, int n_frames,
                 int sm_count, cudaStream_t st);
 size_t cdc_smem_bytes(const DeviceSystem& sys);
+int cdc_pad_site_cap(int p);  // dQ atoms per site, padded to what the kernel's loop structure wants
 
 // acc (double) -> dE (float32), and re-zero acc for the next batch.
 void launch_finish(double* acc, float* dE, int64_t n, cudaStream_t st);

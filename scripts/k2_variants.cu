@@ -15,35 +15,36 @@ struct Data {
   float* xyz8; float4* sites; double* kq; int* col; double* acc;
 };
 
-template <int MB, int UN, int ST, int FL = 0>
-double run(const Data& d, const char* name, int sm_count, double* checksum, int group_sites = 24, int chunk_sites = 8) {
-  auto kern = cdc_kernel<MB, UN, ST, FL>;
-  size_t smem = cdc_smem_layout(chunk_sites, d.P, nullptr, nullptr);
-  int n_groups = (d.S + group_sites - 1) / group_sites;
+template <int MB, int UN, int FL = 0>
+double run(const Data& d, const char* name, int sm_count, double* checksum, int chunk_sites = 8) {
+  auto kern = cdc_kernel<MB, UN, FL>;
+  size_t smem = cdc_smem_layout(chunk_sites, d.P, nullptr);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem));
   cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
-  int tiles = d.n_pad / kTileAtoms, items = tiles * d.F * n_groups;
-  int grid = std::min(items, sm_count * per_sm);
+  int tiles = d.n_pad / kTileAtoms, cpi = (d.S + chunk_sites - 1) / chunk_sites;
+  long long units = (long long)tiles * d.F * cpi;
+  int grid = (int)std::min<long long>(units, sm_count * per_sm);
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  auto launch = [&]() { kern<<<grid, kTileThreads, smem>>>(d.xyz8, d.sites, d.kq, d.col, d.acc, d.n_pad, tiles, units, d.S, d.P, d.G, chunk_sites, cpi); };
   CK(cudaMemset(d.acc, 0, sizeof(double) * (size_t)d.F * d.S * d.G));
-  for (int i = 0; i < 2; i++) kern<<<grid, kTileThreads, smem>>>(d.xyz8, d.sites, d.kq, d.col, d.acc, d.n_pad, tiles, items, d.S, d.P, d.G, n_groups, group_sites, chunk_sites);
+  for (int i = 0; i < 2; i++) launch();
   CK(cudaDeviceSynchronize());
   CK(cudaMemset(d.acc, 0, sizeof(double) * (size_t)d.F * d.S * d.G));
   const int reps = 5;
   CK(cudaEventRecord(e0));
-  for (int i = 0; i < reps; i++) kern<<<grid, kTileThreads, smem>>>(d.xyz8, d.sites, d.kq, d.col, d.acc, d.n_pad, tiles, items, d.S, d.P, d.G, n_groups, group_sites, chunk_sites);
+  for (int i = 0; i < reps; i++) launch();
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
-  std::vector<double> h((size_t)d.S * d.G);
+  std::vector<double> h((size_t)d.F * d.S * d.G);
   CK(cudaMemcpy(h.data(), d.acc, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
   double cs = 0; for (double v : h) cs += fabs(v);
   *checksum = cs / reps;
   double pairs = (double)d.F * d.S * d.P * (d.N - 140);
   double gp = pairs / ms / 1e6;
-  printf("group %2d chunk %2d %-28s regs %3d occ %d grid %4d  %8.3f ms  %8.1f Gpairs/s  frac(16/clk@1.965) %.3f  checksum %.9e\n", group_sites, chunk_sites, name, fa.numRegs, per_sm, grid, ms, gp, gp / 4653.1, *checksum);
+  printf("chunk %2d %-25s regs %3d occ %d grid %4d units/CTA %7.2f smem %6zu  %8.3f ms  %8.1f Gpairs/s  frac(16/clk@1.965) %.3f  checksum %.9e\n", chunk_sites, name, fa.numRegs, per_sm, grid, (double)units / grid, smem, ms, gp, gp / 4653.1, *checksum);
   return ms;
 }
 
@@ -82,13 +83,14 @@ int main(int argc, char** argv) {
   printf("%s, %d SMs, F=%d frames, G=%d\n", prop.name, prop.multiProcessorCount, d.F, d.G);
   double cs_;
   int sm = prop.multiProcessorCount;
-#define RUN(MB, UN, SW) run<MB, UN, SW>(d, "minb" #MB " unroll" #UN " swp" #SW, sm, &cs)
-  for (int gs : {24, 12, 8}) {
-    run<2, 7, 3, 0>(d, "swp3 unroll7 deferred", sm, &cs_, gs, 8);
-    run<2, 21, 3, 0>(d, "swp3 unroll21 deferred", sm, &cs_, gs, 8);
+  // reference checksum of the round-1 kernel on the same data (F=128): 2.584917105e+06
+  for (int rep = 0; rep < 2; rep++) {
+    run<2, 42, 2>(d, "unroll42 F2F", sm, &cs_, 8);
+    run<2, 42, 6>(d, "unroll42 F2F kq-reload", sm, &cs_, 8);
+    run<2, 42, 4>(d, "unroll42 int kq-reload", sm, &cs_, 8);
+    run<2, 21, 6>(d, "unroll21 F2F kq-reload", sm, &cs_, 8);
+    run<2, 14, 6>(d, "unroll14 F2F kq-reload", sm, &cs_, 8);
+    run<2, 42, 1>(d, "unroll42 NO-EPILOGUE", sm, &cs_, 8);
   }
-  run<2, 7, 3, 0>(d, "swp3 unroll7 deferred", sm, &cs_, 24, 6);
-  run<2, 7, 3, 0>(d, "swp3 unroll7 deferred", sm, &cs_, 24, 4);
-  run<2, 7, 3, 1>(d, "swp3 unroll7 NO-EPILOGUE", sm, &cs_, 24, 8);
   return 0;
 }
