@@ -59,29 +59,36 @@ __device__ __forceinline__ float parse_field(const unsigned char* s, int w, int 
 }
 
 // Fast path for the standard GROMACS layout "%8.3f": the 24 coordinate bytes are fetched as aligned 32-bit words,
-// realigned with PRMT, and each field is converted with SWAR arithmetic — digit bytes are 0x3X, every other legal byte
-// (' ', '-', '.') is 0x2X, so ((w >> 4) & 1) * 0x0F masks the digits, and two multiply-adds fold 4 digit bytes into a
-// number.  ~150 instructions per atom instead of ~750 for the byte loop (ncu: the byte loop was issue-bound at 84 %).
-__device__ __forceinline__ unsigned swar4(unsigned d) {   // bytes c0 c1 c2 c3 (c0 lowest, most significant digit)
-  const unsigned p = (d & 0x00FF00FFu) * 10u + ((d >> 8) & 0x00FF00FFu);   // (c0*10+c1) | (c2*10+c3) << 16
-  return (p & 0xFFFFu) * 100u + (p >> 16);
+// realigned with PRMT, and each field is converted with SWAR arithmetic.  A legal field is blanks, an optional '-',
+// up to four digits (word lo), then '.', three digits (word hi): digit bytes are 0x3X, ' ' and '-' are 0x20 / 0x2D.
+// ~25 instructions per field for the value + ~10 for the validation (first version, byte loop: ~250 per field; ncu
+// showed the kernel issue-bound).
+__device__ __forceinline__ unsigned swar4(unsigned d) {   // digit values c0 c1 c2 c3 (c0 lowest byte, most significant)
+  const unsigned p = (d * 10u + (d >> 8)) & 0x00FF00FFu;  // (c0*10+c1) | (c2*10+c3) << 16
+  return (p * 0x00640001u) >> 16;                         // 100*(c0*10+c1) + (c2*10+c3): no carries, both halves <= 99
 }
-__device__ __forceinline__ float parse_field_8_3(unsigned lo, unsigned hi, int& err) {
-  const unsigned mlo = ((lo >> 4) & 0x01010101u) * 0x0Fu, mhi = ((hi >> 4) & 0x01010101u) * 0x0Fu;
-  const unsigned dlo = lo & mlo, dhi = hi & mhi;
-  const unsigned n = swar4(dlo) * 1000u + swar4(dhi);        // hi: '.', c5, c6, c7 -> c5*100 + c6*10 + c7
-  // validation: every byte 0x2X or 0x3X; digits <= 9; non-digits are ' ' or '-' (a few other 0x2X bytes slip through)
-  unsigned bad = ((lo & 0xE0E0E0E0u) ^ 0x20202020u) | ((hi & 0xE0E0E0E0u) ^ 0x20202020u);
-  bad |= ((dlo + 0x06060606u) | (dhi + 0x06060606u)) & 0x10101010u;
-  const unsigned Mlo = mlo | (mlo << 4), Mhi = mhi | (mhi << 4);
-  const unsigned ylo = (lo & ~Mlo) & 0x1F1F1F1Fu, yhi = ((hi & ~Mhi) & 0x1F1F1F00u);  // low 5 bits of the non-digit bytes
-  bad |= (ylo | yhi) & 0x12121212u;                           // allowed: 0x00 (' '), 0x0D ('-') [+ 0x01,0x04,0x05,0x08,0x09,0x0C]
-  if (bad) err |= kDecBadChar;
-  if ((hi & 0xFFu) != 0x2Eu) err |= kDecBadPoint;
-  const unsigned tl = lo ^ 0x2D2D2D2Du, th = hi ^ 0x2D2D2D2Du;
-  const bool neg = ((((tl - 0x01010101u) & ~tl) | ((th - 0x01010101u) & ~th)) & 0x80808080u) != 0;
-  const float r = __fdiv_rn((float)n, 1000.0f);
-  return neg ? -r : r;
+// N / 1000 rounded once to float32 without the division sequence: q = N*r, q += (N - q*1000)*r with r = RN(1/1000).
+// Equal to __fdiv_rn((float)N, 1000.f) — and to the reference's (float)atof — for EVERY integer N < 2^24
+// (checked exhaustively: oracle/cdc_oracle.c cgo_div1000_mismatches, tests/test_oracle.py).
+__device__ __forceinline__ float div1000(float n) {
+  const float r = 1.0f / 1000.0f;
+  const float q = __fmul_rn(n, r);
+  return __fmaf_rn(__fmaf_rn(-q, 1000.0f, n), r, q);
+}
+__device__ __forceinline__ float parse_field_8_3(unsigned lo, unsigned hi, unsigned& bad) {
+  const unsigned isd = lo & 0x10101010u;           // bit 4: a digit byte
+  const unsigned m = isd - (isd >> 4);             // 0x0F under every digit byte of lo
+  const unsigned t = lo & 0x0F0F0F0Fu;
+  const unsigned dlo = t & m;                      // digit values; blanks and the sign -> 0
+  const unsigned y = t & ~m;                       // low nibbles of the non-digit bytes: 0x0 (' ') or 0xD ('-')
+  const unsigned dhi = hi & 0x0F0F0F00u;           // 0, c5, c6, c7
+  const unsigned n = swar4(dlo) * 1000u + swar4(dhi);
+  // validation: lo bytes 0x2X/0x3X with digits <= 9 and non-digits ' ' or '-' (a few other 0x2X bytes slip through:
+  // those with low nibble 1, 4, 5, 8, 9, C); hi exactly '.', digit, digit, digit
+  bad |= ((lo & 0xE0E0E0E0u) ^ 0x20202020u) | ((dlo + 0x06060606u) & 0x10101010u) | (y & 0x02020202u) |
+         ((hi & 0xF0F0F0FFu) ^ 0x3030302Eu) | ((dhi + 0x06060600u) & 0x10101000u);
+  const float r = div1000((float)n);
+  return y ? -r : r;                               // sign applied last, so "-0.000" keeps its sign bit
 }
 
 template <bool kStd>
@@ -131,9 +138,14 @@ decode_kernel(const char* __restrict__ text, int64_t text_bytes, const int64_t* 
       unsigned u[6];
 #pragma unroll
       for (int i = 0; i < 6; i++) u[i] = __byte_perm(w[i], w[i + 1], sel);
-      out.x = parse_field_8_3(u[0], u[1], err);
-      out.y = parse_field_8_3(u[2], u[3], err);
-      out.z = parse_field_8_3(u[4], u[5], err);
+      unsigned bad = 0;
+      out.x = parse_field_8_3(u[0], u[1], bad);
+      out.y = parse_field_8_3(u[2], u[3], bad);
+      out.z = parse_field_8_3(u[4], u[5], bad);
+      if (bad) {  // rare: say which rule broke
+        const bool point = (u[1] & 0xFFu) != 0x2Eu || (u[3] & 0xFFu) != 0x2Eu || (u[5] & 0xFFu) != 0x2Eu;
+        err |= point ? kDecBadPoint : kDecBadChar;
+      }
     } else {
       float p10f = 1.f;
       double p10d = 1.0;

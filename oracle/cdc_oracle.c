@@ -11,6 +11,7 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library.
  */
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -135,4 +136,37 @@ void oracle_cov_f64(int T, int numTot, const float *X, int ddof, double *mean, d
     double div = (double)(T - ddof);
     for (size_t k = 0; k < (size_t)numTot * numTot; k++) cov[k] /= div;
     free(d);
+}
+
+/* Checker for K1's division-free "%8.3f" conversion: for every integer n in [n_lo, n_hi) (n < 2^24, so (float)n is
+ * exact), compare q + (n - q*1000)*r, q = n*r, r = RN(1/1000) — two fused multiply-adds — with the IEEE quotient
+ * (float)n / 1000.0f, which equals the reference's (float)atof("%d.%03d") (src/grom2atomFMO.cpp:448-450).
+ * Returns the number of mismatching bit patterns. */
+long cgo_div1000_mismatches(unsigned n_lo, unsigned n_hi) {
+  const float r = 1.0f / 1000.0f;
+  long bad = 0;
+  for (unsigned n = n_lo; n < n_hi; n++) {
+    const float nf = (float)n;
+    const float q = nf * r;
+    const float q2 = fmaf(fmaf(-q, 1000.0f, nf), r, q);
+    const float ref = nf / 1000.0f;
+    if (memcmp(&q2, &ref, sizeof(float))) bad++;
+  }
+  return bad;
+}
+
+/* The same quotient against the reference's literal text path: snprintf("%u.%03u") -> atof -> (float). */
+long cgo_div1000_vs_atof_mismatches(unsigned n_lo, unsigned n_hi, unsigned step) {
+  const float r = 1.0f / 1000.0f;
+  long bad = 0;
+  char buf[32];
+  for (unsigned n = n_lo; n < n_hi; n += step) {
+    const float nf = (float)n;
+    const float q = nf * r;
+    const float q2 = fmaf(fmaf(-q, 1000.0f, nf), r, q);
+    snprintf(buf, sizeof buf, "%u.%03u", n / 1000u, n % 1000u);
+    const float ref = (float)atof(buf);
+    if (memcmp(&q2, &ref, sizeof(float))) bad++;
+  }
+  return bad;
 }

@@ -131,3 +131,12 @@ def test_oracle_parse_errors(oracle_mod, tmp_path):
     gro.write_text("title t= 0.0\nnot-a-number\n")
     with pytest.raises(O.InputFileMalformed):
         O.read_frame(str(gro), None)
+
+
+def test_division_free_decode_is_exact(oracle_mod):
+    """K1 converts "%8.3f" text as N * r + (N - q * 1000) * r (two FMAs) instead of dividing: bit-identical to the IEEE
+    quotient for EVERY integer N < 2^24 (a "%8.3f" field holds at most 7 digits: N < 10^7), and to the reference's
+    (float)atof(text) (reference src/grom2atomFMO.cpp:448-450)."""
+    L = oracle_mod.lib()
+    assert L.cgo_div1000_mismatches(0, 1 << 24) == 0
+    assert L.cgo_div1000_vs_atof_mismatches(0, 10_000_000, 7) == 0
