@@ -91,86 +91,125 @@ __device__ __forceinline__ float parse_field_8_3(unsigned lo, unsigned hi, unsig
   return y ? -r : r;                               // sign applied last, so "-0.000" keeps its sign bit
 }
 
+// Persistent CTAs: a CTA strides over the chunks of kDecodeThreads lines; the bulk copy of its next chunk is in flight
+// (second shared-memory buffer) while the current one is parsed, so the HBM read stream does not stop while a CTA computes.
+__host__ __device__ inline uint32_t decode_buf_stride(int line_bytes) {
+  return ((uint32_t)kDecodeThreads * line_bytes + 32u + 127u) & ~127u;
+}
+
 template <bool kStd>
 __global__ void __launch_bounds__(kDecodeThreads)
 decode_kernel(const char* __restrict__ text, int64_t text_bytes, const int64_t* __restrict__ atoms_off, int n_atoms,
               int n_pad, int line_bytes, int x_col, int field_w, int ndec,
               const int32_t* __restrict__ slot, const float* __restrict__ slot_dq, int sites_stride /* float4 per frame */,
-              float* __restrict__ xyz8, float4* __restrict__ sites, int* __restrict__ err_flags) {
+              float* __restrict__ xyz8, float4* __restrict__ sites, int* __restrict__ err_flags, int chunks_per_frame,
+              int n_chunks) {
   extern __shared__ __align__(128) unsigned char sm_raw[];
-  __shared__ __align__(8) uint64_t bar;
-  const int f = blockIdx.y;
-  const int a0 = blockIdx.x * kDecodeThreads;
-  const int a = a0 + threadIdx.x;
-  int n_here = n_atoms - a0;
-  n_here = n_here < 0 ? 0 : (n_here > kDecodeThreads ? kDecodeThreads : n_here);
-  uint32_t head = 0;
-  if (n_here > 0) {
-    const int64_t src = atoms_off[f] + (int64_t)a0 * line_bytes;
-    const int64_t src_al = src & ~(int64_t)15;
-    head = (uint32_t)(src - src_al);
-    int64_t bytes = (int64_t)head + (int64_t)n_here * line_bytes;
-    bytes = (bytes + 15) & ~(int64_t)15;
-    const int64_t lim = ((text_bytes + 15) & ~(int64_t)15) - src_al;  // never read past the (16-byte padded) text
-    if (bytes > lim) bytes = lim;
-    if (threadIdx.x == 0) {
-      mbar_init(&bar, 1);
-      mbar_fence_init();
-      mbar_expect_tx(&bar, (uint32_t)bytes);
-      tma_bulk_g2s(sm_raw, text + src_al, (uint32_t)bytes, &bar);
-    }
-    __syncthreads();  // barrier initialised before anyone polls it
-    mbar_wait(&bar, 0);
+  __shared__ __align__(8) uint64_t bar[2];
+  const uint32_t buf_stride = decode_buf_stride(line_bytes);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
   }
-  if (a >= n_pad) return;
-  float3 out;
-  if (a < n_atoms) {
-    const unsigned char* line = sm_raw + head + threadIdx.x * line_bytes;
-    int err = 0;
-    if constexpr (kStd) {
-      const unsigned char* fld = line + x_col;
-      const unsigned mis = (unsigned)(smem_addr(fld) & 3u);
-      const unsigned* wp = reinterpret_cast<const unsigned*>(fld - mis);
-      unsigned w[7];
+  __syncthreads();
+
+  // chunk -> (frame, first atom, lines present, source range rounded out to 16 bytes)
+  struct Chunk { int f, a0, n_here; uint32_t head, bytes; int64_t src_al; };
+  auto locate = [&](int c) {
+    Chunk k;
+    k.f = c / chunks_per_frame;
+    k.a0 = (c - k.f * chunks_per_frame) * kDecodeThreads;
+    int n_here = n_atoms - k.a0;
+    k.n_here = n_here < 0 ? 0 : (n_here > kDecodeThreads ? kDecodeThreads : n_here);
+    k.head = 0; k.bytes = 0; k.src_al = 0;
+    if (k.n_here > 0) {
+      const int64_t src = atoms_off[k.f] + (int64_t)k.a0 * line_bytes;
+      k.src_al = src & ~(int64_t)15;
+      k.head = (uint32_t)(src - k.src_al);
+      int64_t bytes = (int64_t)k.head + (int64_t)k.n_here * line_bytes;
+      bytes = (bytes + 15) & ~(int64_t)15;
+      const int64_t lim = ((text_bytes + 15) & ~(int64_t)15) - k.src_al;  // never read past the (16-byte padded) text
+      k.bytes = (uint32_t)(bytes > lim ? lim : bytes);
+    }
+    return k;
+  };
+  auto issue = [&](int c, int b) {   // thread 0
+    const Chunk k = locate(c);
+    if (k.n_here > 0) {
+      mbar_expect_tx(&bar[b], k.bytes);
+      tma_bulk_g2s(sm_raw + b * buf_stride, text + k.src_al, k.bytes, &bar[b]);
+    }
+  };
+
+  int c = blockIdx.x;
+  if (c >= n_chunks) return;
+  if (threadIdx.x == 0) issue(c, 0);
+  uint32_t phase_bits = 0;
+  for (int i = 0; c < n_chunks; c += gridDim.x, i++) {
+    const int b = i & 1;
+    // the other buffer was last read one iteration ago; the __syncthreads that ended that iteration orders those
+    // reads before this copy
+    if (threadIdx.x == 0 && c + (int)gridDim.x < n_chunks) issue(c + gridDim.x, b ^ 1);
+    const Chunk k = locate(c);
+    if (k.n_here > 0) {
+      mbar_wait(&bar[b], (phase_bits >> b) & 1u);
+      phase_bits ^= 1u << b;
+    }
+    const int f = k.f;
+    const int a = k.a0 + threadIdx.x;
+    if (a < n_pad) {
+      float3 out;
+      if (a < n_atoms) {
+        const unsigned char* line = sm_raw + b * buf_stride + k.head + threadIdx.x * line_bytes;
+        int err = 0;
+        if constexpr (kStd) {
+          const unsigned char* fld = line + x_col;
+          const unsigned mis = (unsigned)(smem_addr(fld) & 3u);
+          const unsigned* wp = reinterpret_cast<const unsigned*>(fld - mis);
+          unsigned w[7];
 #pragma unroll
-      for (int i = 0; i < 7; i++) w[i] = wp[i];
-      const unsigned sel = 0x3210u + 0x1111u * mis;
-      unsigned u[6];
+          for (int j = 0; j < 7; j++) w[j] = wp[j];
+          const unsigned sel = 0x3210u + 0x1111u * mis;
+          unsigned u[6];
 #pragma unroll
-      for (int i = 0; i < 6; i++) u[i] = __byte_perm(w[i], w[i + 1], sel);
-      unsigned bad = 0;
-      out.x = parse_field_8_3(u[0], u[1], bad);
-      out.y = parse_field_8_3(u[2], u[3], bad);
-      out.z = parse_field_8_3(u[4], u[5], bad);
-      if (bad) {  // rare: say which rule broke
-        const bool point = (u[1] & 0xFFu) != 0x2Eu || (u[3] & 0xFFu) != 0x2Eu || (u[5] & 0xFFu) != 0x2Eu;
-        err |= point ? kDecBadPoint : kDecBadChar;
+          for (int j = 0; j < 6; j++) u[j] = __byte_perm(w[j], w[j + 1], sel);
+          unsigned bad = 0;
+          out.x = parse_field_8_3(u[0], u[1], bad);
+          out.y = parse_field_8_3(u[2], u[3], bad);
+          out.z = parse_field_8_3(u[4], u[5], bad);
+          if (bad) {  // rare: say which rule broke
+            const bool point = (u[1] & 0xFFu) != 0x2Eu || (u[3] & 0xFFu) != 0x2Eu || (u[5] & 0xFFu) != 0x2Eu;
+            err |= point ? kDecBadPoint : kDecBadChar;
+          }
+        } else {
+          float p10f = 1.f;
+          double p10d = 1.0;
+          for (int q = 0; q < ndec; q++) { p10f *= 10.f; p10d *= 10.0; }
+          const bool wide = field_w > 8;  // more than 7 digits could exceed 2^24
+          out.x = parse_field(line + x_col, field_w, ndec, p10f, p10d, wide, err);
+          out.y = parse_field(line + x_col + field_w, field_w, ndec, p10f, p10d, wide, err);
+          out.z = parse_field(line + x_col + 2 * field_w, field_w, ndec, p10f, p10d, wide, err);
+        }
+        const bool last_unterminated = (atoms_off[f] + (int64_t)(a + 1) * line_bytes - 1) >= text_bytes;
+        if (!last_unterminated && line[line_bytes - 1] != '\n') err |= kDecBadNewline;
+        if (err) atomicOr(err_flags, err);
+        const int sl = slot[a];
+        if (sl >= 0) {
+          // site block entry for the pair loop: negated coordinates (so dx = x + (-xc) is one FADD2) and dQ
+          sites[(size_t)f * sites_stride + sl] = make_float4(-out.x, -out.y, -out.z, slot_dq[sl]);
+        }
+      } else {
+        out = make_float3(0.f, 0.f, 0.f);  // tile padding: its kq is 0 and its column is -1
       }
-    } else {
-      float p10f = 1.f;
-      double p10d = 1.0;
-      for (int k = 0; k < ndec; k++) { p10f *= 10.f; p10d *= 10.0; }
-      const bool wide = field_w > 8;  // more than 7 digits could exceed 2^24
-      out.x = parse_field(line + x_col, field_w, ndec, p10f, p10d, wide, err);
-      out.y = parse_field(line + x_col + field_w, field_w, ndec, p10f, p10d, wide, err);
-      out.z = parse_field(line + x_col + 2 * field_w, field_w, ndec, p10f, p10d, wide, err);
+      // blocks of 8 atoms, SoA inside a block: [x0..x7][y0..y7][z0..z7] — the pair kernel loads these as packed f32x2
+      float* dst = xyz8 + ((size_t)f * n_pad + (size_t)(a & ~7)) * 3 + (a & 7);
+      dst[0] = out.x;
+      dst[8] = out.y;
+      dst[16] = out.z;
     }
-    const bool last_unterminated = (atoms_off[f] + (int64_t)(a + 1) * line_bytes - 1) >= text_bytes;
-    if (!last_unterminated && line[line_bytes - 1] != '\n') err |= kDecBadNewline;
-    if (err) atomicOr(err_flags, err);
-    const int sl = slot[a];
-    if (sl >= 0) {
-      // site block entry for the pair loop: negated coordinates (so dx = x + (-xc) is one FADD2) and dQ
-      sites[(size_t)f * sites_stride + sl] = make_float4(-out.x, -out.y, -out.z, slot_dq[sl]);
-    }
-  } else {
-    out = make_float3(0.f, 0.f, 0.f);  // tile padding: its kq is 0 and its column is -1
+    __syncthreads();  // everyone is done with buffer b before the copy two chunks ahead overwrites it
   }
-  // blocks of 8 atoms, SoA inside a block: [x0..x7][y0..y7][z0..z7] — the pair kernel loads these as packed f32x2
-  float* dst = xyz8 + ((size_t)f * n_pad + (size_t)(a & ~7)) * 3 + (a & 7);
-  dst[0] = out.x;
-  dst[8] = out.y;
-  dst[16] = out.z;
 }
 
 // xyz8 blocks -> plain [frame][atom][3] (only used by the decode-parity entry point)
@@ -204,15 +243,24 @@ void launch_init_sites(const DeviceSystem& sys, float4* sites, int n_frames, cud
 
 void launch_decode(const DeviceSystem& sys, const char* text, int64_t text_bytes, const int64_t* atoms_off,
                    int n_frames, float* xyz8, float4* sites, int* err_flags, cudaStream_t st) {
-  dim3 grid((sys.n_pad + kDecodeThreads - 1) / kDecodeThreads, n_frames);
-  size_t smem = (size_t)kDecodeThreads * sys.line_bytes + 32;
+  const int chunks_per_frame = (sys.n_pad + kDecodeThreads - 1) / kDecodeThreads;
+  const long long n_chunks = (long long)chunks_per_frame * n_frames;
+  if (n_chunks == 0) return;
+  const size_t smem = 2 * (size_t)decode_buf_stride(sys.line_bytes);
   const bool std_layout = sys.field_w == 8 && sys.ndec == 3;
   auto kern = std_layout ? decode_kernel<true> : decode_kernel<false>;
   static size_t granted[2][16] = {};
   ensure_dynamic_smem(kern, smem, granted[std_layout]);
-  kern<<<grid, kDecodeThreads, smem, st>>>(text, text_bytes, atoms_off, sys.n_atoms, sys.n_pad, sys.line_bytes,
-                                                    sys.x_col, sys.field_w, sys.ndec, sys.slot, sys.slot_dq,
-                                                    sys.n_sites * sys.site_cap, xyz8, sites, err_flags);
+  int dev = 0, sm_count = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDecodeThreads, smem);
+  if (per_sm < 1) per_sm = 1;
+  const long long grid = std::min<long long>(n_chunks, (long long)sm_count * per_sm);
+  kern<<<(unsigned)grid, kDecodeThreads, smem, st>>>(text, text_bytes, atoms_off, sys.n_atoms, sys.n_pad, sys.line_bytes,
+                                                     sys.x_col, sys.field_w, sys.ndec, sys.slot, sys.slot_dq,
+                                                     sys.n_sites * sys.site_cap, xyz8, sites, err_flags,
+                                                     chunks_per_frame, (int)n_chunks);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
