@@ -81,6 +81,19 @@ def calibrate_fp64_tensor(torch, dev):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
+def calibrate_h2d(torch, host, d_text):
+    """Yard-stick for the end-to-end leg: pinned host -> device copy of the same text buffer, best of 5, GB/s."""
+    best = 1e9
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        d_text.copy_(host, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return host.numel() / (best * 1e-3) / 1e9
+
+
 def cores_available() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -359,7 +372,48 @@ def run_ours(args):
         e2e_value = world * args.steps * F / e2e_s
         e2e_ktimes = ctx.kernel_times(reset=True)
         same = float(np.abs(out_host - d_dE.cpu().numpy()).max())
+        h2d_peak = calibrate_h2d(torch, host, d_text)
         ctx.close()
+
+        # ---------------- the same frames as a GROMACS .trr (single precision, coordinates + box): 12 B/atom over PCIe
+        # instead of 45.  Not the headline (the reference reads .gro text); SURVEY.md section 8f-3.
+        from cgromcorrfmo_b200 import synth
+        struct_gro = os.path.join(d, "frame0.gro")
+        with open(struct_gro, "wb") as fh:
+            fh.write(bytes(text[:frame_bytes]))
+        trr_blob = b"".join(synth.trr_frame_bytes(s, rank * F + f) for f in range(F))
+        n_trr = len(trr_blob)
+        host_trr = torch.empty(n_trr + 64, dtype=torch.uint8).pin_memory()
+        host_trr[:n_trr] = torch.from_numpy(np.frombuffer(trr_blob, dtype=np.uint8).copy())
+        host_trr[n_trr:] = 0
+        del trr_blob
+        ctx2 = capi.Context(top, itp, local)
+        ctx2.open_memory_trr((host_trr.data_ptr(), n_trr), struct_gro)
+        ctx2.set_option("batch_frames", args.e2e_batch)
+        cov2 = torch.zeros(ctx2.cov_size(), dtype=torch.float64, device=dev)
+        ctx2.cov_bind(cov2.data_ptr())
+        ctx2.cov_set_shift_device(row0.data_ptr(), stream)            # the same shift on every rank, as above
+        out_trr = np.empty((F, S, G), dtype=np.float32)
+        for _ in range(max(3, args.warmup)):
+            ctx2.run(0, F, out=out_trr)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            ctx2.run(0, F, out=out_trr)
+        if world > 1:
+            cdist.allreduce_partials(cov2, S, G)
+        e1.record()
+        barrier()
+        trr_s = max(time.perf_counter() - t0, e0.elapsed_time(e1) / 1e3)
+        if world > 1:
+            t = torch.tensor([trr_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            trr_s = float(t.item())
+        trr_value = world * args.steps * F / trr_s
+        trr_same = float(np.abs(out_trr.astype(np.float64) - out_host.astype(np.float64)).max())
+        trr_scale = float(np.abs(out_host).max())
+        ctx2.close()
         fp64_peak = calibrate_fp64_tensor(torch, dev) if rank == 0 else None
 
     if rank != 0:
@@ -426,7 +480,15 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_text + 8 * F), "d2h_bytes_per_step": int(F * S * G * 4),
                 "api": "cgc_run (C-ABI) on pinned host text, %d-frame batches double-buffered; dE rows copied back to host" % args.e2e_batch,
-                "max_abs_diff_vs_device_path": same},
+                "max_abs_diff_vs_device_path": same,
+                "bound": "PCIe host->device copy of the text", "h2d_gbs": e2e_value / world * frame_bytes / 1e9,
+                "h2d_peak_gbs": h2d_peak, "frac_of_h2d_peak": (e2e_value / world * frame_bytes / 1e9) / h2d_peak,
+                "h2d_peak_source": "pinned cudaMemcpyAsync of the same text buffer, best of 6, measured in this run"},
+        "e2e_trr": {"value": trr_value, "unit": UNIT, "h2d_bytes_per_step": int(n_trr + 8 * F), "d2h_bytes_per_step": int(F * S * G * 4),
+                    "api": "cgc_open_memory_trr + cgc_run on pinned .trr frames (float32 coordinates + box, %d B/frame), %d-frame batches"
+                           % (n_trr // F, args.e2e_batch),
+                    "note": "same frames as the headline; not the reference's input format (it reads .gro text)",
+                    "max_abs_diff_vs_gro_path": trr_same, "max_abs_dE": trr_scale},
         "gpu_launches": int(launches),
         "kernel_ms": {k: v[0] for k, v in ktimes.items()},
         "roofline": roofline, "rooflines_other": others, "cpu_baseline": cpu,

@@ -36,6 +36,8 @@ SIGNATURES = {
     "cgc_topology_warnings": (c_int, [c_void_p]),
     "cgc_open": (c_int, [c_void_p, c_char_p]),
     "cgc_open_memory": (c_int, [c_void_p, c_void_p, c_int64]),
+    "cgc_open_trr": (c_int, [c_void_p, c_char_p, c_char_p]),
+    "cgc_open_memory_trr": (c_int, [c_void_p, c_void_p, c_int64, c_char_p]),
     "cgc_dims": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "cgc_get_groups": (c_int, [c_void_p, c_void_p]),
     "cgc_get_columns": (c_int, [c_void_p, c_void_p]),
@@ -185,6 +187,28 @@ class Context:
             self._keep = arr
             addr, n = arr.ctypes.data, arr.size
         self._check(self._lib.cgc_open_memory(self._h, c_void_p(addr), n))
+        return self
+
+    def open_trr(self, trr_path: str, structure_gro: str):
+        """GROMACS .trr coordinates; names, residues and hence groups/charges from frame 0 of `structure_gro`."""
+        self._keep = None
+        self._check(self._lib.cgc_open_trr(self._h, os.fsencode(trr_path), os.fsencode(structure_gro)))
+        return self
+
+    def open_memory_trr(self, data, structure_gro: str):
+        """data: bytes / numpy uint8 array / (address, nbytes) holding .trr frames.  NOT copied; kept alive here."""
+        if isinstance(data, tuple):
+            addr, n = data
+            self._keep = None
+        elif isinstance(data, (bytes, bytearray)):
+            arr = np.frombuffer(data, dtype=np.uint8)
+            self._keep = (data, arr)
+            addr, n = arr.ctypes.data, arr.size
+        else:
+            arr = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+            self._keep = arr
+            addr, n = arr.ctypes.data, arr.size
+        self._check(self._lib.cgc_open_memory_trr(self._h, c_void_p(addr), n, os.fsencode(structure_gro)))
         return self
 
     def dims(self):

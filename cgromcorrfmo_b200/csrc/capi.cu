@@ -73,6 +73,8 @@ struct cgc_context {
   std::vector<FrameSpan> frames;  // frames located so far
   bool index_complete = false;
   bool opened = false;
+  int trr_real = 0;               // 0: .gro text; 4 / 8: .trr with single / double precision coordinates
+  int64_t frame_span_max = 0;     // .trr: largest distance between the coordinate arrays of consecutive frames
 
   // static per-atom data (host copies kept for the getters)
   std::vector<float> q_ground;    // table charge of the atom's own key
@@ -264,6 +266,7 @@ void build_static(cgc_context* c) {
   sys.x_col = L.x_col;
   sys.field_w = L.field_w;
   sys.ndec = L.ndec;
+  sys.traj_mode = c->trr_real == 4 ? 1 : c->trr_real == 8 ? 2 : 0;
   // dQ != 0 atoms of every computed site, in file order (zero-dQ atoms add exactly +-0 to every bin)
   std::vector<int> count(sys.n_sites, 0);
   std::vector<int32_t> slot(sys.n_pad, -1);
@@ -385,7 +388,22 @@ int64_t index_upto(cgc_context* c, int64_t upto) {
     int64_t pos = c->frames.empty() ? 0 : c->frames.back().end;
     FrameSpan sp;
     bool trunc = false;
-    if (!locate_frame(c->text, c->nbytes, pos, c->L.n_atoms, c->L.line_bytes, sp, nullptr, &trunc)) {
+    if (c->trr_real) {
+      TrrFrame tf;
+      if (!locate_trr_frame(c->text, c->nbytes, pos, tf, &trunc)) {
+        c->index_complete = true;
+        break;
+      }
+      if (tf.n_atoms != c->L.n_atoms) {
+        throw InputFileMalformed("Number of atoms changes between frames; the group layout of the structure file no longer applies.");
+      }
+      if (tf.real_bytes != c->trr_real) throw Unsupported(".trr precision changes between frames");
+      sp.begin = tf.begin;
+      sp.atoms = tf.x_off;
+      sp.end = tf.end;
+      if (!c->frames.empty()) c->frame_span_max = std::max(c->frame_span_max, sp.atoms - c->frames.back().atoms);
+      c->frame_span_max = std::max(c->frame_span_max, sp.end - sp.begin);
+    } else if (!locate_frame(c->text, c->nbytes, pos, c->L.n_atoms, c->L.line_bytes, sp, nullptr, &trunc)) {
       c->index_complete = true;
       break;
     }
@@ -521,14 +539,61 @@ void enqueue_compute(cgc_context* c, const char* d_text, int64_t text_bytes, con
   CUDA_OK(cudaGetLastError());
 }
 
-void open_common(cgc_context* c) {
+// A read-only mapping of a whole file, released on scope exit.
+struct MappedFile {
+  const char* p = nullptr;
+  int64_t n = 0;
+  explicit MappedFile(const char* path) {
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) throw ReadError("Open failed on file passed in.");
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || sb.st_size == 0) {
+      close(fd);
+      throw ReadError("file is empty or cannot be stat'ed");
+    }
+    void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) throw ReadError("mmap failed");
+    p = (const char*)m;
+    n = sb.st_size;
+  }
+  ~MappedFile() { if (p) munmap((void*)p, (size_t)n); }
+  MappedFile(const MappedFile&) = delete;
+  MappedFile& operator=(const MappedFile&) = delete;
+};
+
+// structure_gro == nullptr: c->text is .gro text and frame 0 is its own structure.  Otherwise c->text is a .trr and
+// the names, residue numbers and hence groups/keys come from the first frame of the .gro file `structure_gro`.
+void open_common(cgc_context* c, const char* structure_gro = nullptr) {
   c->frames.clear();
   c->index_complete = false;
   c->opened = false;
+  c->trr_real = 0;
+  c->frame_span_max = 0;
   FrameSpan sp;
   c->L = FrameLayout();
-  scan_first_frame(c->text, c->nbytes, c->L, sp);
-  c->frames.push_back(sp);
+  if (structure_gro) {
+    {
+      MappedFile st(structure_gro);
+      scan_first_frame(st.p, st.n, c->L, sp);
+    }
+    TrrFrame tf;
+    bool trunc = false;
+    if (!locate_trr_frame(c->text, c->nbytes, 0, tf, &trunc)) {
+      throw InputFileMalformed(trunc ? "first frame of the .trr trajectory is incomplete" : "empty .trr trajectory");
+    }
+    if (tf.n_atoms != c->L.n_atoms) {
+      throw InputFileMalformed("the structure file has " + std::to_string(c->L.n_atoms) + " atoms, the .trr trajectory " +
+                               std::to_string(tf.n_atoms));
+    }
+    c->trr_real = tf.real_bytes;
+    c->L.line_bytes = 3 * tf.real_bytes;   // one "line" = the coordinates of one atom
+    // the whole index up front (one header per frame): the staging buffers are sized from the largest frame
+    index_upto(c, INT64_MAX - 1);
+  } else {
+    scan_first_frame(c->text, c->nbytes, c->L, sp);
+    c->frames.push_back(sp);
+  }
   resolve_atoms(c);
   c->n_sites = c->L.n_chromo;
   c->cov_opt = -1;
@@ -630,6 +695,45 @@ int cgc_open_memory(cgc_context* ctx, const char* text, int64_t nbytes) {
     // A caller-pinned buffer (cudaHostAlloc / cudaHostRegister / torch pin_memory) is detected in cgc_run and then
     // copied H2D directly, without the pinned staging copy.
     open_common(ctx);
+    return CGC_OK;
+  });
+}
+
+int cgc_open_trr(cgc_context* ctx, const char* trr_path, const char* structure_gro_path) {
+  if (!ctx || !trr_path || !structure_gro_path) return fail(ctx, CGC_ERR_ARG, "null argument");
+  return guarded(ctx, [&]() {
+    if (ctx->device >= 0) { free_pipeline(ctx); }
+    release_text(ctx);
+    int fd = open(trr_path, O_RDONLY);
+    if (fd < 0) throw ReadError("Open failed on file passed in.");
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || sb.st_size == 0) {
+      close(fd);
+      throw ReadError("trajectory file is empty or cannot be stat'ed");
+    }
+    void* p = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (p == MAP_FAILED) {
+      close(fd);
+      throw ReadError("mmap of the trajectory failed");
+    }
+    ctx->text = (const char*)p;
+    ctx->nbytes = sb.st_size;
+    ctx->mapped = true;
+    ctx->fd = fd;
+    open_common(ctx, structure_gro_path);
+    return CGC_OK;
+  });
+}
+
+int cgc_open_memory_trr(cgc_context* ctx, const char* data, int64_t nbytes, const char* structure_gro_path) {
+  if (!ctx || !data || nbytes <= 0 || !structure_gro_path) return fail(ctx, CGC_ERR_ARG, "null or empty argument");
+  return guarded(ctx, [&]() {
+    if (ctx->device >= 0) { free_pipeline(ctx); }
+    release_text(ctx);
+    ctx->text = data;
+    ctx->nbytes = nbytes;
+    ctx->mapped = false;
+    open_common(ctx, structure_gro_path);
     return CGC_OK;
   });
 }
@@ -777,7 +881,7 @@ int cgc_run(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_k
     need_device(ctx);
     const DeviceSystem& sys = ctx->sys;
     const int B = ctx->batch_frames > 0 ? ctx->batch_frames : default_batch(ctx);
-    const int64_t frame_text_max = (int64_t)sys.n_atoms * sys.line_bytes + 4096;
+    const int64_t frame_text_max = std::max<int64_t>((int64_t)sys.n_atoms * sys.line_bytes, ctx->frame_span_max) + 4096;
     // is the text already page-locked (caller-pinned memory given to cgc_open_memory)?
     bool direct = false;
     if (!ctx->mapped) {

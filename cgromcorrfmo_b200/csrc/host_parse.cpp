@@ -385,4 +385,74 @@ void scan_first_frame(const char* text, int64_t nbytes, FrameLayout& L, FrameSpa
   L.n_chromo = -g_minus;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// .trr frame headers
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+inline uint32_t be32(const char* p) {
+  const unsigned char* u = reinterpret_cast<const unsigned char*>(p);
+  return ((uint32_t)u[0] << 24) | ((uint32_t)u[1] << 16) | ((uint32_t)u[2] << 8) | (uint32_t)u[3];
+}
+}  // namespace
+
+bool locate_trr_frame(const char* data, int64_t nbytes, int64_t pos, TrrFrame& out, bool* truncated) {
+  if (truncated) *truncated = false;
+  if (pos >= nbytes) return false;
+  auto cut = [&]() {
+    if (truncated) *truncated = true;
+    return false;
+  };
+  if (pos + 12 > nbytes) return cut();
+  if (be32(data + pos) != 1993u) throw InputFileMalformed("not a .trr frame: magic number 1993 expected");
+  const uint32_t slen = be32(data + pos + 4);     // strlen + 1 as written by GROMACS
+  const uint32_t len = be32(data + pos + 8);      // XDR string length
+  if (len > 64 || slen > 65) throw InputFileMalformed(".trr version string has an impossible length");
+  int64_t p = pos + 12;
+  const int64_t padded = ((int64_t)len + 3) & ~(int64_t)3;
+  if (p + padded + 13 * 4 > nbytes) return cut();
+  if (len != 12 || memcmp(data + p, "GMX_trn_file", 12) != 0) {
+    throw InputFileMalformed(".trr version string is not \"GMX_trn_file\"");
+  }
+  p += padded;
+  int32_t h[13];
+  for (int i = 0; i < 13; i++) h[i] = (int32_t)be32(data + p + 4 * i);
+  p += 13 * 4;
+  const int32_t ir_size = h[0], e_size = h[1], box_size = h[2], vir_size = h[3], pres_size = h[4], top_size = h[5],
+                sym_size = h[6], x_size = h[7], v_size = h[8], f_size = h[9], natoms = h[10], step = h[11];
+  for (int i = 0; i < 10; i++)
+    if (h[i] < 0) throw InputFileMalformed(".trr header holds a negative section size");
+  if (natoms <= 0) throw InputFileMalformed(".trr frame with no atoms");
+  int real_bytes = 0;
+  if (box_size) real_bytes = box_size / 9;
+  else if (x_size) real_bytes = x_size / (3 * natoms);
+  else if (v_size) real_bytes = v_size / (3 * natoms);
+  else if (f_size) real_bytes = f_size / (3 * natoms);
+  if (real_bytes != 4 && real_bytes != 8) throw InputFileMalformed(".trr frame: cannot tell single from double precision");
+  if (x_size == 0) throw Unsupported(".trr frame without coordinates (x_size == 0): write the trajectory with nstxout set");
+  if ((int64_t)x_size != (int64_t)3 * natoms * real_bytes) throw InputFileMalformed(".trr header: x_size does not match natoms");
+  if (p + 2 * real_bytes > nbytes) return cut();
+  if (real_bytes == 4) {
+    uint32_t b = be32(data + p);
+    float t;
+    memcpy(&t, &b, 4);
+    out.time = t;
+  } else {
+    uint64_t b = ((uint64_t)be32(data + p) << 32) | be32(data + p + 4);
+    double t;
+    memcpy(&t, &b, 8);
+    out.time = t;
+  }
+  p += 2 * real_bytes;  // t, lambda
+  p += (int64_t)ir_size + e_size + box_size + vir_size + pres_size + top_size + sym_size;
+  out.begin = pos;
+  out.x_off = p;
+  out.end = p + (int64_t)x_size + v_size + f_size;
+  out.n_atoms = natoms;
+  out.real_bytes = real_bytes;
+  out.step = step;
+  if (out.end > nbytes) return cut();
+  return true;
+}
+
 }  // namespace cgc

@@ -65,6 +65,27 @@ struct FrameSpan {
 bool locate_frame(const char* text, int64_t nbytes, int64_t pos, int n_atoms, int line_bytes, FrameSpan& out,
                   int* n_atoms_found, bool* truncated);
 
+// ---- GROMACS .trr (binary, XDR big-endian) --------------------------------------------------------------------------
+// Not a reference format: the authors convert .trr to .gro text with trjconv before traj2dEcsv
+// (reference scripts/2014-09-trr2dEcsv.sh:22); reading the .trr directly removes the 45-69 B/atom text tax.
+// Frame = header (magic 1993, version string "GMX_trn_file", 13 int32: ir/e/box/vir/pres/top/sym/x/v/f sizes, natoms,
+// step, nre; then t and lambda as float or double) followed by box, vir, pres (9 reals each when present), x, v, f
+// (3*natoms reals each when present).  The precision is box_size / 9, else x_size / (3*natoms)  (GROMACS
+// src/gromacs/fileio/trrio.cpp, do_trr_frame_header / nFloatSize).
+struct TrrFrame {
+  int64_t begin = 0;     // offset of the magic number
+  int64_t x_off = 0;     // offset of the coordinate array
+  int64_t end = 0;       // offset one past the frame
+  int n_atoms = 0;
+  int real_bytes = 4;    // 4 (single precision) or 8
+  int64_t step = 0;
+  double time = 0.0;
+};
+// Parse the frame header at `pos`.  Returns false at a clean end of data (pos == nbytes) or when the frame is cut short
+// (*truncated = true).  Throws InputFileMalformed for a bad magic/version/size field, Unsupported for a frame without
+// coordinates.
+bool locate_trr_frame(const char* data, int64_t nbytes, int64_t pos, TrrFrame& out, bool* truncated);
+
 // Frame-0 pass with the reference's whitespace-token rules (reference src/grom2atomFMO.cpp:396-462), then the
 // fixed-column layout check.  Throws Unsupported when the atom lines are not fixed-column.
 void scan_first_frame(const char* text, int64_t nbytes, FrameLayout& out, FrameSpan& span);

@@ -97,7 +97,11 @@ __host__ __device__ inline uint32_t decode_buf_stride(int line_bytes) {
   return ((uint32_t)kDecodeThreads * line_bytes + 32u + 127u) & ~127u;
 }
 
-template <bool kStd>
+// kMode: kDecText generic "%W.Df" text, kDecText83 the "%8.3f" fast path, kDecTrr32 / kDecTrr64 big-endian binary
+// coordinates of a .trr frame (a "line" is then the 12 or 24 bytes of one atom; nothing to validate).
+enum : int { kDecText = 0, kDecText83 = 1, kDecTrr32 = 2, kDecTrr64 = 3 };
+
+template <int kMode>
 __global__ void __launch_bounds__(kDecodeThreads)
 decode_kernel(const char* __restrict__ text, int64_t text_bytes, const int64_t* __restrict__ atoms_off, int n_atoms,
               int n_pad, int line_bytes, int x_col, int field_w, int ndec,
@@ -163,7 +167,21 @@ decode_kernel(const char* __restrict__ text, int64_t text_bytes, const int64_t* 
       if (a < n_atoms) {
         const unsigned char* line = sm_raw + b * buf_stride + k.head + threadIdx.x * line_bytes;
         int err = 0;
-        if constexpr (kStd) {
+        if constexpr (kMode == kDecTrr32) {
+          const unsigned* wp = reinterpret_cast<const unsigned*>(line);   // 4-byte aligned: every .trr field is
+          out.x = __uint_as_float(__byte_perm(wp[0], 0, 0x0123));
+          out.y = __uint_as_float(__byte_perm(wp[1], 0, 0x0123));
+          out.z = __uint_as_float(__byte_perm(wp[2], 0, 0x0123));
+        } else if constexpr (kMode == kDecTrr64) {
+          const unsigned* wp = reinterpret_cast<const unsigned*>(line);
+          float v[3];
+#pragma unroll
+          for (int d = 0; d < 3; d++) {
+            const unsigned hi = __byte_perm(wp[2 * d], 0, 0x0123), lo = __byte_perm(wp[2 * d + 1], 0, 0x0123);
+            v[d] = (float)__hiloint2double((int)hi, (int)lo);   // rounded once, like (float)atof of the text would be
+          }
+          out.x = v[0]; out.y = v[1]; out.z = v[2];
+        } else if constexpr (kMode == kDecText83) {
           const unsigned char* fld = line + x_col;
           const unsigned mis = (unsigned)(smem_addr(fld) & 3u);
           const unsigned* wp = reinterpret_cast<const unsigned*>(fld - mis);
@@ -191,9 +209,11 @@ decode_kernel(const char* __restrict__ text, int64_t text_bytes, const int64_t* 
           out.y = parse_field(line + x_col + field_w, field_w, ndec, p10f, p10d, wide, err);
           out.z = parse_field(line + x_col + 2 * field_w, field_w, ndec, p10f, p10d, wide, err);
         }
-        const bool last_unterminated = (atoms_off[f] + (int64_t)(a + 1) * line_bytes - 1) >= text_bytes;
-        if (!last_unterminated && line[line_bytes - 1] != '\n') err |= kDecBadNewline;
-        if (err) atomicOr(err_flags, err);
+        if constexpr (kMode == kDecText || kMode == kDecText83) {
+          const bool last_unterminated = (atoms_off[f] + (int64_t)(a + 1) * line_bytes - 1) >= text_bytes;
+          if (!last_unterminated && line[line_bytes - 1] != '\n') err |= kDecBadNewline;
+          if (err) atomicOr(err_flags, err);
+        }
         const int sl = slot[a];
         if (sl >= 0) {
           // site block entry for the pair loop: negated coordinates (so dx = x + (-xc) is one FADD2) and dQ
@@ -247,10 +267,12 @@ void launch_decode(const DeviceSystem& sys, const char* text, int64_t text_bytes
   const long long n_chunks = (long long)chunks_per_frame * n_frames;
   if (n_chunks == 0) return;
   const size_t smem = 2 * (size_t)decode_buf_stride(sys.line_bytes);
-  const bool std_layout = sys.field_w == 8 && sys.ndec == 3;
-  auto kern = std_layout ? decode_kernel<true> : decode_kernel<false>;
-  static size_t granted[2][16] = {};
-  ensure_dynamic_smem(kern, smem, granted[std_layout]);
+  const int mode = sys.traj_mode == 1 ? kDecTrr32 : sys.traj_mode == 2 ? kDecTrr64
+                   : (sys.field_w == 8 && sys.ndec == 3) ? kDecText83 : kDecText;
+  auto kern = mode == kDecTrr32 ? decode_kernel<kDecTrr32> : mode == kDecTrr64 ? decode_kernel<kDecTrr64>
+              : mode == kDecText83 ? decode_kernel<kDecText83> : decode_kernel<kDecText>;
+  static size_t granted[4][16] = {};
+  ensure_dynamic_smem(kern, smem, granted[mode]);
   int dev = 0, sm_count = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);

@@ -24,6 +24,7 @@ struct DeviceSystem {
   int n_sites = 0;                      // sites computed (<= n_chromo)
   int site_cap = 0;                     // P: dQ atoms per site, padded to the largest site
   int line_bytes = 0, x_col = 20, field_w = 8, ndec = 3;
+  int traj_mode = 0;                    // 0 .gro text; 1 / 2: .trr coordinates, single / double (line_bytes = 12 / 24)
   double* kq = nullptr;                 // [n_pad] (double)33.2f * (double)q
   int32_t* col = nullptr;               // [n_pad] dE column, -1 = contributes nowhere (pads)
   int32_t* slot = nullptr;              // [n_pad] s*P + c for the c-th dQ atom of site s, else -1

@@ -8,6 +8,8 @@
 //     the reference's literal arithmetic instead (its stride variable stays 0, src/FMOparse.cpp:42,193,202);
 //   * asking for more frames than the file holds stops cleanly (the reference segfaults, README.md:31);
 //   * stdout is quiet unless --verbose (per-frame site totals in cm^-1, the reference's "=<sum> cm-1" log).
+//   * traj_in may be a GROMACS .trr (binary) when --structure some.gro names a .gro of the same system: the authors'
+//     trjconv step (reference scripts/2014-09-trr2dEcsv.sh:22) and its 45-69 bytes of text per atom are skipped.
 // Extra flags come AFTER the five positionals.
 #include <unistd.h>
 
@@ -51,13 +53,15 @@ int main(int argc, char** argv) {
   if (argc < 6) {
     printf("Five inputs required for this program.\n");
     printf("Order of args: fmo_traj_path, fmo_top_path, bcx_itp_path, output_path, num_frames "
-           "[--sites N] [--mtx-compat] [--no-mtx] [--device D] [--first-frame F] [--batch-frames B] [--verbose]\n");
+           "[--sites N] [--mtx-compat] [--no-mtx] [--device D] [--first-frame F] [--batch-frames B] [--verbose] "
+           "[--structure frame0.gro (traj_in is then a .trr)]\n");
     return EXIT_FAILURE;
   }
   const std::string traj = argv[1], top = argv[2], itp = argv[3], out = argv[4];
   const long long num_frames = atoll(argv[5]);
   int sites = 0, device = 0, batch = 0;
   long long first = 0;
+  std::string structure;
   bool compat = false, no_mtx = false, verbose = false, timing = false;
   for (int i = 6; i < argc; i++) {
     std::string a = argv[i];
@@ -72,6 +76,7 @@ int main(int argc, char** argv) {
     else if (a == "--device") device = atoi(val("--device"));
     else if (a == "--first-frame") first = atoll(val("--first-frame"));
     else if (a == "--batch-frames") batch = atoi(val("--batch-frames"));
+    else if (a == "--structure") structure = val("--structure");
     else if (a == "--mtx-compat") compat = true;
     else if (a == "--no-mtx") no_mtx = true;
     else if (a == "--verbose") verbose = true;
@@ -92,7 +97,13 @@ int main(int argc, char** argv) {
            cgc_topology_warnings(ctx));
   }
   const double t_created = now_s();
-  rc = cgc_open(ctx, traj.c_str());
+  const bool is_trr = traj.size() > 4 && traj.compare(traj.size() - 4, 4, ".trr") == 0;
+  if (is_trr && structure.empty()) {
+    fprintf(stderr, "traj2dEcsv: a .trr trajectory holds no atom names: pass --structure <file.gro> (any .gro frame of the same system)\n");
+    cgc_destroy(ctx);
+    return EXIT_FAILURE;
+  }
+  rc = structure.empty() ? cgc_open(ctx, traj.c_str()) : cgc_open_trr(ctx, traj.c_str(), structure.c_str());
   if (rc != CGC_OK) return die(ctx, rc, "opening the trajectory");
   if (sites > 0 && (rc = cgc_set_option(ctx, "sites", sites)) != CGC_OK) return die(ctx, rc, "setting --sites");
   if (no_mtx && (rc = cgc_set_option(ctx, "covariance", 0)) != CGC_OK) return die(ctx, rc, "setting --no-mtx");

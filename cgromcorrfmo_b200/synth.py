@@ -301,6 +301,44 @@ def write_gro(path: str, s: System, n_frames: int, velocities: bool = False, jit
     return size
 
 
+def trr_frame_bytes(s: System, frame: int, double: bool = False, velocities: bool = False, forces: bool = False,
+                    box: bool = True, jitter: float = 0.01, dt_ps: float = 0.2) -> bytes:
+    """One GROMACS .trr frame (XDR, big-endian) holding exactly the numbers frame_bytes() prints as "%8.3f" text:
+    single precision stores float32(milli / 1000) — the value (float)atof of the text yields — double stores milli/1000."""
+    n = s.n_atoms
+    real = ">f8" if double else ">f4"
+    rb = 8 if double else 4
+    milli = frame_milli(s, frame, jitter)
+    x = (milli.astype(np.float64) / 1000.0)
+    if not double:
+        x = x.astype(np.float32)
+    sizes = [0, 0, 9 * rb if box else 0, 0, 0, 0, 0, 3 * n * rb, 3 * n * rb if velocities else 0,
+             3 * n * rb if forces else 0, n, frame, 0]
+    out = [np.array([1993, 13, 12], ">i4").tobytes(), b"GMX_trn_file", np.array(sizes, ">i4").tobytes(),
+           np.array([frame * dt_ps, 0.0], real).tobytes()]
+    if box:
+        out.append((np.eye(3) * s.box).astype(real).tobytes())
+    out.append(x.astype(real).tobytes())
+    rng = np.random.default_rng([s.seed, 104729, frame])
+    if velocities:
+        out.append(rng.normal(0, 0.5, (n, 3)).astype(real).tobytes())
+    if forces:
+        out.append(rng.normal(0, 100.0, (n, 3)).astype(real).tobytes())
+    return b"".join(out)
+
+
+def write_trr(path: str, s: System, n_frames: int, double: bool = False, velocities: bool = False,
+              forces: bool = False, box: bool = True, jitter: float = 0.01) -> int:
+    """The .trr twin of write_gro (same frames).  Returns the byte size of frame 0."""
+    fb = 0
+    with open(path, "wb") as f:
+        for t in range(n_frames):
+            b = trr_frame_bytes(s, t, double, velocities, forces, box, jitter)
+            fb = fb or len(b)
+            f.write(b)
+    return fb
+
+
 def write_inputs(outdir: str, s: System, n_frames: int, velocities: bool = False, jitter: float = 0.01):
     """Write traj.gro / topol.top / bcx.itp into outdir and return their absolute paths."""
     os.makedirs(outdir, exist_ok=True)

@@ -68,6 +68,17 @@ int cgc_topology_warnings(const cgc_context *ctx);
  * stay valid until the context is destroyed or re-opened). */
 int cgc_open(cgc_context *ctx, const char *traj_path);
 int cgc_open_memory(cgc_context *ctx, const char *text, int64_t nbytes);
+/* GROMACS .trr trajectories (binary, big-endian, single or double precision) read directly.  Not a reference format:
+ * the authors run trjconv to turn .trr into .gro text before traj2dEcsv (scripts/2014-09-trr2dEcsv.sh:22); this entry
+ * point removes that step and the 45-69 bytes of text per atom and frame with it.  A .trr holds
+ * no names, so residue numbers, residue and atom names — hence groups, keys and charges — come from the first frame of
+ * `structure_gro_path` (any .gro of the same system, e.g. the frame trjconv would have written first); its coordinates
+ * are not used.  Frames may carry box, velocities and forces: only the coordinate array is decoded.  Coordinates are
+ * used as stored (double precision is rounded once to float32): a .trr written from the same numbers as a "%8.3f" .gro
+ * gives bit-identical dE.  CGC_ERR_INPUT_MALFORMED for a bad magic number / version string / size field or an atom
+ * count different from the structure file's, CGC_ERR_UNSUPPORTED for frames without coordinates. */
+int cgc_open_trr(cgc_context *ctx, const char *trr_path, const char *structure_gro_path);
+int cgc_open_memory_trr(cgc_context *ctx, const char *data, int64_t nbytes, const char *structure_gro_path);
 
 int cgc_dims(const cgc_context *ctx, int *n_atoms, int *n_chromo, int *n_groups, int *num_tot);
 /* atomGroupi of ReadOneTimeGrom2Atom: -k for the k-th chromophore, +g for the g-th other residue. int32[n_atoms] */
