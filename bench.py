@@ -262,6 +262,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — the hot path is CUDA-only, there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cores = cdist.bind_to_gpu_numa(local) if world > 1 else None   # before any pinned allocation
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -357,6 +358,7 @@ def run_ours(args):
         for _ in range(max(3, args.warmup)):
             ctx.run(0, F, out=out_host)
         barrier()
+        ctx.kernel_times(reset=True)
         t0 = time.perf_counter()
         e0.record()
         for _ in range(args.steps):
@@ -390,6 +392,7 @@ def run_ours(args):
         ctx2 = capi.Context(top, itp, local)
         ctx2.open_memory_trr((host_trr.data_ptr(), n_trr), struct_gro)
         ctx2.set_option("batch_frames", args.e2e_batch)
+        ctx2.set_option("profile", 1)
         cov2 = torch.zeros(ctx2.cov_size(), dtype=torch.float64, device=dev)
         ctx2.cov_bind(cov2.data_ptr())
         ctx2.cov_set_shift_device(row0.data_ptr(), stream)            # the same shift on every rank, as above
@@ -397,6 +400,7 @@ def run_ours(args):
         for _ in range(max(3, args.warmup)):
             ctx2.run(0, F, out=out_trr)
         barrier()
+        ctx2.kernel_times(reset=True)
         t0 = time.perf_counter()
         e0.record()
         for _ in range(args.steps):
@@ -410,6 +414,7 @@ def run_ours(args):
             t = torch.tensor([trr_s], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             trr_s = float(t.item())
+        trr_ktimes = ctx2.kernel_times(reset=True)
         trr_value = world * args.steps * F / trr_s
         trr_same = float(np.abs(out_trr.astype(np.float64) - out_host.astype(np.float64)).max())
         trr_scale = float(np.abs(out_host).max())
@@ -475,12 +480,13 @@ def run_ours(args):
                    "step": "K1 decode + K2 CDC (all sites) + float32 rows + K3 Correlate over one batch of frames",
                    "input_bytes_per_step": int(n_text), "l2": "per-step input exceeds the 126 MB L2 (no flush needed)",
                    "parallelism": "frame-sharded x%d, one all-reduce of the Correlate sums" % world,
+                   "numa": ("rank 0 bound to %d cores local to its GPU" % len(numa_cores)) if numa_cores else "unbound",
                    "pairs_per_frame": pairs_per_frame, "pair_convention": "dQ != 0 site atoms only (44 of 140)"},
         "pairs_per_s": value * pairs_per_frame, "pairs_per_s_reference_count_140": value * pairs_per_frame_140,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_text + 8 * F), "d2h_bytes_per_step": int(F * S * G * 4),
-                "api": "cgc_run (C-ABI) on pinned host text, %d-frame batches double-buffered; dE rows copied back to host" % args.e2e_batch,
-                "max_abs_diff_vs_device_path": same,
+                "api": "cgc_run (C-ABI) on pinned host text, %d-frame batches in a 3-slot ring; dE rows copied back to host" % args.e2e_batch,
+                "max_abs_diff_vs_device_path": same, "kernel_ms": {k: v[0] for k, v in e2e_ktimes.items()}, "wall_ms": e2e_s * 1e3,
                 "bound": "PCIe host->device copy of the text", "h2d_gbs": e2e_value / world * frame_bytes / 1e9,
                 "h2d_peak_gbs": h2d_peak, "frac_of_h2d_peak": (e2e_value / world * frame_bytes / 1e9) / h2d_peak,
                 "h2d_peak_source": "pinned cudaMemcpyAsync of the same text buffer, best of 6, measured in this run"},
@@ -488,7 +494,8 @@ def run_ours(args):
                     "api": "cgc_open_memory_trr + cgc_run on pinned .trr frames (float32 coordinates + box, %d B/frame), %d-frame batches"
                            % (n_trr // F, args.e2e_batch),
                     "note": "same frames as the headline; not the reference's input format (it reads .gro text)",
-                    "max_abs_diff_vs_gro_path": trr_same, "max_abs_dE": trr_scale},
+                    "max_abs_diff_vs_gro_path": trr_same, "max_abs_dE": trr_scale,
+                    "kernel_ms": {k: v[0] for k, v in trr_ktimes.items()}, "wall_ms": trr_s * 1e3},
         "gpu_launches": int(launches),
         "kernel_ms": {k: v[0] for k, v in ktimes.items()},
         "roofline": roofline, "rooflines_other": others, "cpu_baseline": cpu,

@@ -39,7 +39,7 @@ struct CudaError : std::runtime_error {
     }                                                                                                         \
   } while (0)
 
-// One half of the double-buffered stream: text in, dE out.
+// One slot of the streaming ring (cgc_context::kSlots of them): text in, dE out.
 struct Slot {
   char* h_text = nullptr;   // pinned staging (file path only)
   char* d_text = nullptr;
@@ -89,7 +89,8 @@ struct cgc_context {
   int batch_frames = 0;
 
   // pipeline
-  Slot slot[2];
+  static constexpr int kSlots = 3;   // batches in flight: one being copied in, one computing, one being drained
+  Slot slot[kSlots];
   bool dev_pipeline = false;
   int alloc_batch = 0;
   int64_t alloc_text = 0;
@@ -926,7 +927,14 @@ int cgc_run(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_k
     bool eof = false;
     while (done < n_frames && !eof) {
       const int64_t f_begin = first_frame + done;
+      // Batch size ramps up at the start of a call (the first H2D copy is not hidden behind any compute) and down at
+      // its end (neither are the last batch's kernels and D2H copy): B/4, B/2, B, ..., B, then halving.
       int want = (int)std::min<int64_t>(B, n_frames - done);
+      {
+        const int64_t min_b = std::max<int64_t>(1, B / 4), left = n_frames - done;
+        want = (int)std::min<int64_t>(want, done + min_b);
+        if (left > min_b) want = (int)std::min<int64_t>(want, std::max<int64_t>(min_b, (left + 1) / 2));
+      }
       const int64_t known = index_upto(ctx, f_begin + want - 1);
       if (known < f_begin + want) {
         want = (int)std::max<int64_t>(0, known - f_begin);
@@ -963,10 +971,9 @@ int cgc_run(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_k
       s.out_frame = done;
       s.busy = true;
       done += want;
-      which ^= 1;
+      which = (which + 1) % cgc_context::kSlots;
     }
-    drain(ctx->slot[which]);
-    drain(ctx->slot[which ^ 1]);
+    for (int i = 0; i < cgc_context::kSlots; i++) drain(ctx->slot[(which + i) % cgc_context::kSlots]);   // oldest first
     int flags = 0;
     CUDA_OK(cudaMemcpy(&flags, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
     if (flags) {

@@ -14,6 +14,32 @@ import os
 import shutil
 
 
+def bind_to_gpu_numa(device_index: int):
+    """Pin this process to the CPU cores NVML reports as local to GPU `device_index` (the host side of its PCIe link).
+    Called BEFORE any pinned host memory is allocated, so that first-touch places the staging buffers on that NUMA node:
+    with one rank per GPU the end-to-end rate is bound by host memory -> PCIe traffic, and a rank whose pinned text
+    sits on the other socket pays the inter-socket link twice.  Returns the list of cores, or None when NVML or the
+    affinity call is unavailable (the run then proceeds unbound)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            n_words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        finally:
+            pynvml.nvmlShutdown()
+        cores = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cores = sorted(set(cores) & allowed)
+        if not cores:
+            return None
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:
+        return None
+
+
 def frame_range(rank: int, world: int, total_frames: int):
     """Contiguous, balanced, ordered: concatenating the ranges in rank order gives range(total_frames)."""
     if world < 1 or not (0 <= rank < world):

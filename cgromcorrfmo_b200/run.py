@@ -25,6 +25,8 @@ def traj2dEcsv(traj, top, itp, out, num_frames, sites=0, mtx_compat=False, chunk
     if not torch.cuda.is_available():
         raise RuntimeError("no CUDA device: the hot path is CUDA-only (no CPU fallback)")
     torch.cuda.set_device(local)
+    if world > 1:
+        cdist.bind_to_gpu_numa(local)           # pinned staging buffers land on the GPU's own NUMA node
     if world > 1 and not tdist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         tdist.init_process_group("nccl", device_id=torch.device("cuda", local))

@@ -108,7 +108,7 @@ double cgc_get_option(const cgc_context *ctx, const char *key);
 
 /* ---- the hot path -----------------------------------------------------------------------------------------------
  * cgc_run replaces the per-frame body of main_Cr (src/FMOparse.cpp:68-179): for frames [first, first+n) it streams the
- * text through pinned double-buffered H2D copies, decodes it (K1), evaluates ComputeCDC_v1 for every site (K2), and
+ * text through pinned, ring-buffered (3 slots) H2D copies, decodes it (K1), evaluates ComputeCDC_v1 for every site (K2), and
  * accumulates the Correlate sums (K3).  dE_kcal (nullable) receives float32 [n][sites][numTot], caller-owned HOST memory.
  * Returns CGC_OK, or CGC_EOF with *frames_done < n when the trajectory ends early. */
 int cgc_run(cgc_context *ctx, int64_t first_frame, int64_t n_frames, float *dE_kcal, int64_t *frames_done);

@@ -87,3 +87,17 @@ def test_two_rank_merge_gloo(tmp_path):
     port = s.getsockname()[1]
     s.close()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+
+
+def test_numa_binding_is_a_no_op_without_nvml():
+    """bind_to_gpu_numa never raises and leaves the affinity alone when NVML / the GPU is absent."""
+    import os
+    from cgromcorrfmo_b200 import dist as cdist
+    before = os.sched_getaffinity(0)
+    cores = cdist.bind_to_gpu_numa(0)
+    after = os.sched_getaffinity(0)
+    if cores is None:
+        assert before == after
+    else:
+        assert set(cores) == after and after <= before
+        os.sched_setaffinity(0, before)
