@@ -118,19 +118,21 @@ decode_kernel(const char* __restrict__ text, int64_t text_bytes, const int64_t* 
   }
   __syncthreads();
 
-  // chunk -> (frame, first atom, lines present, source range rounded out to 16 bytes)
-  struct Chunk { int f, a0, n_here; uint32_t head, bytes; int64_t src_al; };
-  auto locate = [&](int c) {
+  // (frame, chunk in frame) -> first atom, lines present, source range rounded out to 16 bytes
+  struct Chunk { int f, a0, n_here; uint32_t head, bytes; int64_t src_al; bool tail_open; };
+  auto locate = [&](int f, int cf) {
     Chunk k;
-    k.f = c / chunks_per_frame;
-    k.a0 = (c - k.f * chunks_per_frame) * kDecodeThreads;
+    k.f = f;
+    k.a0 = cf * kDecodeThreads;
     int n_here = n_atoms - k.a0;
     k.n_here = n_here < 0 ? 0 : (n_here > kDecodeThreads ? kDecodeThreads : n_here);
-    k.head = 0; k.bytes = 0; k.src_al = 0;
+    k.head = 0; k.bytes = 0; k.src_al = 0; k.tail_open = false;
     if (k.n_here > 0) {
-      const int64_t src = atoms_off[k.f] + (int64_t)k.a0 * line_bytes;
+      const int64_t src = atoms_off[f] + (int64_t)k.a0 * line_bytes;
       k.src_al = src & ~(int64_t)15;
       k.head = (uint32_t)(src - k.src_al);
+      const int64_t end = src + (int64_t)k.n_here * line_bytes;
+      k.tail_open = end - 1 >= text_bytes;   // the very last line of the text may lack its newline
       int64_t bytes = (int64_t)k.head + (int64_t)k.n_here * line_bytes;
       bytes = (bytes + 15) & ~(int64_t)15;
       const int64_t lim = ((text_bytes + 15) & ~(int64_t)15) - k.src_al;  // never read past the (16-byte padded) text
@@ -138,24 +140,38 @@ decode_kernel(const char* __restrict__ text, int64_t text_bytes, const int64_t* 
     }
     return k;
   };
-  auto issue = [&](int c, int b) {   // thread 0
-    const Chunk k = locate(c);
+  auto issue = [&](const Chunk& k, int b) {   // thread 0
     if (k.n_here > 0) {
       mbar_expect_tx(&bar[b], k.bytes);
       tma_bulk_g2s(sm_raw + b * buf_stride, text + k.src_al, k.bytes, &bar[b]);
     }
   };
+  // the chunk index advances by gridDim.x per trip: keep (frame, chunk in frame) incrementally instead of dividing
+  const int step_f = (int)gridDim.x / chunks_per_frame, step_c = (int)gridDim.x - step_f * chunks_per_frame;
+  auto advance = [&](int& f, int& cf) {
+    f += step_f;
+    cf += step_c;
+    if (cf >= chunks_per_frame) { cf -= chunks_per_frame; f++; }
+  };
 
   int c = blockIdx.x;
   if (c >= n_chunks) return;
-  if (threadIdx.x == 0) issue(c, 0);
+  int f_cur = c / chunks_per_frame, cf_cur = c - f_cur * chunks_per_frame;
+  Chunk k = locate(f_cur, cf_cur);
+  if (threadIdx.x == 0) issue(k, 0);
   uint32_t phase_bits = 0;
   for (int i = 0; c < n_chunks; c += gridDim.x, i++) {
     const int b = i & 1;
     // the other buffer was last read one iteration ago; the __syncthreads that ended that iteration orders those
     // reads before this copy
-    if (threadIdx.x == 0 && c + (int)gridDim.x < n_chunks) issue(c + gridDim.x, b ^ 1);
-    const Chunk k = locate(c);
+    int f_next = f_cur, cf_next = cf_cur;
+    advance(f_next, cf_next);
+    Chunk k_next = k;
+    const bool has_next = c + (int)gridDim.x < n_chunks;
+    if (has_next) {
+      k_next = locate(f_next, cf_next);
+      if (threadIdx.x == 0) issue(k_next, b ^ 1);
+    }
     if (k.n_here > 0) {
       mbar_wait(&bar[b], (phase_bits >> b) & 1u);
       phase_bits ^= 1u << b;
@@ -210,7 +226,7 @@ decode_kernel(const char* __restrict__ text, int64_t text_bytes, const int64_t* 
           out.z = parse_field(line + x_col + 2 * field_w, field_w, ndec, p10f, p10d, wide, err);
         }
         if constexpr (kMode == kDecText || kMode == kDecText83) {
-          const bool last_unterminated = (atoms_off[f] + (int64_t)(a + 1) * line_bytes - 1) >= text_bytes;
+          const bool last_unterminated = k.tail_open && (int)threadIdx.x == k.n_here - 1;
           if (!last_unterminated && line[line_bytes - 1] != '\n') err |= kDecBadNewline;
           if (err) atomicOr(err_flags, err);
         }
@@ -229,6 +245,9 @@ decode_kernel(const char* __restrict__ text, int64_t text_bytes, const int64_t* 
       dst[16] = out.z;
     }
     __syncthreads();  // everyone is done with buffer b before the copy two chunks ahead overwrites it
+    k = k_next;
+    f_cur = f_next;
+    cf_cur = cf_next;
   }
 }
 
