@@ -60,6 +60,7 @@ SIGNATURES = {
     "cgc_cov_partials": (c_int, [c_void_p, c_void_p]),
     "cgc_cov_set_shift_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "cgc_cov_accumulate_device": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "cgc_project": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "cgc_cov_finalize": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "cgc_write_time": (c_int, [c_char_p, c_int, c_void_p, c_int64, c_int]),
     "cgc_write_mtx": (c_int, [c_void_p, c_char_p, c_int]),
@@ -345,6 +346,19 @@ class Context:
         cov = np.empty((S, G, G), np.float64)
         self._check(self._lib.cgc_cov_finalize(self._h, int(ddof), _ptr(mean), _ptr(cov)))
         return mean, cov
+
+    def project(self, dE_rows, mean, modes):
+        """out[t, s, m] = sum_g (dE_rows[t, s, g] - mean[s, g]) * modes[s, m, g] on the device (FP64 tensor cores).
+        dE_rows float32 (T, S, G); mean (S, G); modes (S, M, G), eigenvectors as rows.  Returns float64 (T, S, M)."""
+        x = np.ascontiguousarray(dE_rows, dtype=np.float32)
+        mu = np.ascontiguousarray(mean, dtype=np.float64)
+        w = np.ascontiguousarray(modes, dtype=np.float64)
+        S, G = self.n_sites, self.num_tot
+        if x.ndim != 3 or x.shape[1:] != (S, G) or mu.shape != (S, G) or w.ndim != 3 or w.shape[0] != S or w.shape[2] != G:
+            raise ValueError("project: expected rows (T, %d, %d), mean (%d, %d), modes (%d, M, %d)" % (S, G, S, G, S, G))
+        out = np.empty((x.shape[0], S, w.shape[1]), dtype=np.float64)
+        self._check(self._lib.cgc_project(self._h, _ptr(x), x.shape[0], _ptr(mu), _ptr(w), w.shape[1], _ptr(out)))
+        return out
 
     def write_mtx(self, path: str, compat: bool = False):
         self._check(self._lib.cgc_write_mtx(self._h, os.fsencode(path), 1 if compat else 0))

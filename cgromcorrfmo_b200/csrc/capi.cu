@@ -1140,6 +1140,44 @@ int cgc_cov_finalize(cgc_context* ctx, int ddof, double* mean, double* cov) {
   });
 }
 
+int cgc_project(cgc_context* ctx, const float* dE_rows, int64_t n_frames, const double* mean, const double* modes,
+                int n_modes, double* out) {
+  if (!ctx || !dE_rows || !mean || !modes || !out) return fail(ctx, CGC_ERR_ARG, "null argument");
+  if (!ctx->opened) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  if (n_frames < 0 || n_modes < 1) return fail(ctx, CGC_ERR_ARG, "bad frame or mode count");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    const int S = ctx->sys.n_sites, G = ctx->sys.num_tot, M = n_modes;
+    if (n_frames == 0) return CGC_OK;
+    const int64_t sg = (int64_t)S * G, sm = (int64_t)S * M;
+    // frames per pass: rows (4 B) + centred rows (8 B) + projections (8 B) within about 1 GiB
+    const int64_t chunk = std::max<int64_t>(64, std::min<int64_t>(n_frames, ((int64_t)1 << 30) / (sg * 12 + sm * 8)));
+    float* d_x = nullptr;
+    double *d_c = nullptr, *d_o = nullptr, *d_mean = nullptr, *d_modes = nullptr;
+    cudaError_t err = cudaSuccess;
+    auto ok = [&](cudaError_t e) { if (err == cudaSuccess) err = e; return e == cudaSuccess; };
+    CUDA_OK(cudaDeviceSynchronize());
+    if (ok(cudaMalloc(&d_x, sizeof(float) * chunk * sg)) && ok(cudaMalloc(&d_c, sizeof(double) * chunk * sg)) &&
+        ok(cudaMalloc(&d_o, sizeof(double) * chunk * sm)) && ok(cudaMalloc(&d_mean, sizeof(double) * sg)) &&
+        ok(cudaMalloc(&d_modes, sizeof(double) * sm * G)) &&
+        ok(cudaMemcpy(d_mean, mean, sizeof(double) * sg, cudaMemcpyHostToDevice)) &&
+        ok(cudaMemcpy(d_modes, modes, sizeof(double) * sm * G, cudaMemcpyHostToDevice))) {
+      for (int64_t t = 0; t < n_frames && err == cudaSuccess; t += chunk) {
+        const int n = (int)std::min<int64_t>(chunk, n_frames - t);
+        if (!ok(cudaMemcpyAsync(d_x, dE_rows + t * sg, sizeof(float) * n * sg, cudaMemcpyHostToDevice, ctx->st_comp))) break;
+        launch_project(d_x, n, d_mean, d_modes, M, d_c, d_o, S, G, ctx->st_comp);
+        ctx->launches += 2;
+        ok(cudaGetLastError());
+        ok(cudaMemcpyAsync(out + t * sm, d_o, sizeof(double) * n * sm, cudaMemcpyDeviceToHost, ctx->st_comp));
+        ok(cudaStreamSynchronize(ctx->st_comp));
+      }
+    }
+    cudaFree(d_x); cudaFree(d_c); cudaFree(d_o); cudaFree(d_mean); cudaFree(d_modes);
+    CUDA_OK(err);
+    return CGC_OK;
+  });
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // writers
 // ---------------------------------------------------------------------------------------------------------------------

@@ -523,6 +523,102 @@ void launch_cov_accumulate(const float* dE, int n_frames, double* buf, float* co
   cov_syrk_kernel<<<grid, 128, 0, st>>>(centred_scratch, n_frames, buf, S, G, nblk);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// K4  mode projection (depca's ApplyPCA, reference scripts/depca/depca/convert.py:84-125) on FP64 tensor cores
+// ---------------------------------------------------------------------------------------------------------------------
+// out[t][s][m] = sum_g (x[t][s][g] - mean[s][g]) * modes[s][m][g] : per site a (frames x G) by (G x M) GEMM.
+// centre_rows_kernel writes D = x - mean in FP64; project_kernel computes 64 x 64 tiles of D_s W_s^T with
+// mma.sync m8n8k4 f64 (4 warps, each a 32 x 32 quarter), both operands K-contiguous in global memory and staged by
+// cp.async into double-buffered tiles whose 20-double row stride makes the fragment loads conflict-free.
+__global__ void centre_rows_kernel(const float* __restrict__ x, const double* __restrict__ mean, double* __restrict__ d,
+                                   int64_t n, int SG) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) d[i] = (double)x[i] - mean[i % SG];
+}
+
+constexpr int kPrjBlk = 64;    // tile edge (frames and modes)
+constexpr int kPrjK = 16;      // columns of G per stage
+constexpr int kPrjLd = 20;     // row stride in doubles: (gid * 20 + tig) mod 16 is a permutation of 0..15 for gid, tig < 4
+
+__global__ void __launch_bounds__(128)
+project_kernel(const double* __restrict__ D, const double* __restrict__ W, double* __restrict__ out, int T, int S, int G,
+               int M) {
+  __shared__ __align__(16) double As[2][kPrjBlk][kPrjLd];   // frames x k
+  __shared__ __align__(16) double Bs[2][kPrjBlk][kPrjLd];   // modes x k
+  const int t0 = blockIdx.x * kPrjBlk, m0 = blockIdx.y * kPrjBlk, s = blockIdx.z;
+  const int SG = S * G;
+  const double* Ds = D + (size_t)s * G;               // row t at Ds + t * SG
+  const double* Ws = W + (size_t)s * M * G;           // row m at Ws + m * G
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wi = (warp >> 1) * 32, wj = (warp & 1) * 32;
+  const int gid = lane >> 2, tig = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  auto stage = [&](int b, int k0) {
+    for (int idx = threadIdx.x; idx < kPrjBlk * kPrjK; idx += 128) {
+      const int r = idx / kPrjK, k = idx - r * kPrjK;
+      const int g = k0 + k, t = t0 + r, m = m0 + r;
+      const bool gv = g < G;
+      cp_async_8(&As[b][r][k], Ds + (size_t)(t < T ? t : 0) * SG + (gv ? g : 0), gv && t < T);
+      cp_async_8(&Bs[b][r][k], Ws + (size_t)(m < M ? m : 0) * G + (gv ? g : 0), gv && m < M);
+    }
+    cp_async_commit();
+  };
+
+  const int n_chunks = (G + kPrjK - 1) / kPrjK;
+  stage(0, 0);
+  for (int ch = 0; ch < n_chunks; ch++) {
+    const int cb = ch & 1;
+    if (ch + 1 < n_chunks) {
+      stage(cb ^ 1, (ch + 1) * kPrjK);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k0 = 0; k0 < kPrjK; k0 += 4) {
+      double a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = As[cb][wi + i * 8 + gid][k0 + tig];
+#pragma unroll
+      for (int j = 0; j < 4; j++) bb[j] = Bs[cb][wj + j * 8 + gid][k0 + tig];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int t = t0 + wi + i * 8 + gid;
+    if (t >= T) continue;
+    double* row = out + ((size_t)t * S + s) * M;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int m = m0 + wj + j * 8 + tig * 2;
+      if (m < M) row[m] = acc[i][j][0];
+      if (m + 1 < M) row[m + 1] = acc[i][j][1];
+    }
+  }
+}
+
+void launch_project(const float* x, int n_frames, const double* mean, const double* modes, int n_modes, double* centred,
+                    double* out, int S, int G, cudaStream_t st) {
+  if (n_frames <= 0 || n_modes <= 0) return;
+  const int64_t n = (int64_t)n_frames * S * G;
+  int64_t blocks = std::min<int64_t>((n + 255) / 256, 148 * 16);
+  centre_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, mean, centred, n, S * G);
+  dim3 grid((n_frames + kPrjBlk - 1) / kPrjBlk, (n_modes + kPrjBlk - 1) / kPrjBlk, S);
+  project_kernel<<<grid, 128, 0, st>>>(centred, modes, out, n_frames, S, G, n_modes);
+}
+
 // mean = c + sum/n ; cov_ij = (sumsq_ij - sum_i sum_j / n) / (n - ddof), upper blocks mirrored
 __global__ void cov_finalize_kernel(const double* __restrict__ buf, int S, int G, int ddof, double* __restrict__ mean,
                                     double* __restrict__ cov) {

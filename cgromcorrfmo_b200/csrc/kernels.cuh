@@ -56,6 +56,9 @@ void launch_cov_set_shift(const float* dE_row0, double* buf, int S, int G, cudaS
 // centred_scratch: n_frames * S * G doubles (the centred rows the SYRK consumes)
 void launch_cov_accumulate(const float* dE, int n_frames, double* buf, float* compat /* float32 [2][S*G] or null */,
                            double* centred_scratch, int S, int G, cudaStream_t st);
+// K4: out[t][s][m] = sum_g (x[t][s][g] - mean[s][g]) * modes[s][m][g]  (all DEVICE; centred: n_frames*S*G doubles scratch)
+void launch_project(const float* x, int n_frames, const double* mean, const double* modes, int n_modes, double* centred,
+                    double* out, int S, int G, cudaStream_t st);
 void launch_cov_finalize(const double* buf, int S, int G, int ddof, double* mean, double* cov, cudaStream_t st);
 
 }  // namespace cgc

@@ -10,6 +10,7 @@ what follows it (eigen-decomposition, projection) is plain numpy, as in depca.
     E_t_ia               = load_E_t_ia(traj, top, itp, num_frames)            # float32 (T, Nsites, Ncoarse), cm^-1
     Corr_i_ab, AvgEia    = AvgAndCorrelateSidechains_gpu(traj, top, itp, T)   # depca's return order
     vi, wi, impact_i     = ComputeModes(Corr_i_ab)
+    proj_t_im            = ApplyPCA_gpu(ctx, E_t_ia, AvgEia, wi)              # (E - mean) . modes on FP64 tensor cores
 """
 from __future__ import annotations
 
@@ -86,3 +87,10 @@ def ApplyPCA(E_t_ia, AvgEia, wi):
     """depca.convert.ApplyPCA_hdf5 (convert.py:84-125) in memory: (E - mean) projected on the modes, per site."""
     E = np.asarray(E_t_ia, dtype=np.float64)
     return np.stack([np.inner(E[:, i, :] - AvgEia[i], wi[i]) for i in range(E.shape[1])], axis=1)
+
+
+def ApplyPCA_gpu(ctx, E_t_ia, AvgEia, wi):
+    """ApplyPCA on the device: `ctx` is an open capi.Context of the same system (it fixes Nsites and Ncoarse); the rows,
+    the means and the modes are host arrays as above.  Returns float64 (T, Nsites, Nmodes) == ApplyPCA(E_t_ia, AvgEia, wi)
+    up to FP64 summation order (K4, DMMA; C-ABI cgc_project)."""
+    return ctx.project(E_t_ia, AvgEia, wi)

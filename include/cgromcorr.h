@@ -150,6 +150,15 @@ int cgc_cov_accumulate_device(cgc_context *ctx, const float *d_dE_kcal, int n_fr
 /* mean [S][G] and covariance [S][G][G] (HOST, double) from the partial sums; ddof 0 = population (the formula the
  * reference intends, src/FMOparse.cpp:189-206), 1 = np.cov as used by depca (scripts/depca/depca/sidechain_corr.py:67). */
 int cgc_cov_finalize(cgc_context *ctx, int ddof, double *mean, double *cov);
+/* Mode projection, the step that follows the covariance in the pyPCA pipeline (depca.convert.ApplyPCA_hdf5,
+ * scripts/depca/depca/convert.py:84-125, and the np.inner at the end of sidechain_corr.py's usage): per site,
+ *   out[t][s][m] = sum_g (dE_rows[t][s][g] - mean[s][g]) * modes[s][m][g]
+ * computed on FP64 tensor cores (K4).  All pointers are HOST memory: dE_rows float32 [n_frames][sites][numTot] (what
+ * cgc_run returned, any unit), mean float64 [sites][numTot], modes float64 [sites][n_modes][numTot] (eigenvectors as
+ * rows, as depca's ComputeModes returns them), out float64 [n_frames][sites][n_modes].  The eigen-decomposition itself
+ * stays on the host (numpy.linalg.eigh in depca): it runs once per trajectory on 7..24 matrices. */
+int cgc_project(cgc_context *ctx, const float *dE_rows, int64_t n_frames, const double *mean, const double *modes,
+                int n_modes, double *out);
 
 /* ---- writers ----------------------------------------------------------------------------------------------------
  * cgc_write_time appends rows to <path> exactly as src/FMOparse.cpp:151-165 does: value = float(double(kcal)*349.7),

@@ -545,3 +545,26 @@ def test_c1_shape_against_the_stock_reference_program(tmp_path, oracle_mod, capi
     tol = 1.3e-6 * np.tile(scale, (frames, 1)) * 1.5 + 1.2e-5 * np.abs(ref_rows)
     assert np.all(np.abs(our_rows - ref_rows) <= tol)
     assert np.all(our_rows[np.tile(scale, (frames, 1)) == 0] == 0)
+
+
+@pytest.mark.parametrize("n_dq", [1, 2, 9, 31, 100, 140])
+def test_other_dq_atom_counts(n_dq, tmp_path, oracle_mod, capi_mod):
+    """The pair kernel's main loop is instantiated for 42 site atoms per trip (the 44 dQ != 0 atoms of the stock bcx.itp)
+    and for 7 otherwise, with the site blocks padded by neutral entries: excited-state tables with 1 .. 140 non-zero dQ
+    atoms, several frames and a site count that does not fill the last chunk."""
+    O, capi = oracle_mod, capi_mod
+    from cgromcorrfmo_b200 import synth
+    s = synth.make_system(4000, 11, 300 + n_dq, "shared")
+    has_b = np.zeros(140, dtype=bool)
+    has_b[np.random.default_rng(n_dq).permutation(140)[:n_dq]] = True
+    s.bcl_has_b = has_b
+    s.bcl_qB = np.where(has_b, np.round(s.bcl_qA + 0.05 + 0.01 * np.arange(140), 3), s.bcl_qA)
+    traj, top, itp = synth.write_inputs(str(tmp_path), s, 3)
+    ref = O.run(traj, top, itp, 3)
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        assert int(c.get_option("site_cap")) >= max(2, n_dq)
+        dE, done, _ = c.run(0, 3)
+        assert done == 3
+    e, z = scaled_err(dE, ref["dE_f64"], ref["scale"])
+    assert e <= DE_TOL and z == 0.0, (n_dq, e, z)

@@ -53,3 +53,30 @@ def test_gpu_reduction_matches_numpy(small_inputs):
     ok = scale > 0
     assert np.all(np.abs(corr - rc)[ok] <= 1e-9 * scale[ok])
     assert np.allclose(avg, ra, rtol=1e-12, atol=1e-300)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_modes", [1, 5, None])
+def test_gpu_projection_matches_numpy(n_modes, small_inputs):
+    """K4 (cgc_project) against depca's ApplyPCA restated in numpy float64, on the rows and modes of a real run and on
+    frame counts that are not a multiple of the 64-frame tile."""
+    from cgromcorrfmo_b200 import capi
+    traj, top, itp, frames = small_inputs("permol")
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        E, done, _ = c.run(0, frames)
+        S, G = c.n_sites, c.num_tot
+        rng = np.random.default_rng(11)
+        # a longer series with the statistics of the real rows (the run itself is only a few frames long)
+        T = 333
+        X = (E.mean(axis=0)[None] + rng.normal(size=(T, S, G)) * (np.abs(E).mean() + 1e-3)).astype(np.float32)
+        corr, avg = pypca.AvgAndCorrelateSidechains(X)
+        vi, wi, imp = pypca.ComputeModes(corr)
+        W = wi if n_modes is None else wi[:, -n_modes:, :]
+        ref = pypca.ApplyPCA(X, avg, W)
+        got = pypca.ApplyPCA_gpu(c, X, avg, W)
+        assert got.shape == ref.shape == (T, S, W.shape[1])
+        scale = np.einsum("tsg,smg->tsm", np.abs(X.astype(np.float64) - avg[None]), np.abs(W))
+        assert np.all(np.abs(got - ref) <= 1e-13 * scale + 1e-300)
+        with pytest.raises(ValueError):
+            c.project(X[:, :1], avg, W)
