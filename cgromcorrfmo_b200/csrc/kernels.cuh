@@ -5,7 +5,10 @@
 
 namespace cgc {
 
-constexpr int kTileThreads = 256;   // threads per CTA of the pair kernel
+#ifndef CGC_TILE_THREADS
+#define CGC_TILE_THREADS 256          // overridden only by scripts/k2_variants.cu builds
+#endif
+constexpr int kTileThreads = CGC_TILE_THREADS;   // threads per CTA of the pair kernel
 constexpr int kAtomsPerThread = 8;  // environment atoms held in registers by one thread
 constexpr int kTileAtoms = kTileThreads * kAtomsPerThread;
 constexpr int kDecodeThreads = 256; // atom lines per CTA of the decode kernel

@@ -50,7 +50,7 @@ double run(const Data& d, const char* name, int sm_count, double* checksum, int 
 
 int main(int argc, char** argv) {
   Data d; d.F = argc > 1 ? atoi(argv[1]) : 64;
-  d.n_pad = (d.N + 2047) / 2048 * 2048;
+  d.n_pad = (d.N + kTileAtoms - 1) / kTileAtoms * kTileAtoms;
   std::mt19937 rng(1);
   std::uniform_real_distribution<float> U(0.f, 10.f);
   std::normal_distribution<float> Nq(0.f, 0.4f);
@@ -84,13 +84,12 @@ int main(int argc, char** argv) {
   double cs_;
   int sm = prop.multiProcessorCount;
   // reference checksum of the round-1 kernel on the same data (F=128): 2.584917105e+06
+  printf("kTileThreads %d, tile %d atoms, n_pad %d\n", kTileThreads, kTileAtoms, d.n_pad);
   for (int rep = 0; rep < 2; rep++) {
-    run<2, 42, 2>(d, "unroll42 F2F", sm, &cs_, 8);
-    run<2, 42, 6>(d, "unroll42 F2F kq-reload", sm, &cs_, 8);
-    run<2, 42, 4>(d, "unroll42 int kq-reload", sm, &cs_, 8);
-    run<2, 21, 6>(d, "unroll21 F2F kq-reload", sm, &cs_, 8);
-    run<2, 14, 6>(d, "unroll14 F2F kq-reload", sm, &cs_, 8);
-    run<2, 42, 1>(d, "unroll42 NO-EPILOGUE", sm, &cs_, 8);
+    run<2, 42, 0>(d, "unroll42 2 CTA/SM", sm, &cs_, 8);
+    run<2, 42, 1>(d, "unroll42 2 CTA/SM NO-EPI", sm, &cs_, 8);
+    run<1, 42, 0>(d, "unroll42 1 CTA/SM", sm, &cs_, 8);
+    run<3, 42, 0>(d, "unroll42 3 CTA/SM", sm, &cs_, 8);
   }
   return 0;
 }
