@@ -10,6 +10,8 @@
 //   * stdout is quiet unless --verbose (per-frame site totals in cm^-1, the reference's "=<sum> cm-1" log).
 //   * traj_in may be a GROMACS .trr (binary) when --structure some.gro names a .gro of the same system: the authors'
 //     trjconv step (reference scripts/2014-09-trr2dEcsv.sh:22) and its 45-69 bytes of text per atom are skipped.
+//   * --npy additionally writes csv_out.time.npy: the same rows as raw float32 (frames, sites, numTot) in kcal/mol, the
+//     array the pyPCA scripts rebuild from the text (reference scripts/2014-06-csv2hdf5.py:56-74) without the text.
 // Extra flags come AFTER the five positionals.
 #include <unistd.h>
 
@@ -33,6 +35,22 @@ static void on_sigint(int) {
   g_keep_running = 0;
 }
 
+// NumPy .npy v1.0 header for a C-order float32 array (frames, sites, num_tot); rewritten in place once `frames` is known
+// (the header is padded to a fixed 128 bytes so that the rewrite does not move the data).
+static bool write_npy_header(FILE* f, long long frames, int sites, int num_tot) {
+  char dict[112];
+  int n = snprintf(dict, sizeof dict, "{'descr': '<f4', 'fortran_order': False, 'shape': (%lld, %d, %d), }", frames, sites, num_tot);
+  if (n < 0 || n > 116) return false;
+  unsigned char head[128];
+  memset(head, ' ', sizeof head);
+  memcpy(head, "\x93NUMPY\x01\x00", 8);
+  head[8] = 118;  // header length (little endian): 128 - 10
+  head[9] = 0;
+  memcpy(head + 10, dict, (size_t)n);
+  head[127] = '\n';
+  return fseek(f, 0, SEEK_SET) == 0 && fwrite(head, 1, sizeof head, f) == sizeof head;
+}
+
 static double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -54,7 +72,7 @@ int main(int argc, char** argv) {
     printf("Five inputs required for this program.\n");
     printf("Order of args: fmo_traj_path, fmo_top_path, bcx_itp_path, output_path, num_frames "
            "[--sites N] [--mtx-compat] [--no-mtx] [--device D] [--first-frame F] [--batch-frames B] [--verbose] "
-           "[--structure frame0.gro (traj_in is then a .trr)]\n");
+           "[--structure frame0.gro (traj_in is then a .trr)] [--npy]\n");
     return EXIT_FAILURE;
   }
   const std::string traj = argv[1], top = argv[2], itp = argv[3], out = argv[4];
@@ -62,7 +80,7 @@ int main(int argc, char** argv) {
   int sites = 0, device = 0, batch = 0;
   long long first = 0;
   std::string structure;
-  bool compat = false, no_mtx = false, verbose = false, timing = false;
+  bool compat = false, no_mtx = false, verbose = false, timing = false, npy = false;
   for (int i = 6; i < argc; i++) {
     std::string a = argv[i];
     auto val = [&](const char* name) -> const char* {
@@ -81,6 +99,7 @@ int main(int argc, char** argv) {
     else if (a == "--no-mtx") no_mtx = true;
     else if (a == "--verbose") verbose = true;
     else if (a == "--timing") timing = true;
+    else if (a == "--npy") npy = true;
     else {
       fprintf(stderr, "traj2dEcsv: unknown flag %s\n", a.c_str());
       return EXIT_FAILURE;
@@ -123,6 +142,15 @@ int main(int argc, char** argv) {
     cgc_destroy(ctx);
     return EXIT_FAILURE;
   }
+  FILE* npy_file = nullptr;
+  if (npy) {
+    npy_file = fopen((time_path + ".npy").c_str(), "wb");
+    if (!npy_file || !write_npy_header(npy_file, 0, S, num_tot)) {
+      fprintf(stderr, "traj2dEcsv: cannot write %s.npy\n", time_path.c_str());
+      cgc_destroy(ctx);
+      return EXIT_FAILURE;
+    }
+  }
   signal(SIGINT, on_sigint);
   const double t_opened = now_s();
   double t_run = 0, t_wait_writer = 0, t_best_chunk = 1e30;
@@ -161,6 +189,7 @@ int main(int argc, char** argv) {
     const long long base = done_total;
     writer = std::thread([=, &wrc] {
       wrc = cgc_write_time(time_path.c_str(), 0, data, done * S, num_tot);
+      if (npy_file && fwrite(data, sizeof(float), (size_t)done * row, npy_file) != (size_t)done * row) wrc = CGC_ERR_READ;
       if (verbose) {
         for (long long t = 0; t < done; t++) {
           printf("timeCount:%lld Computing site", base + t);
@@ -178,6 +207,10 @@ int main(int argc, char** argv) {
   }
   const double t_loop_end = now_s();
   if (writer.joinable()) writer.join();
+  if (npy_file) {
+    if (!write_npy_header(npy_file, done_total, S, num_tot)) wrc = CGC_ERR_READ;
+    fclose(npy_file);
+  }
   const double t_written = now_s();
   if (wrc != CGC_OK) {
     fprintf(stderr, "traj2dEcsv: cannot write %s\n", time_path.c_str());

@@ -43,6 +43,15 @@ def load_E_t_ia(traj, top, itp, num_frames, sites=7, device=0, units="cm-1"):
     return (dE.astype(np.float64) * CM_PER_KCAL).astype(np.float32)
 
 
+def load_E_t_ia_npy(time_npy_path, units="cm-1"):
+    """The array the CLI wrote with --npy (csv_out.time.npy: float32 (frames, Nsites, Ncoarse) in kcal/mol) as depca's
+    E_t_ia — the text round trip of scripts/2014-06-csv2hdf5.py:56-74 without the text.  Memory-mapped when units="kcal"."""
+    E = np.load(time_npy_path, mmap_mode="r")
+    if units == "kcal":
+        return E
+    return (np.asarray(E, dtype=np.float64) * CM_PER_KCAL).astype(np.float32)
+
+
 def AvgAndCorrelateSidechains_gpu(traj, top, itp, num_frames, sites=7, device=0, units="cm-1"):
     """depca.sidechain_corr.AvgAndCorrelateSidechains (sidechain_corr.py:36-72) without materialising the time series on
     the host: returns (Corr_i_ab [Nsites, Ncoarse, Ncoarse], AvgEia [Nsites, Ncoarse]) — np.cov(rowvar=0) (ddof 1) and the

@@ -568,3 +568,24 @@ def test_other_dq_atom_counts(n_dq, tmp_path, oracle_mod, capi_mod):
         assert done == 3
     e, z = scaled_err(dE, ref["dE_f64"], ref["scale"])
     assert e <= DE_TOL and z == 0.0, (n_dq, e, z)
+
+
+def test_cli_npy_sidecar(small_inputs, capi_mod, tmp_path):
+    """--npy: the rows of csv_out.time as raw float32 (frames, sites, numTot), for the pyPCA scripts."""
+    import subprocess
+    from cgromcorrfmo_b200 import build, pypca
+    traj, top, itp, frames = small_inputs("golden7")
+    out = str(tmp_path / "o")
+    r = subprocess.run([build.CLI, traj, top, itp, out, str(frames + 2), "--npy", "--sites", "7"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    E = np.load(out + ".time.npy")
+    rows = np.array([[float(v) for v in ln.split(",")] for ln in open(out + ".time").read().strip().split("\n")])
+    assert E.dtype == np.float32 and E.shape == (frames, 7, rows.shape[1])
+    cm = pypca.load_E_t_ia_npy(out + ".time.npy")
+    assert np.allclose(cm.reshape(-1, rows.shape[1]), rows, rtol=2e-6, atol=0)      # the text has 6 significant digits
+    with capi_mod.Context(top, itp, 0) as c:
+        c.open(traj)
+        c.set_option("sites", 7)
+        dE, _, _ = c.run(0, frames)
+    d = np.abs(E.astype(np.float64) - dE.astype(np.float64))
+    assert np.all(d <= 1e-6 * np.maximum(np.abs(dE), 1e-3))
