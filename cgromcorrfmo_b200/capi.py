@@ -49,6 +49,8 @@ SIGNATURES = {
     "cgc_set_option": (c_int, [c_void_p, c_char_p, c_double]),
     "cgc_get_option": (c_double, [c_void_p, c_char_p]),
     "cgc_run": (c_int, [c_void_p, c_int64, c_int64, c_void_p, POINTER(c_int64)]),
+    "cgc_run_write_time": (c_int, [c_void_p, c_int64, c_int64, c_char_p, c_int, c_void_p, POINTER(c_int64)]),
+    "cgc_format_text_device": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, POINTER(c_int64), POINTER(c_int)]),
     "cgc_run_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "cgc_decode_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "cgc_kernel_times": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
@@ -292,6 +294,29 @@ class Context:
         if want_dE:
             out = out[: done.value]
         return (out if want_dE else None), done.value, rc
+
+    def run_write_time(self, first_frame: int, n_frames: int, time_path: str, truncate: bool = True, want_dE: bool = False):
+        """run() that also appends the .time text of the processed frames to `time_path`, formatted on the device.
+        Returns (dE or None, frames_done, status)."""
+        S, G = self.n_sites, self.num_tot
+        dE = np.empty((n_frames, S, G), dtype=np.float32) if want_dE else None
+        done = c_int64(0)
+        rc = self._lib.cgc_run_write_time(self._h, first_frame, n_frames, os.fsencode(time_path), 1 if truncate else 0,
+                                          _ptr(dE), ctypes.byref(done))
+        self._check(rc, ok=(CGC_OK, CGC_EOF))
+        return (dE[:done.value] if dE is not None else None), done.value, rc
+
+    def format_text_device(self, values, to_cm: bool = False):
+        """The device "%g" formatter on a 2-D float32 array: returns (text bytes, needs_host flag)."""
+        v = np.ascontiguousarray(values, dtype=np.float32)
+        if v.ndim != 2:
+            raise ValueError("format_text_device wants a 2-D array")
+        cap = v.size * 13 + 16
+        out = np.empty(cap, dtype=np.uint8)
+        n, flag = c_int64(0), c_int(0)
+        self._check(self._lib.cgc_format_text_device(self._h, _ptr(v), v.shape[0], v.shape[1], 1 if to_cm else 0, _ptr(out),
+                                                     cap, ctypes.byref(n), ctypes.byref(flag)))
+        return out[:n.value].tobytes(), flag.value
 
     def run_device(self, d_text, text_bytes: int, atoms_offset, n_frames: int, d_dE, stream=0):
         off = np.ascontiguousarray(atoms_offset, dtype=np.int64)

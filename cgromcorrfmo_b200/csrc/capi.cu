@@ -9,6 +9,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -50,6 +53,13 @@ struct Slot {
   double* d_acc = nullptr;
   float* d_dE = nullptr;
   float* h_dE = nullptr;     // pinned
+  // `.time` text of the batch, formatted on the device (cgc_run_write_time); allocated on first use
+  char* d_ttext = nullptr;
+  char* h_ttext = nullptr;      // pinned
+  int64_t* d_rowoff = nullptr;  // rows + 1
+  int64_t* h_tinfo = nullptr;   // pinned [2]: total bytes, format flags
+  int64_t ttext_cap = 0;
+  std::atomic<bool>* write_pending = nullptr;   // h_ttext is still being written to the file
   cudaEvent_t ev_copied = nullptr, ev_done = nullptr;
   int frames = 0;            // frames of the batch in flight
   int64_t out_frame = 0;     // where its rows go in the caller's dE block
@@ -68,7 +78,7 @@ struct cgc_context {
   const char* text = nullptr;
   int64_t nbytes = 0;
   bool mapped = false;
-  int fd = -1;              // the trajectory file, kept open for threaded pread() into the pinned staging buffers
+  int fd = -1;              // the trajectory file behind the mapping
   FrameLayout L;
   std::vector<FrameSpan> frames;  // frames located so far
   bool index_complete = false;
@@ -94,8 +104,9 @@ struct cgc_context {
   bool dev_pipeline = false;
   int alloc_batch = 0;
   int64_t alloc_text = 0;
-  cudaStream_t st_copy = nullptr, st_comp = nullptr;
+  cudaStream_t st_copy = nullptr, st_comp = nullptr, st_out = nullptr;
   int* d_err = nullptr;
+  int* d_fmt_flags = nullptr;   // K5: a value outside the device formatter's range was met
   int64_t launches = 0;
 
   // optional per-kernel timing (option "profile"): event pairs around each launch of the hot path
@@ -141,6 +152,11 @@ void free_pipeline(cgc_context* c) {
     if (s.d_acc) cudaFree(s.d_acc);
     if (s.d_dE) cudaFree(s.d_dE);
     if (s.h_dE) cudaFreeHost(s.h_dE);
+    if (s.d_ttext) cudaFree(s.d_ttext);
+    if (s.h_ttext) cudaFreeHost(s.h_ttext);
+    if (s.d_rowoff) cudaFree(s.d_rowoff);
+    if (s.h_tinfo) cudaFreeHost(s.h_tinfo);
+    delete s.write_pending;
     if (s.ev_copied) cudaEventDestroy(s.ev_copied);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     s = Slot();
@@ -180,6 +196,8 @@ cgc_context::~cgc_context() {
     for (auto& e : ev_pool) cudaEventDestroy(e);
     if (st_copy) cudaStreamDestroy(st_copy);
     if (st_comp) cudaStreamDestroy(st_comp);
+    if (st_out) cudaStreamDestroy(st_out);
+    if (d_fmt_flags) cudaFree(d_fmt_flags);
     if (d_err) cudaFree(d_err);
   }
   release_text(this);
@@ -309,6 +327,11 @@ void build_static(cgc_context* c) {
   CUDA_OK(cudaMemcpy(sys.slot_dq, slot_dq.data(), sizeof(float) * slot_dq.size(), cudaMemcpyHostToDevice));
   if (!c->st_copy) CUDA_OK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
   if (!c->st_comp) CUDA_OK(cudaStreamCreateWithFlags(&c->st_comp, cudaStreamNonBlocking));
+  if (!c->st_out) CUDA_OK(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
+  if (!c->d_fmt_flags) {
+    CUDA_OK(cudaMalloc(&c->d_fmt_flags, sizeof(int)));
+    CUDA_OK(cudaMemset(c->d_fmt_flags, 0, sizeof(int)));
+  }
   if (!c->d_err) {
     CUDA_OK(cudaMalloc(&c->d_err, sizeof(int)));
     CUDA_OK(cudaMemset(c->d_err, 0, sizeof(int)));
@@ -343,8 +366,10 @@ void ensure_cov(cgc_context* c) {
 }
 
 int default_batch(const cgc_context* c) {
+  // about 192 MB of trajectory per batch: three slots of pinned staging this size cost ~0.2 s to page-lock and as much
+  // to release (512 MB slots: ~1 s, a third of a 4096-frame run), and the streaming rate no longer improves beyond it
   const int64_t frame_text = (int64_t)c->L.n_atoms * c->L.line_bytes + 256;
-  int64_t b = ((int64_t)512 << 20) / frame_text;
+  int64_t b = ((int64_t)192 << 20) / frame_text;
   // the FP64 bins of a batch should stay small next to the text
   const int64_t per_frame_out = (int64_t)c->sys.n_sites * c->sys.num_tot * 12;
   b = std::min<int64_t>(b, ((int64_t)2 << 30) / std::max<int64_t>(1, per_frame_out));
@@ -383,6 +408,103 @@ void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_ho
   c->alloc_text = text_bytes;
 }
 
+// Appends byte ranges to a file from one background thread, in the order they were queued.
+class TextSink {
+ public:
+  explicit TextSink(int fd) : fd_(fd), th_([this] { loop(); }) {}
+  ~TextSink() { finish(); }
+  // `done` is set to false here and to true once the bytes are written (or the sink has failed)
+  void push(const char* p, int64_t n, std::atomic<bool>* done) {
+    if (done) done->store(false);
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      q_.push_back({p, n, done});
+    }
+    cv_.notify_one();
+  }
+  static void wait(std::atomic<bool>* done) {
+    while (done && !done->load()) std::this_thread::yield();
+  }
+  bool finish() {   // drains the queue, joins the thread; returns false when a write failed
+    if (th_.joinable()) {
+      {
+        std::lock_guard<std::mutex> g(mu_);
+        stop_ = true;
+      }
+      cv_.notify_one();
+      th_.join();
+    }
+    return ok_;
+  }
+
+ private:
+  struct Item { const char* p; int64_t n; std::atomic<bool>* done; };
+  void loop() {
+    for (;;) {
+      Item it;
+      {
+        std::unique_lock<std::mutex> g(mu_);
+        cv_.wait(g, [this] { return stop_ || !q_.empty(); });
+        if (q_.empty()) return;
+        it = q_.front();
+        q_.pop_front();
+      }
+      int64_t off = 0;
+      while (ok_ && off < it.n) {
+        ssize_t w = write(fd_, it.p + off, (size_t)(it.n - off));
+        if (w <= 0) ok_ = false; else off += w;
+      }
+      if (it.done) it.done->store(true);
+    }
+  }
+  int fd_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<Item> q_;
+  bool stop_ = false;
+  std::atomic<bool> ok_{true};
+  std::thread th_;
+};
+
+void ensure_time_text(cgc_context* c, int batch) {
+  const int64_t rows = (int64_t)batch * c->sys.n_sites;
+  const int64_t cap = format_time_capacity(rows, c->sys.num_tot) + 64;
+  for (auto& s : c->slot) {
+    if (s.ttext_cap >= cap) continue;
+    if (s.d_ttext) CUDA_OK(cudaFree(s.d_ttext));
+    if (s.h_ttext) CUDA_OK(cudaFreeHost(s.h_ttext));
+    if (s.d_rowoff) CUDA_OK(cudaFree(s.d_rowoff));
+    s.d_ttext = nullptr; s.h_ttext = nullptr; s.d_rowoff = nullptr; s.ttext_cap = 0;
+    CUDA_OK(cudaMalloc(&s.d_ttext, (size_t)cap));
+    CUDA_OK(cudaHostAlloc(&s.h_ttext, (size_t)cap, cudaHostAllocDefault));
+    CUDA_OK(cudaMalloc(&s.d_rowoff, sizeof(int64_t) * (size_t)(rows + 1)));
+    if (!s.h_tinfo) CUDA_OK(cudaHostAlloc(&s.h_tinfo, sizeof(int64_t) * 2, cudaHostAllocDefault));
+    if (!s.write_pending) s.write_pending = new std::atomic<bool>(true);
+    s.ttext_cap = cap;
+  }
+}
+
+// "%g" of a float, as std::ostream << float prints it (precision 6)
+inline int fmt_g(char* p, float v) { return fmt_g6(p, v); }
+
+// format rows [r0, r1) of a float matrix into `out`
+void format_rows(const float* m, int64_t r0, int64_t r1, int ncol, bool to_cm, std::string& out) {
+  out.clear();
+  out.reserve((size_t)(r1 - r0) * ncol * 10);
+  char buf[40];
+  for (int64_t r = r0; r < r1; r++) {
+    const float* row = m + r * ncol;
+    for (int j = 0; j < ncol; j++) {
+      float v = row[j];
+      if (to_cm) v = (float)((double)v * 349.7);  // reference src/FMOparse.cpp:151
+      if (j) out.push_back(',');
+      int n = fmt_g(buf, v);
+      out.append(buf, (size_t)n);
+    }
+    out.push_back('\n');
+  }
+}
+
 // make sure frames [0, upto] are located; returns the number of frames known
 int64_t index_upto(cgc_context* c, int64_t upto) {
   while (!c->index_complete && (int64_t)c->frames.size() <= upto) {
@@ -413,33 +535,13 @@ int64_t index_upto(cgc_context* c, int64_t upto) {
   return (int64_t)c->frames.size();
 }
 
-void parallel_pread(int fd, char* dst, int64_t offset, int64_t n) {
-  const int64_t kMin = 4 << 20;
-  int nt = (int)std::min<int64_t>(std::max(1u, std::min(16u, std::thread::hardware_concurrency())), std::max<int64_t>(1, n / kMin));
-  auto work = [=](int64_t b, int64_t e) {
-    while (b < e) {
-      ssize_t got = pread(fd, dst + b, (size_t)(e - b), (off_t)(offset + b));
-      if (got <= 0) break;  // short file: the frame index never points past the end, so this is an I/O error
-      b += got;
-    }
-  };
-  if (nt <= 1) {
-    work(0, n);
-    return;
-  }
-  std::vector<std::thread> th;
-  const int64_t chunk = ((n + nt - 1) / nt + 4095) & ~(int64_t)4095;
-  for (int i = 0; i < nt; i++) {
-    int64_t b = (int64_t)i * chunk, e = std::min(n, b + chunk);
-    if (b >= e) break;
-    th.emplace_back(work, b, e);
-  }
-  for (auto& t : th) t.join();
-}
-
-void parallel_copy(char* dst, const char* src, int64_t n) {
+// Threaded memcpy.  For trajectory text the source is the read-only mmap of the file: on the B200 box 16 threads copying
+// from a fresh mapping (page faults with fault-around included) move 68-83 GB/s into pinned memory, threaded pread() of
+// the same pages 51-53 GB/s, and cudaHostRegister of a file mapping is refused (scripts/dev_hostregister.cu,
+// profiles/r01_host_staging_paths.log).
+void parallel_copy(char* dst, const char* src, int64_t n, unsigned max_threads = 8) {
   const int64_t kMin = 8 << 20;
-  int nt = (int)std::min<int64_t>(std::max(1u, std::min(8u, std::thread::hardware_concurrency())), std::max<int64_t>(1, n / kMin));
+  int nt = (int)std::min<int64_t>(std::max(1u, std::min(max_threads, std::thread::hardware_concurrency())), std::max<int64_t>(1, n / kMin));
   if (nt <= 1) {
     memcpy(dst, src, (size_t)n);
     return;
@@ -669,13 +771,13 @@ int cgc_open(cgc_context* ctx, const char* traj_path) {
       close(fd);
       throw ReadError("trajectory file is empty or cannot be stat'ed");
     }
-    void* p = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    void* p = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_SHARED, fd, 0);
     if (p == MAP_FAILED) {
       close(fd);
       throw ReadError("mmap of the trajectory failed");
     }
-    // the mapping serves the frame-0 pass and the frame index (a few bytes per frame); the bulk text is pread() by several
-    // threads straight into the pinned staging buffers, which avoids one page fault per 4 KiB of trajectory
+    // the mapping serves the frame-0 pass, the frame index, and the bulk text: several threads memcpy it into the pinned
+    // staging buffers (see parallel_copy)
     ctx->text = (const char*)p;
     ctx->nbytes = sb.st_size;
     ctx->mapped = true;
@@ -712,7 +814,7 @@ int cgc_open_trr(cgc_context* ctx, const char* trr_path, const char* structure_g
       close(fd);
       throw ReadError("trajectory file is empty or cannot be stat'ed");
     }
-    void* p = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    void* p = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_SHARED, fd, 0);
     if (p == MAP_FAILED) {
       close(fd);
       throw ReadError("mmap of the trajectory failed");
@@ -873,7 +975,11 @@ int cgc_decode_errors(cgc_context* ctx, int* flags) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-int cgc_run(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_kcal, int64_t* frames_done) {
+namespace {
+
+// The streaming loop behind cgc_run and cgc_run_write_time.  sink != nullptr: the `.time` text of every batch is formatted
+// on the device (K5) and appended through the sink.
+int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_kcal, int64_t* frames_done, TextSink* sink) {
   if (frames_done) *frames_done = 0;
   if (!ctx) return CGC_ERR_ARG;
   if (!ctx->opened) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
@@ -892,7 +998,9 @@ int cgc_run(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_k
     }
     ensure_pipeline(ctx, B, frame_text_max * B, !direct);
     ensure_cov(ctx);
+    if (sink) ensure_time_text(ctx, B);
     const int64_t sg = (int64_t)sys.n_sites * sys.num_tot;
+    const bool want_rows = dE_kcal != nullptr || sink != nullptr;   // the text path keeps the rows for its host fallback
 
     // The shift c of the Correlate sums is the dE row of the trajectory's frame 0 on EVERY rank (so partial sums of
     // different frame ranges add up).  A run that does not start at frame 0 evaluates frame 0 first, unaccumulated.
@@ -912,11 +1020,28 @@ int cgc_run(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_k
       CUDA_OK(cudaStreamSynchronize(ctx->st_comp));
     }
 
+    std::string fallback_text;
     auto drain = [&](Slot& s) {
       if (!s.busy) return;
       CUDA_OK(cudaEventSynchronize(s.ev_done));
       if (dE_kcal) {
         parallel_copy((char*)(dE_kcal + s.out_frame * sg), (const char*)s.h_dE, (int64_t)sizeof(float) * sg * s.frames);
+      }
+      if (sink) {
+        const int64_t total = s.h_tinfo[0];
+        if (s.h_tinfo[1] != 0 || total < 0 || total > s.ttext_cap) {
+          // a value the device formatter does not cover (non-finite, or outside [1e-16, 1e16)): this batch on the host
+          CUDA_OK(cudaMemset(ctx->d_fmt_flags, 0, sizeof(int)));
+          format_rows(s.h_dE, 0, (int64_t)s.frames * sys.n_sites, sys.num_tot, true, fallback_text);
+          std::atomic<bool> done(false);
+          sink->push(fallback_text.data(), (int64_t)fallback_text.size(), &done);
+          TextSink::wait(&done);
+        } else {
+          // the kernels of this batch are done (ev_done); later batches keep st_comp busy, so the copy goes on its own stream
+          CUDA_OK(cudaMemcpyAsync(s.h_ttext, s.d_ttext, (size_t)total, cudaMemcpyDeviceToHost, ctx->st_out));
+          CUDA_OK(cudaStreamSynchronize(ctx->st_out));
+          sink->push(s.h_ttext, total, s.write_pending);
+        }
       }
       if (frames_done) *frames_done += s.frames;
       s.busy = false;
@@ -943,6 +1068,7 @@ int cgc_run(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_k
       }
       Slot& s = ctx->slot[which];
       drain(s);  // the slot's previous batch must have left before its buffers are reused
+      if (sink) TextSink::wait(s.write_pending);   // ... and its text must be in the file before h_ttext is refilled
       const FrameSpan& fa = ctx->frames[(size_t)f_begin];
       const FrameSpan& fb = ctx->frames[(size_t)(f_begin + want - 1)];
       const int64_t b0 = fa.atoms & ~(int64_t)15;
@@ -954,8 +1080,7 @@ int cgc_run(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_k
       const char* src = ctx->text + b0;
       if (!direct) {
         // page cache / pageable memory -> pinned
-        if (ctx->mapped && ctx->fd >= 0) parallel_pread(ctx->fd, s.h_text, b0, nb);
-        else parallel_copy(s.h_text, src, nb);
+        parallel_copy(s.h_text, src, nb, 16);
         src = s.h_text;
       }
       CUDA_OK(cudaMemcpyAsync(s.d_text, src, (size_t)nb, cudaMemcpyHostToDevice, ctx->st_copy));
@@ -963,8 +1088,16 @@ int cgc_run(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_k
       CUDA_OK(cudaEventRecord(s.ev_copied, ctx->st_copy));
       CUDA_OK(cudaStreamWaitEvent(ctx->st_comp, s.ev_copied, 0));
       enqueue_compute(ctx, s.d_text, nb, s.d_off, want, s.d_xyz8, s.d_sites, s.d_acc, s.d_dE, true, ctx->st_comp);
-      if (dE_kcal) {
+      if (want_rows) {
         CUDA_OK(cudaMemcpyAsync(s.h_dE, s.d_dE, sizeof(float) * (size_t)(sg * want), cudaMemcpyDeviceToHost, ctx->st_comp));
+      }
+      if (sink) {
+        const int64_t rows = (int64_t)want * sys.n_sites;
+        launch_format_time(s.d_dE, rows, sys.num_tot, true, s.d_rowoff, s.d_ttext, ctx->d_fmt_flags, ctx->st_comp);
+        ctx->launches += 3;
+        CUDA_OK(cudaMemcpyAsync(&s.h_tinfo[0], s.d_rowoff + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->st_comp));
+        s.h_tinfo[1] = 0;
+        CUDA_OK(cudaMemcpyAsync(&s.h_tinfo[1], ctx->d_fmt_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->st_comp));
       }
       CUDA_OK(cudaEventRecord(s.ev_done, ctx->st_comp));
       s.frames = want;
@@ -974,6 +1107,9 @@ int cgc_run(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_k
       which = (which + 1) % cgc_context::kSlots;
     }
     for (int i = 0; i < cgc_context::kSlots; i++) drain(ctx->slot[(which + i) % cgc_context::kSlots]);   // oldest first
+    if (sink) {
+      for (auto& sl : ctx->slot) TextSink::wait(sl.write_pending);
+    }
     int flags = 0;
     CUDA_OK(cudaMemcpy(&flags, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
     if (flags) {
@@ -985,6 +1121,69 @@ int cgc_run(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_k
       throw InputFileMalformed(m);
     }
     return done < n_frames ? CGC_EOF : CGC_OK;
+  });
+}
+
+}  // namespace
+
+int cgc_run(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_kcal, int64_t* frames_done) {
+  return run_impl(ctx, first_frame, n_frames, dE_kcal, frames_done, nullptr);
+}
+
+int cgc_run_write_time(cgc_context* ctx, int64_t first_frame, int64_t n_frames, const char* time_path, int truncate,
+                       float* dE_kcal, int64_t* frames_done) {
+  if (frames_done) *frames_done = 0;
+  if (!ctx || !time_path) return fail(ctx, CGC_ERR_ARG, "null argument");
+  int fd = open(time_path, O_WRONLY | O_CREAT | (truncate ? O_TRUNC : O_APPEND), 0644);
+  if (fd < 0) return fail(ctx, CGC_ERR_READ, std::string("cannot open ") + time_path + " for writing");
+  int rc;
+  bool wrote;
+  {
+    TextSink sink(fd);
+    rc = run_impl(ctx, first_frame, n_frames, dE_kcal, frames_done, &sink);
+    wrote = sink.finish();
+  }
+  if (close(fd) != 0) wrote = false;
+  if (!wrote && (rc == CGC_OK || rc == CGC_EOF)) return fail(ctx, CGC_ERR_READ, std::string("write to ") + time_path + " failed");
+  return rc;
+}
+
+int cgc_format_text_device(cgc_context* ctx, const float* values, int64_t rows, int num_col, int to_cm, char* out,
+                           int64_t cap, int64_t* nbytes, int* needs_host) {
+  if (nbytes) *nbytes = 0;
+  if (needs_host) *needs_host = 0;
+  if (!ctx || !values || !out || !nbytes || rows < 0 || num_col < 1) return fail(ctx, CGC_ERR_ARG, "bad argument");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    if (rows == 0) return CGC_OK;
+    if (!ctx->st_comp) CUDA_OK(cudaStreamCreateWithFlags(&ctx->st_comp, cudaStreamNonBlocking));
+    float* d_x = nullptr;
+    char* d_o = nullptr;
+    int64_t* d_off = nullptr;
+    int* d_fl = nullptr;
+    cudaError_t err = cudaSuccess;
+    auto ok = [&](cudaError_t e) { if (err == cudaSuccess) err = e; return e == cudaSuccess; };
+    const int64_t n = rows * num_col, capd = format_time_capacity(rows, num_col);
+    int64_t total = 0;
+    int fl = 0;
+    if (ok(cudaMalloc(&d_x, sizeof(float) * n)) && ok(cudaMalloc(&d_o, (size_t)capd)) &&
+        ok(cudaMalloc(&d_off, sizeof(int64_t) * (rows + 1))) && ok(cudaMalloc(&d_fl, sizeof(int))) &&
+        ok(cudaMemsetAsync(d_fl, 0, sizeof(int), ctx->st_comp)) &&
+        ok(cudaMemcpyAsync(d_x, values, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->st_comp))) {
+      launch_format_time(d_x, rows, num_col, to_cm != 0, d_off, d_o, d_fl, ctx->st_comp);
+      ctx->launches += 3;
+      ok(cudaGetLastError());
+      ok(cudaMemcpyAsync(&total, d_off + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->st_comp));
+      ok(cudaMemcpyAsync(&fl, d_fl, sizeof(int), cudaMemcpyDeviceToHost, ctx->st_comp));
+      ok(cudaStreamSynchronize(ctx->st_comp));
+      if (err == cudaSuccess && total <= cap) ok(cudaMemcpy(out, d_o, (size_t)total, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d_x); cudaFree(d_o); cudaFree(d_off); cudaFree(d_fl);
+    CUDA_OK(err);
+    *nbytes = total;
+    if (needs_host) *needs_host = fl;
+    if (total > cap) throw std::invalid_argument("output buffer too small for the formatted text");
+    return CGC_OK;
   });
 }
 
@@ -1182,27 +1381,6 @@ int cgc_project(cgc_context* ctx, const float* dE_rows, int64_t n_frames, const 
 // writers
 // ---------------------------------------------------------------------------------------------------------------------
 namespace {
-
-// "%g" of a float, as std::ostream << float prints it (precision 6)
-inline int fmt_g(char* p, float v) { return fmt_g6(p, v); }
-
-// format rows [r0, r1) of a float matrix into `out`
-void format_rows(const float* m, int64_t r0, int64_t r1, int ncol, bool to_cm, std::string& out) {
-  out.clear();
-  out.reserve((size_t)(r1 - r0) * ncol * 10);
-  char buf[40];
-  for (int64_t r = r0; r < r1; r++) {
-    const float* row = m + r * ncol;
-    for (int j = 0; j < ncol; j++) {
-      float v = row[j];
-      if (to_cm) v = (float)((double)v * 349.7);  // reference src/FMOparse.cpp:151
-      if (j) out.push_back(',');
-      int n = fmt_g(buf, v);
-      out.append(buf, (size_t)n);
-    }
-    out.push_back('\n');
-  }
-}
 
 int write_matrix_text(const char* path, bool truncate, const float* m, int64_t rows, int ncol, bool to_cm) {
   int fd = open(path, O_WRONLY | O_CREAT | (truncate ? O_TRUNC : O_APPEND), 0644);

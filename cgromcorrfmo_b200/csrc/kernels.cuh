@@ -62,6 +62,11 @@ void launch_cov_accumulate(const float* dE, int n_frames, double* buf, float* co
 // K4: out[t][s][m] = sum_g (x[t][s][g] - mean[s][g]) * modes[s][m][g]  (all DEVICE; centred: n_frames*S*G doubles scratch)
 void launch_project(const float* x, int n_frames, const double* mean, const double* modes, int n_modes, double* centred,
                     double* out, int S, int G, cudaStream_t st);
+// K5: rows of float32 -> the reference's `.time` text on the device (format_kernel.cu).  d_row_off: rows + 1 int64 (scratch;
+// [rows] = total bytes afterwards); d_out: format_time_capacity(rows, ncol) bytes; *d_flags |= 1 when a value needs the host.
+int64_t format_time_capacity(int64_t rows, int ncol);
+void launch_format_time(const float* d_x, int64_t rows, int ncol, bool to_cm, int64_t* d_row_off, char* d_out, int* d_flags,
+                        cudaStream_t st);
 void launch_cov_finalize(const double* buf, int S, int G, int ddof, double* mean, double* cov, cudaStream_t st);
 
 }  // namespace cgc

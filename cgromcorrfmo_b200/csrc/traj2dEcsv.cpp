@@ -10,6 +10,8 @@
 //   * stdout is quiet unless --verbose (per-frame site totals in cm^-1, the reference's "=<sum> cm-1" log).
 //   * traj_in may be a GROMACS .trr (binary) when --structure some.gro names a .gro of the same system: the authors'
 //     trjconv step (reference scripts/2014-09-trr2dEcsv.sh:22) and its 45-69 bytes of text per atom are skipped.
+//   * csv_out.time is formatted on the device (cgc_run_write_time); --host-format uses the host formatter instead
+//     (cgc_run + cgc_write_time, what the first version did; the bytes are the same);
 //   * --npy additionally writes csv_out.time.npy: the same rows as raw float32 (frames, sites, numTot) in kcal/mol, the
 //     array the pyPCA scripts rebuild from the text (reference scripts/2014-06-csv2hdf5.py:56-74) without the text.
 // Extra flags come AFTER the five positionals.
@@ -72,7 +74,7 @@ int main(int argc, char** argv) {
     printf("Five inputs required for this program.\n");
     printf("Order of args: fmo_traj_path, fmo_top_path, bcx_itp_path, output_path, num_frames "
            "[--sites N] [--mtx-compat] [--no-mtx] [--device D] [--first-frame F] [--batch-frames B] [--verbose] "
-           "[--structure frame0.gro (traj_in is then a .trr)] [--npy]\n");
+           "[--structure frame0.gro (traj_in is then a .trr)] [--npy] [--host-format]\n");
     return EXIT_FAILURE;
   }
   const std::string traj = argv[1], top = argv[2], itp = argv[3], out = argv[4];
@@ -80,7 +82,7 @@ int main(int argc, char** argv) {
   int sites = 0, device = 0, batch = 0;
   long long first = 0;
   std::string structure;
-  bool compat = false, no_mtx = false, verbose = false, timing = false, npy = false;
+  bool compat = false, no_mtx = false, verbose = false, timing = false, npy = false, host_format = false;
   for (int i = 6; i < argc; i++) {
     std::string a = argv[i];
     auto val = [&](const char* name) -> const char* {
@@ -100,6 +102,7 @@ int main(int argc, char** argv) {
     else if (a == "--verbose") verbose = true;
     else if (a == "--timing") timing = true;
     else if (a == "--npy") npy = true;
+    else if (a == "--host-format") host_format = true;
     else {
       fprintf(stderr, "traj2dEcsv: unknown flag %s\n", a.c_str());
       return EXIT_FAILURE;
@@ -156,7 +159,9 @@ int main(int argc, char** argv) {
   double t_run = 0, t_wait_writer = 0, t_best_chunk = 1e30;
   long long best_chunk_frames = 0;
 
-  const long long chunk = 4LL * (long long)cgc_get_option(ctx, "batch_frames");
+  // frames per cgc_run call: long enough to amortise the call's batch-size ramp, short enough that formatting chunk i
+  // overlaps computing chunk i+1 from early on
+  const long long chunk = 16LL * (long long)cgc_get_option(ctx, "batch_frames");
   const size_t row = (size_t)S * num_tot;
   std::vector<float> buf[2];
   std::thread writer;
@@ -166,10 +171,12 @@ int main(int argc, char** argv) {
   bool eof = false;
   while (done_total < num_frames && g_keep_running && !eof) {
     const long long n = std::min(chunk, num_frames - done_total);
-    buf[which].resize((size_t)n * row);
+    if (host_format || verbose || npy_file != nullptr) buf[which].resize((size_t)n * row);
     int64_t done = 0;
     double t0 = now_s();
-    rc = cgc_run(ctx, first + done_total, n, buf[which].data(), &done);
+    const bool need_rows = host_format || verbose || npy_file != nullptr;
+    if (host_format) rc = cgc_run(ctx, first + done_total, n, buf[which].data(), &done);
+    else rc = cgc_run_write_time(ctx, first + done_total, n, time_path.c_str(), 0, need_rows ? buf[which].data() : nullptr, &done);
     const double t_chunk = now_s() - t0;
     t_run += t_chunk;
     if (done == n && t_chunk / (double)n < t_best_chunk / (double)std::max<long long>(1, best_chunk_frames)) {
@@ -188,7 +195,7 @@ int main(int argc, char** argv) {
     const float* data = buf[which].data();
     const long long base = done_total;
     writer = std::thread([=, &wrc] {
-      wrc = cgc_write_time(time_path.c_str(), 0, data, done * S, num_tot);
+      if (host_format) wrc = cgc_write_time(time_path.c_str(), 0, data, done * S, num_tot);
       if (npy_file && fwrite(data, sizeof(float), (size_t)done * row, npy_file) != (size_t)done * row) wrc = CGC_ERR_READ;
       if (verbose) {
         for (long long t = 0; t < done; t++) {

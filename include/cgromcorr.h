@@ -112,6 +112,17 @@ double cgc_get_option(const cgc_context *ctx, const char *key);
  * accumulates the Correlate sums (K3).  dE_kcal (nullable) receives float32 [n][sites][numTot], caller-owned HOST memory.
  * Returns CGC_OK, or CGC_EOF with *frames_done < n when the trajectory ends early. */
 int cgc_run(cgc_context *ctx, int64_t first_frame, int64_t n_frames, float *dE_kcal, int64_t *frames_done);
+/* cgc_run that also appends the `.time` rows of the frames it processed to `time_path` (truncate != 0 empties the file
+ * first, src/FMOparse.cpp:48-50) — the text of src/FMOparse.cpp:151-165, byte for byte what cgc_write_time prints for the
+ * same rows, but formatted ON THE DEVICE (K5, csrc/format_kernel.cu) and written by a background thread, so the host cores
+ * are left to stage the trajectory.  dE_kcal may be NULL when the caller wants the file only. */
+int cgc_run_write_time(cgc_context *ctx, int64_t first_frame, int64_t n_frames, const char *time_path, int truncate,
+                       float *dE_kcal, int64_t *frames_done);
+/* The device formatter on its own (HOST in, HOST out): rows x num_col float32 -> "%g" text, ',' between values, '\n' after
+ * each row; to_cm != 0 applies float(double(v) * 349.7) first.  *needs_host != 0 when a value was non-finite or outside
+ * [1e-16, 1e16) in magnitude (printed as '?': cgc_write_time handles those).  cap >= rows * num_col * 13 always suffices. */
+int cgc_format_text_device(cgc_context *ctx, const float *values, int64_t rows, int num_col, int to_cm, char *out,
+                           int64_t cap, int64_t *nbytes, int *needs_host);
 
 /* Same computation on text that is already in DEVICE memory (d_text 16-byte aligned; atoms_offset[f] = byte offset of
  * the first atom line of frame f, HOST array).  d_dE_kcal: DEVICE float32 [n_frames][sites][numTot].  Work is enqueued

@@ -582,7 +582,7 @@ def test_cli_npy_sidecar(small_inputs, capi_mod, tmp_path):
     rows = np.array([[float(v) for v in ln.split(",")] for ln in open(out + ".time").read().strip().split("\n")])
     assert E.dtype == np.float32 and E.shape == (frames, 7, rows.shape[1])
     cm = pypca.load_E_t_ia_npy(out + ".time.npy")
-    assert np.allclose(cm.reshape(-1, rows.shape[1]), rows, rtol=2e-6, atol=0)      # the text has 6 significant digits
+    assert np.allclose(cm.reshape(-1, rows.shape[1]), rows, rtol=6e-6, atol=0)      # the text has 6 significant digits
     with capi_mod.Context(top, itp, 0) as c:
         c.open(traj)
         c.set_option("sites", 7)
