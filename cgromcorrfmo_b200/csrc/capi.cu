@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -408,37 +409,44 @@ void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_ho
   c->alloc_text = text_bytes;
 }
 
-// Appends byte ranges to a file from one background thread, in the order they were queued.
+// Appends byte ranges to a file from a background thread.  Every range gets its file offset when it is queued (the sizes
+// are known then) and is written with pwrite().  One thread is the default: page-cache writes ran at 3.4-5.6 GB/s from one
+// thread on the B200 box and no faster from four (they serialise on the inode), while the `.time` text of the C2 workload
+// needs 240 kB per frame — 2.6 GB/s at 11k frames/s.
 class TextSink {
  public:
-  explicit TextSink(int fd) : fd_(fd), th_([this] { loop(); }) {}
+  explicit TextSink(int fd, int n_threads = 1) : fd_(fd) {
+    const off_t end = lseek(fd, 0, SEEK_END);
+    next_off_ = end < 0 ? 0 : (int64_t)end;
+    for (int i = 0; i < n_threads; i++) th_.emplace_back([this] { loop(); });
+  }
   ~TextSink() { finish(); }
   // `done` is set to false here and to true once the bytes are written (or the sink has failed)
   void push(const char* p, int64_t n, std::atomic<bool>* done) {
     if (done) done->store(false);
     {
       std::lock_guard<std::mutex> g(mu_);
-      q_.push_back({p, n, done});
+      q_.push_back({p, n, next_off_, done});
+      next_off_ += n;
     }
     cv_.notify_one();
   }
   static void wait(std::atomic<bool>* done) {
     while (done && !done->load()) std::this_thread::yield();
   }
-  bool finish() {   // drains the queue, joins the thread; returns false when a write failed
-    if (th_.joinable()) {
-      {
-        std::lock_guard<std::mutex> g(mu_);
-        stop_ = true;
-      }
-      cv_.notify_one();
-      th_.join();
+  bool finish() {   // drains the queue, joins the threads; returns false when a write failed
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      stop_ = true;
     }
+    cv_.notify_all();
+    for (auto& t : th_)
+      if (t.joinable()) t.join();
     return ok_;
   }
 
  private:
-  struct Item { const char* p; int64_t n; std::atomic<bool>* done; };
+  struct Item { const char* p; int64_t n; int64_t off; std::atomic<bool>* done; };
   void loop() {
     for (;;) {
       Item it;
@@ -451,19 +459,20 @@ class TextSink {
       }
       int64_t off = 0;
       while (ok_ && off < it.n) {
-        ssize_t w = write(fd_, it.p + off, (size_t)(it.n - off));
+        ssize_t w = pwrite(fd_, it.p + off, (size_t)(it.n - off), (off_t)(it.off + off));
         if (w <= 0) ok_ = false; else off += w;
       }
       if (it.done) it.done->store(true);
     }
   }
   int fd_;
+  int64_t next_off_ = 0;
   std::mutex mu_;
   std::condition_variable cv_;
   std::deque<Item> q_;
   bool stop_ = false;
   std::atomic<bool> ok_{true};
-  std::thread th_;
+  std::vector<std::thread> th_;
 };
 
 void ensure_time_text(cgc_context* c, int batch) {
@@ -1020,13 +1029,23 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       CUDA_OK(cudaStreamSynchronize(ctx->st_comp));
     }
 
+    // host-side time of this call by phase, printed when CGC_TRACE is set (developer aid)
+    const bool trace = getenv("CGC_TRACE") != nullptr;
+    double t_wait_gpu = 0, t_rows = 0, t_text = 0, t_stage = 0, t_enqueue = 0, t_wait_file = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_call0 = now();
     std::string fallback_text;
     auto drain = [&](Slot& s) {
       if (!s.busy) return;
+      double t0 = now();
       CUDA_OK(cudaEventSynchronize(s.ev_done));
+      t_wait_gpu += now() - t0;
+      t0 = now();
       if (dE_kcal) {
         parallel_copy((char*)(dE_kcal + s.out_frame * sg), (const char*)s.h_dE, (int64_t)sizeof(float) * sg * s.frames);
       }
+      t_rows += now() - t0;
+      t0 = now();
       if (sink) {
         const int64_t total = s.h_tinfo[0];
         if (s.h_tinfo[1] != 0 || total < 0 || total > s.ttext_cap) {
@@ -1043,6 +1062,7 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
           sink->push(s.h_ttext, total, s.write_pending);
         }
       }
+      t_text += now() - t0;
       if (frames_done) *frames_done += s.frames;
       s.busy = false;
     };
@@ -1068,7 +1088,11 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       }
       Slot& s = ctx->slot[which];
       drain(s);  // the slot's previous batch must have left before its buffers are reused
-      if (sink) TextSink::wait(s.write_pending);   // ... and its text must be in the file before h_ttext is refilled
+      if (sink) {   // ... and its text must be in the file before h_ttext is refilled
+        const double t0 = now();
+        TextSink::wait(s.write_pending);
+        t_wait_file += now() - t0;
+      }
       const FrameSpan& fa = ctx->frames[(size_t)f_begin];
       const FrameSpan& fb = ctx->frames[(size_t)(f_begin + want - 1)];
       const int64_t b0 = fa.atoms & ~(int64_t)15;
@@ -1078,11 +1102,14 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       if (nb > ctx->alloc_text) throw std::runtime_error("internal: batch text larger than the staging buffer");
       for (int i = 0; i < want; i++) s.h_off[i] = ctx->frames[(size_t)(f_begin + i)].atoms - b0;
       const char* src = ctx->text + b0;
+      const double t_stage0 = now();
       if (!direct) {
         // page cache / pageable memory -> pinned
         parallel_copy(s.h_text, src, nb, 16);
         src = s.h_text;
       }
+      t_stage += now() - t_stage0;
+      const double t_enq0 = now();
       CUDA_OK(cudaMemcpyAsync(s.d_text, src, (size_t)nb, cudaMemcpyHostToDevice, ctx->st_copy));
       CUDA_OK(cudaMemcpyAsync(s.d_off, s.h_off, sizeof(int64_t) * want, cudaMemcpyHostToDevice, ctx->st_copy));
       CUDA_OK(cudaEventRecord(s.ev_copied, ctx->st_copy));
@@ -1100,6 +1127,7 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
         CUDA_OK(cudaMemcpyAsync(&s.h_tinfo[1], ctx->d_fmt_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->st_comp));
       }
       CUDA_OK(cudaEventRecord(s.ev_done, ctx->st_comp));
+      t_enqueue += now() - t_enq0;
       s.frames = want;
       s.out_frame = done;
       s.busy = true;
@@ -1108,7 +1136,14 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
     }
     for (int i = 0; i < cgc_context::kSlots; i++) drain(ctx->slot[(which + i) % cgc_context::kSlots]);   // oldest first
     if (sink) {
+      const double t0 = now();
       for (auto& sl : ctx->slot) TextSink::wait(sl.write_pending);
+      t_wait_file += now() - t0;
+    }
+    if (trace) {
+      fprintf(stderr, "cgc trace: %lld frames in %.1f ms | host: staging copy %.1f, enqueue %.1f, wait for GPU %.1f, rows to caller %.1f, "
+                      "text D2H+queue %.1f, wait for file %.1f ms\n", (long long)done, (now() - t_call0) * 1e3, t_stage * 1e3,
+              t_enqueue * 1e3, t_wait_gpu * 1e3, t_rows * 1e3, t_text * 1e3, t_wait_file * 1e3);
     }
     int flags = 0;
     CUDA_OK(cudaMemcpy(&flags, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1134,7 +1169,7 @@ int cgc_run_write_time(cgc_context* ctx, int64_t first_frame, int64_t n_frames, 
                        float* dE_kcal, int64_t* frames_done) {
   if (frames_done) *frames_done = 0;
   if (!ctx || !time_path) return fail(ctx, CGC_ERR_ARG, "null argument");
-  int fd = open(time_path, O_WRONLY | O_CREAT | (truncate ? O_TRUNC : O_APPEND), 0644);
+  int fd = open(time_path, O_WRONLY | O_CREAT | (truncate ? O_TRUNC : 0), 0644);   // the sink appends by offset (pwrite)
   if (fd < 0) return fail(ctx, CGC_ERR_READ, std::string("cannot open ") + time_path + " for writing");
   int rc;
   bool wrote;

@@ -26,7 +26,7 @@ for name, args in (("gro", [d + "/traj.gro", top, itp, d + "/out_gro", str(frame
                    ("trr", [d + "/traj.trr", top, itp, d + "/out_trr", str(frames), "--structure", d + "/frame0.gro"])):
     for rep in range(2):
         t0 = time.time()
-        r = subprocess.run([build.CLI] + args + ["--timing"], capture_output=True, text=True)
+        r = subprocess.run([build.CLI] + args + ["--timing"], capture_output=True, text=True, env=dict(os.environ, CGC_TRACE="1") if rep == 1 else None)
         dt = time.time() - t0
-        print("%-14s rep %d rc %d wall %.2f s = %.0f frames/s | %s" % (name, rep, r.returncode, dt, frames / dt, r.stderr.strip()[-600:]), flush=True)
+        print("%-14s rep %d rc %d wall %.2f s = %.0f frames/s | %s" % (name, rep, r.returncode, dt, frames / dt, r.stderr.strip()[-1800:]), flush=True)
 print(".time size %.2f GB" % (os.path.getsize(d + "/out_gro.time") / 1e9))
