@@ -352,6 +352,16 @@ def run_ours(args):
             ms_total = float(t.item())
         value = world * args.steps * F / (ms_total / 1e3)
 
+        if args.device_leg_only:
+            ctx.close()
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                                  "ms_per_step": ms_total / args.steps, "device_leg_only": True,
+                                  "kernel_ms": {k: v[0] for k, v in ktimes.items()}, "gpu_launches": int(launches)}))
+            if world > 1:
+                dist.destroy_process_group()
+            return 0
+
         # ---------------- end to end through cgc_run: pinned host text in, dE rows out to host memory
         out_host = np.empty((F, S, G), dtype=np.float32)
         ctx.set_option("batch_frames", args.e2e_batch)               # several batches per call: H2D overlaps the kernels
@@ -515,6 +525,9 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=128)
     ap.add_argument("--e2e-batch", type=int, default=32, help="frames per device batch inside cgc_run (e2e leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-leg-only", action="store_true",
+                    help="profiling aid: run only the device-resident leg (the ncu launch list then holds nothing but "
+                         "the 128-frame launches whose shares bench.py reports in kernel_ms); prints a reduced JSON line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
