@@ -125,6 +125,10 @@ struct cgc_context {
   float* d_compat = nullptr;  // float32 [2][S*G]
   double* d_centred = nullptr;  // scratch: centred FP64 rows of the batch being accumulated
   int64_t centred_frames = 0;
+  // rows waiting for K3: the streaming loop gathers the float32 rows of small batches here and runs the Correlate kernels
+  // once per kCovGather frames (their write-back touches all S*G*G sums, whatever the batch size)
+  float* d_cov_rows = nullptr;
+  int64_t cov_rows_cap = 0, cov_rows_pending = 0;
 
   ~cgc_context();
 };
@@ -183,6 +187,9 @@ void free_static(cgc_context* c) {
   if (c->d_centred) cudaFree(c->d_centred);
   c->d_centred = nullptr;
   c->centred_frames = 0;
+  if (c->d_cov_rows) cudaFree(c->d_cov_rows);
+  c->d_cov_rows = nullptr;
+  c->cov_rows_cap = c->cov_rows_pending = 0;
   c->shift_set = false;
   c->dev_static = false;
 }
@@ -619,6 +626,47 @@ double* centred_scratch(cgc_context* c, int n_frames) {
   return c->d_centred;
 }
 
+constexpr int64_t kCovGather = 128;
+
+// run K3 on the gathered rows
+void flush_cov_rows(cgc_context* c, cudaStream_t st) {
+  if (c->cov_rows_pending <= 0) return;
+  const DeviceSystem& sys = c->sys;
+  const int n = (int)c->cov_rows_pending;
+  {
+    ScopedKernelTimer t(c, 3, st);
+    launch_cov_accumulate(c->d_cov_rows, n, c->d_cov, c->d_compat, centred_scratch(c, n), sys.n_sites, sys.num_tot, st);
+  }
+  c->launches += 2;
+  c->cov_rows_pending = 0;
+}
+
+// hand the rows of one batch to K3: directly when the batch is large, through the gather buffer otherwise
+void accumulate_rows(cgc_context* c, const float* d_dE, int n_frames, cudaStream_t st) {
+  const DeviceSystem& sys = c->sys;
+  const int64_t sg = (int64_t)sys.n_sites * sys.num_tot;
+  if (n_frames >= kCovGather && c->cov_rows_pending == 0) {
+    ScopedKernelTimer t(c, 3, st);
+    launch_cov_accumulate(d_dE, n_frames, c->d_cov, c->d_compat, centred_scratch(c, n_frames), sys.n_sites, sys.num_tot, st);
+    c->launches += 2;
+    return;
+  }
+  const int64_t cap = std::max<int64_t>(kCovGather, n_frames);
+  if (c->cov_rows_cap < cap) {
+    flush_cov_rows(c, st);
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (c->d_cov_rows) CUDA_OK(cudaFree(c->d_cov_rows));
+    c->d_cov_rows = nullptr;
+    CUDA_OK(cudaMalloc(&c->d_cov_rows, sizeof(float) * (size_t)(cap * sg)));
+    c->cov_rows_cap = cap;
+  }
+  if (c->cov_rows_pending + n_frames > c->cov_rows_cap) flush_cov_rows(c, st);
+  CUDA_OK(cudaMemcpyAsync(c->d_cov_rows + c->cov_rows_pending * sg, d_dE, sizeof(float) * (size_t)(n_frames * sg),
+                          cudaMemcpyDeviceToDevice, st));
+  c->cov_rows_pending += n_frames;
+  if (c->cov_rows_pending >= kCovGather) flush_cov_rows(c, st);
+}
+
 // K1 -> K2 -> finish (-> K3) for one batch whose text is already in d_text; everything on `st`
 void enqueue_compute(cgc_context* c, const char* d_text, int64_t text_bytes, const int64_t* d_off, int n_frames,
                      float* d_xyz8, float4* d_sites, double* d_acc, float* d_dE, bool accumulate, cudaStream_t st) {
@@ -642,11 +690,7 @@ void enqueue_compute(cgc_context* c, const char* d_text, int64_t text_bytes, con
       c->shift_set = true;
       c->launches++;
     }
-    {
-      ScopedKernelTimer t(c, 3, st);
-      launch_cov_accumulate(d_dE, n_frames, c->d_cov, c->d_compat, centred_scratch(c, n_frames), sys.n_sites, sys.num_tot, st);
-    }
-    c->launches += 2;
+    accumulate_rows(c, d_dE, n_frames, st);
   }
   CUDA_OK(cudaGetLastError());
 }
@@ -1008,6 +1052,7 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
     ensure_pipeline(ctx, B, frame_text_max * B, !direct);
     ensure_cov(ctx);
     if (sink) ensure_time_text(ctx, B);
+    ctx->cov_rows_pending = 0;   // non-zero only after a call that ended in an error
     const int64_t sg = (int64_t)sys.n_sites * sys.num_tot;
     const bool want_rows = dE_kcal != nullptr || sink != nullptr;   // the text path keeps the rows for its host fallback
 
@@ -1067,6 +1112,10 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       s.busy = false;
     };
 
+    // crude per-frame model: host->device copy at ~45 GB/s against the pair kernel at ~0.8 of its 16 pairs/clk/SM ceiling
+    const double copy_s = (double)frame_text_max / 45e9;
+    const double pair_s = (double)sys.n_sites * sys.site_cap * sys.n_atoms / (0.8 * 16.0 * ctx->sm_count * 1.9e9);
+    const bool ramp_down = copy_s > pair_s;
     int64_t done = 0;
     int which = 0;
     bool eof = false;
@@ -1078,7 +1127,9 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       {
         const int64_t min_b = std::max<int64_t>(1, B / 4), left = n_frames - done;
         want = (int)std::min<int64_t>(want, done + min_b);
-        if (left > min_b) want = (int)std::min<int64_t>(want, std::max<int64_t>(min_b, (left + 1) / 2));
+        // the ramp down only pays when the copies are the bottleneck (text): a compute-bound stream (.trr) would just
+        // finish on small, less efficient launches
+        if (ramp_down && left > min_b) want = (int)std::min<int64_t>(want, std::max<int64_t>(min_b, (left + 1) / 2));
       }
       const int64_t known = index_upto(ctx, f_begin + want - 1);
       if (known < f_begin + want) {
@@ -1134,7 +1185,9 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       done += want;
       which = (which + 1) % cgc_context::kSlots;
     }
+    flush_cov_rows(ctx, ctx->st_comp);   // rows still gathered for K3
     for (int i = 0; i < cgc_context::kSlots; i++) drain(ctx->slot[(which + i) % cgc_context::kSlots]);   // oldest first
+    CUDA_OK(cudaStreamSynchronize(ctx->st_comp));
     if (sink) {
       const double t0 = now();
       for (auto& sl : ctx->slot) TextSink::wait(sl.write_pending);
@@ -1279,6 +1332,7 @@ int cgc_cov_bind(cgc_context* ctx, double* d_buffer) {
     ctx->d_cov = d_buffer;
     ctx->cov_bound = true;
     ctx->shift_set = false;
+    ctx->cov_rows_pending = 0;
     CUDA_OK(cudaMemset(ctx->d_cov, 0, sizeof(double) * cov_doubles(ctx)));
     ensure_cov(ctx);
     const int64_t SG = (int64_t)ctx->sys.n_sites * ctx->sys.num_tot;
@@ -1297,6 +1351,7 @@ int cgc_cov_reset(cgc_context* ctx) {
     CUDA_OK(cudaMemset(ctx->d_cov, 0, sizeof(double) * cov_doubles(ctx)));
     CUDA_OK(cudaMemset(ctx->d_compat, 0, sizeof(float) * 2 * SG));
     ctx->shift_set = false;
+    ctx->cov_rows_pending = 0;
     return CGC_OK;
   });
 }
