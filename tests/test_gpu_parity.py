@@ -589,3 +589,41 @@ def test_cli_npy_sidecar(small_inputs, capi_mod, tmp_path):
         dE, _, _ = c.run(0, frames)
     d = np.abs(E.astype(np.float64) - dE.astype(np.float64))
     assert np.all(d <= 1e-6 * np.maximum(np.abs(dE), 1e-3))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_shapes_against_oracle(seed, tmp_path, oracle_mod, capi_mod):
+    """Random small systems: atom counts that are not a multiple of the 2048-atom tile or the 256-line decode chunk, 1..13
+    chromophores, 1..9 frames, every batch size — the pair kernel's unit ranges then start and end in the middle of a
+    (frame, tile) and its chunk size varies with the launch."""
+    O, capi = oracle_mod, capi_mod
+    from cgromcorrfmo_b200 import synth
+    rng = np.random.default_rng(1000 + seed)
+    n_bcl = int(rng.choice([1, 2, 3, 5, 8, 13]))
+    n_atoms = int(n_bcl * 140 * 1.3) + int(rng.integers(50, 6000))
+    frames = int(rng.integers(1, 10))
+    solvent = str(rng.choice(["shared", "per_molecule", "none"]))
+    s = synth.make_system(n_atoms, n_bcl, 500 + seed, solvent)
+    traj, top, itp = synth.write_inputs(str(tmp_path), s, frames, velocities=bool(rng.integers(0, 2)))
+    ref = O.run(traj, top, itp, frames)
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        assert np.array_equal(c.groups(), ref["groups"])
+        c.set_option("batch_frames", int(rng.integers(1, frames + 2)))
+        first = int(rng.integers(0, frames))
+        dE, done, rc = c.run(first, frames)                       # over-asks unless first == 0
+        assert done == frames - first
+        e, z = scaled_err(dE, ref["dE_f64"][first:], ref["scale"][first:])
+        assert e <= DE_TOL and z == 0.0, (seed, n_atoms, n_bcl, frames, solvent, e, z)
+        sites = int(rng.integers(1, n_bcl + 1))
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        c.set_option("sites", sites)
+        dE, done, rc = c.run(0, frames)
+        e, z = scaled_err(dE, ref["dE_f64"][:, :sites], ref["scale"][:, :sites])
+        assert dE.shape[1] == sites and e <= DE_TOL and z == 0.0
+        if done > 1 and c.cov_size():
+            mean, cov = c.cov_finalize(0)
+            _, c64 = O.cov_f64(dE, 0)
+            cs = np.maximum(np.abs(c64), np.sqrt(np.einsum("sii,sjj->sij", c64, c64)))
+            assert np.all(np.abs(cov - c64)[cs > 0] <= COV_TOL * cs[cs > 0])
