@@ -5,6 +5,7 @@
 #include <vector>
 #include <random>
 #include <cmath>
+#include <string>
 #include "cdc_kernel.cuh"
 
 using namespace cgc;
@@ -59,7 +60,8 @@ int main(int argc, char** argv) {
   int a = 0, g = 24;
   while (a < 16500) { int k = 7 + rng() % 18; for (int i = 0; i < k && a < 16500; i++) col[a++] = g; g++; }
   for (int s = 0; s < 24; s++) for (int i = 0; i < 140; i++) col[a++] = s;
-  for (; a < d.N; a++) col[a] = g;
+  const bool permol = argc > 2 && std::string(argv[2]) == "permol";   // every 3 solvent atoms their own column (C4-like)
+  { int a_s = a; for (; a < d.N; a++) col[a] = permol ? g + (a - a_s) / 3 : g; g = col[d.N - 1]; }
   d.G = g + 1;
   for (int i = 0; i < d.N; i++) kq[i] = 33.2 * Nq(rng);
   std::vector<float> xyz((size_t)d.F * d.n_pad * 3, 0.f);
