@@ -140,6 +140,7 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
   f32x2 X[4], Y[4], Z[4];
   double kq[8];
   const int32_t* col_ptr = col_all;   // this thread's 8 columns (re-read from L1 by the mixed-group epilogue only)
+  unsigned run_mask = 0;              // bit e: atom e ends a run of equal, real columns; bit 8+e: atom e starts a run
   bool warp_uniform = false;
   int c_lane0 = -1;
   double* acc_frame = acc;
@@ -178,6 +179,16 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
       }
       const bool same = c0.y == c0.x && c0.z == c0.x && c0.w == c0.x && c1.x == c0.x && c1.y == c0.x && c1.z == c0.x &&
                         c1.w == c0.x;
+      {
+        const int ce[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        run_mask = 1u << 8;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          const bool end = e == 7 || ce[e + 1] != ce[e];
+          if (end && ce[e] >= 0) run_mask |= 1u << e;
+          if (end && e < 7) run_mask |= 1u << (9 + e);
+        }
+      }
       c_lane0 = __shfl_sync(0xffffffffu, c0.x, 0);
       // whole warp inside one environment group (columns < 0 are padding)
       warp_uniform = __all_sync(0xffffffffu, same && c0.x == c_lane0) && c_lane0 >= 0;
@@ -209,18 +220,15 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
         const int4 c0 = __ldg(reinterpret_cast<const int4*>(col_ptr));
         const int4 c1 = __ldg(reinterpret_cast<const int4*>(col_ptr + 4));
         const int cols[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        // branch-free segmented sum: the run structure is a per-item bit mask, the flush a predicated reduction
         double run = 0.0;
-        int cc = cols[0];
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-          if (cols[e] != cc) {
-            if (cc >= 0 && cc != s) atomicAdd(acc_row + cc, run);   // own-site column: reference src/grom2atomFMO.cpp:674
-            cc = cols[e];
-            run = 0.0;
-          }
-          run += f2d<kBits>(Vf[e]) * kq[e];
+          const double w = f2d<kBits>(Vf[e]) * kq[e];
+          run = ((run_mask >> (8 + e)) & 1u) ? w : run + w;
+          // own-site column: reference src/grom2atomFMO.cpp:674
+          if (((run_mask >> e) & 1u) && cols[e] != s) atomicAdd(acc_row + cols[e], run);
         }
-        if (cc >= 0 && cc != s) atomicAdd(acc_row + cc, run);
       }
     };
 

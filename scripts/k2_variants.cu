@@ -88,10 +88,8 @@ int main(int argc, char** argv) {
   // reference checksum of the round-1 kernel on the same data (F=128): 2.584917105e+06
   printf("kTileThreads %d, tile %d atoms, n_pad %d\n", kTileThreads, kTileAtoms, d.n_pad);
   for (int rep = 0; rep < 2; rep++) {
-    run<2, 42, 0>(d, "unroll42 2 CTA/SM", sm, &cs_, 8);
-    run<2, 42, 1>(d, "unroll42 2 CTA/SM NO-EPI", sm, &cs_, 8);
-    run<1, 42, 0>(d, "unroll42 1 CTA/SM", sm, &cs_, 8);
-    run<3, 42, 0>(d, "unroll42 3 CTA/SM", sm, &cs_, 8);
+    run<2, 42, 0>(d, "unroll42", sm, &cs_, 8);
+    run<2, 42, 1>(d, "unroll42 NO-EPI", sm, &cs_, 8);
   }
   return 0;
 }
