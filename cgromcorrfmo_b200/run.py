@@ -29,7 +29,11 @@ def traj2dEcsv(traj, top, itp, out, num_frames, sites=0, mtx_compat=False, chunk
         cdist.bind_to_gpu_numa(local)           # pinned staging buffers land on the GPU's own NUMA node
     if world > 1 and not tdist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        backend = os.environ.get("CGC_DIST_BACKEND", "nccl")    # "gloo" lets two test ranks share one GPU
+        if backend == "nccl":
+            tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            tdist.init_process_group(backend)
     with capi.Context(top, itp, local) as c:
         c.open(traj)
         if sites:
@@ -43,14 +47,13 @@ def traj2dEcsv(traj, top, itp, out, num_frames, sites=0, mtx_compat=False, chunk
             c.cov_bind(cov.data_ptr())
         part = out + (".time.part%d" % rank if world > 1 else ".time")
         capi.write_time(part, np.empty((0, G), np.float32), truncate=True)
-        step = chunk_frames or 4 * int(c.get_option("batch_frames"))
+        step = chunk_frames or 16 * int(c.get_option("batch_frames"))
         done = 0
         while done < count:
             n = min(step, count - done)
-            dE, got, rc = c.run(first + done, n)
-            capi.write_time(part, dE, truncate=False)
+            _, got, rc = c.run_write_time(first + done, n, part, truncate=False)   # text formatted on the device (K5)
             done += got
-            if rc == capi.CGC_EOF:
+            if rc == capi.CGC_EOF or got == 0:
                 break
         if world > 1:
             if cov is not None:
@@ -71,8 +74,9 @@ def main(argv=None):
     ap.add_argument("num_frames", type=int)
     ap.add_argument("--sites", type=int, default=0)
     ap.add_argument("--mtx-compat", action="store_true")
+    ap.add_argument("--device", type=int, default=None, help="CUDA device for this rank (default: LOCAL_RANK)")
     a = ap.parse_args(argv)
-    traj2dEcsv(a.traj_in, a.topology, a.excited_itp, a.csv_out, a.num_frames, a.sites, a.mtx_compat)
+    traj2dEcsv(a.traj_in, a.topology, a.excited_itp, a.csv_out, a.num_frames, a.sites, a.mtx_compat, device=a.device)
     return 0
 
 

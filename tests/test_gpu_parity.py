@@ -627,3 +627,28 @@ def test_random_shapes_against_oracle(seed, tmp_path, oracle_mod, capi_mod):
             _, c64 = O.cov_f64(dE, 0)
             cs = np.maximum(np.abs(c64), np.sqrt(np.einsum("sii,sjj->sij", c64, c64)))
             assert np.all(np.abs(cov - c64)[cs > 0] <= COV_TOL * cs[cs > 0])
+
+
+def test_python_driver_two_ranks_on_one_gpu(small_inputs, capi_mod, tmp_path):
+    """python -m cgromcorrfmo_b200.run under torchrun with two ranks (gloo, both on cuda:0): each rank streams its frame
+    range and writes its .time part with the device formatter, the Correlate sums are all-reduced once, rank 0 joins the
+    parts and writes the .mtx.  Same files as one process."""
+    import subprocess
+    import sys
+    from cgromcorrfmo_b200 import build
+    traj, top, itp, frames = small_inputs("tiny")
+    one, two = str(tmp_path / "one"), str(tmp_path / "two")
+    r = subprocess.run([build.CLI, traj, top, itp, one, str(frames)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    env = dict(os.environ, CGC_DIST_BACKEND="gloo", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", "-m", "cgromcorrfmo_b200.run", traj, top, itp, two, str(frames),
+                        "--device", "0"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    a = np.array([[float(v) for v in ln.split(",")] for ln in open(one + ".time").read().strip().split("\n")])
+    b = np.array([[float(v) for v in ln.split(",")] for ln in open(two + ".time").read().strip().split("\n")])
+    assert a.shape == b.shape and np.allclose(a, b, rtol=3e-5, atol=1e-4)
+    assert not os.path.exists(two + ".time.part0")
+    ma = np.array([[float(v) for v in ln.split(",")] for ln in open(one + ".mtx").read().strip().split("\n")])
+    mb = np.array([[float(v) for v in ln.split(",")] for ln in open(two + ".mtx").read().strip().split("\n")])
+    assert ma.shape == mb.shape and np.all(np.abs(ma - mb) <= 2e-5 * np.abs(ma).max() + 1e-12)
