@@ -21,7 +21,6 @@ for r in rows[1:]:
 ours = sum(v[1] for k, v in agg.items() if "cgc::" in k)
 print("# ncu --metrics gpu__time_duration.sum --clock-control none -c 400 %s" % cmd)
 print("# per-launch times are cold-cache and serialised: compare SHARES with bench.py's CUDA-event shares (kernel_ms), not absolutes")
-print("# the list mixes the 128-frame launches of the device leg with the smaller launches of the end-to-end legs")
 for k, (n, t) in agg.items():
     short = k.split("(")[0][:70]
     print("%-70s launches %4d  total %10.1f us  avg %9.1f us  share_of_cgc %.3f" % (short, n, t, t / n, (t / ours) if "cgc::" in k and ours else 0.0))
