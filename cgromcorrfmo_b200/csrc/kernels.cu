@@ -307,13 +307,22 @@ void launch_decode(const DeviceSystem& sys, const char* text, int64_t text_bytes
 // ---------------------------------------------------------------------------------------------------------------------
 // K2  CDC pair kernel: see cdc_kernel.cuh
 // ---------------------------------------------------------------------------------------------------------------------
-// Sites per work unit (chunk): 8 when the launch has plenty of units, fewer — down to 1 — when it is small, so that even
-// a single frame gives every resident CTA a few units.
+// Sites per work unit (chunk).  A unit of cs sites costs about cs + 0.3 site-times (ring hand-over, pipeline fill and
+// drain); a launch takes ceil(units / CTAs) of them, and a launch with fewer units than resident CTAs leaves SMs with one
+// CTA (8 warps), which runs the pair loop about 15 % slower.  Pick the cs <= 8 that minimises that estimate: 8 for any
+// launch of a few frames or more (C2: 8 frames = 1176 units over 296 CTAs, 0.7 % tail), 2 for a single frame.
 static int cdc_chunk_sites(const DeviceSystem& sys, int n_frames, int resident_ctas) {
   const long long items = (long long)(sys.n_pad / kTileAtoms) * n_frames;
-  int cs = std::min(sys.n_sites, kCdcMaxChunkSites);
-  while (cs > 1 && items * ((sys.n_sites + cs - 1) / cs) < 8LL * resident_ctas) cs--;
-  return cs;
+  const int cs_max = std::min(sys.n_sites, kCdcMaxChunkSites);
+  int best = cs_max;
+  double best_t = 1e300;
+  for (int cs = cs_max; cs >= 1; cs--) {
+    const long long units = items * ((sys.n_sites + cs - 1) / cs);
+    const double unit = cs + 0.3;
+    const double t = units >= resident_ctas ? (double)((units + resident_ctas - 1) / resident_ctas) * unit : 1.15 * unit;
+    if (t < best_t * 0.999) { best_t = t; best = cs; }
+  }
+  return best;
 }
 
 size_t cdc_smem_bytes(const DeviceSystem& sys) {
