@@ -1525,13 +1525,67 @@ int cgc_write_mtx(cgc_context* ctx, const char* path, int compat) {
     need_device(ctx);
     if (!ctx->d_cov) throw std::invalid_argument("no covariance sums on this context");
     const int S = ctx->sys.n_sites, G = ctx->sys.num_tot;
-    std::vector<float> m((size_t)S * G * G);
+    std::vector<float> m;
     if (!compat) {
-      std::vector<double> mean((size_t)S * G), cov((size_t)S * G * G);
-      int rc = cgc_cov_finalize(ctx, 0, mean.data(), cov.data());
-      if (rc != CGC_OK) return rc;
-      for (size_t i = 0; i < cov.size(); i++) m[i] = (float)cov[i];
+      // covariance -> float32 -> "%g" text, all on the device (K5); the host only writes the bytes.  A value the device
+      // formatter does not cover (|v| < 1e-16 and not 0, or non-finite) sends the whole matrix to the host formatter.
+      const int64_t n = (int64_t)S * G * G, rows = (int64_t)S * G, cap = format_time_capacity(rows, G);
+      double *d_mean = nullptr, *d_covm = nullptr;
+      float* d_m32 = nullptr;
+      char* d_txt = nullptr;
+      int64_t* d_off = nullptr;
+      std::vector<char> text;
+      int64_t total = -1;
+      int flag = 0;
+      cudaError_t err = cudaSuccess;
+      auto ok = [&](cudaError_t e) { if (err == cudaSuccess) err = e; return e == cudaSuccess; };
+      CUDA_OK(cudaDeviceSynchronize());
+      m.resize((size_t)n);
+      if (ok(cudaMalloc(&d_mean, sizeof(double) * S * G)) && ok(cudaMalloc(&d_covm, sizeof(double) * n)) &&
+          ok(cudaMalloc(&d_m32, sizeof(float) * n))) {
+        launch_cov_finalize(ctx->d_cov, S, G, 0, d_mean, d_covm, ctx->st_comp);
+        launch_narrow(d_covm, d_m32, n, ctx->st_comp);
+        ctx->launches += 2;
+        ok(cudaMemsetAsync(ctx->d_fmt_flags, 0, sizeof(int), ctx->st_comp));
+        if (ok(cudaStreamSynchronize(ctx->st_comp))) {
+          cudaFree(d_covm);
+          d_covm = nullptr;
+          if (cudaMalloc(&d_txt, (size_t)cap) == cudaSuccess && cudaMalloc(&d_off, sizeof(int64_t) * (rows + 1)) == cudaSuccess) {
+            launch_format_time(d_m32, rows, G, false, d_off, d_txt, ctx->d_fmt_flags, ctx->st_comp);
+            ctx->launches += 3;
+            ok(cudaMemcpyAsync(&total, d_off + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->st_comp));
+            ok(cudaMemcpyAsync(&flag, ctx->d_fmt_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->st_comp));
+            ok(cudaStreamSynchronize(ctx->st_comp));
+            if (err == cudaSuccess && flag == 0 && total >= 0 && total <= cap) {
+              text.resize((size_t)total);
+              ok(cudaMemcpy(text.data(), d_txt, (size_t)total, cudaMemcpyDeviceToHost));
+            } else {
+              total = -1;
+            }
+          } else {
+            cudaGetLastError();   // not enough device memory for the text: the host formatter takes over
+          }
+          if (total < 0 && err == cudaSuccess) ok(cudaMemcpy(m.data(), d_m32, sizeof(float) * n, cudaMemcpyDeviceToHost));
+          if (flag) cudaMemset(ctx->d_fmt_flags, 0, sizeof(int));
+        }
+      }
+      cudaFree(d_mean); cudaFree(d_covm); cudaFree(d_m32); cudaFree(d_txt); cudaFree(d_off);
+      CUDA_OK(err);
+      if (total >= 0) {
+        int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (fd < 0) throw ReadError(std::string("cannot write ") + path);
+        int64_t off = 0;
+        bool wrote = true;
+        while (off < total) {
+          ssize_t w = write(fd, text.data() + off, (size_t)(total - off));
+          if (w <= 0) { wrote = false; break; }
+          off += w;
+        }
+        if (close(fd) != 0 || !wrote) throw ReadError(std::string("cannot write ") + path);
+        return CGC_OK;
+      }
     } else {
+      m.resize((size_t)S * G * G);
       // the reference's literal arithmetic (src/FMOparse.cpp:189-206 with dEsize == 0), float32 throughout
       CUDA_OK(cudaDeviceSynchronize());
       double n = 0;

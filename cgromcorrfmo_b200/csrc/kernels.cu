@@ -646,6 +646,17 @@ __global__ void cov_finalize_kernel(const double* __restrict__ buf, int S, int G
   if (i == 0) mean[(size_t)s * G + j] = buf[1 + (size_t)s * G + j] + sum[j] / n;
 }
 
+__global__ void narrow_kernel(const double* __restrict__ in, float* __restrict__ out, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = (float)in[i];
+}
+
+void launch_narrow(const double* in, float* out, int64_t n, cudaStream_t st) {
+  if (n <= 0) return;
+  narrow_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(in, out, n);
+}
+
 void launch_cov_finalize(const double* buf, int S, int G, int ddof, double* mean, double* cov, cudaStream_t st) {
   dim3 block(32, 8);
   dim3 grid((G + 31) / 32, (G + 7) / 8, S);

@@ -67,6 +67,7 @@ void launch_project(const float* x, int n_frames, const double* mean, const doub
 int64_t format_time_capacity(int64_t rows, int ncol);
 void launch_format_time(const float* d_x, int64_t rows, int ncol, bool to_cm, int64_t* d_row_off, char* d_out, int* d_flags,
                         cudaStream_t st);
+void launch_narrow(const double* in, float* out, int64_t n, cudaStream_t st);   // out[i] = (float)in[i]
 void launch_cov_finalize(const double* buf, int S, int G, int ddof, double* mean, double* cov, cudaStream_t st);
 
 }  // namespace cgc
