@@ -306,7 +306,7 @@ void build_static(cgc_context* c) {
   P = cdc_pad_site_cap(P);
   sys.site_cap = P;
   if (cdc_smem_bytes(sys) > 200 * 1024) {
-    throw Unsupported("site block (sites x dQ atoms x 16 B, double buffered) exceeds shared memory; lower the \"sites\" option");
+    throw Unsupported("site block (8 sites x dQ atoms x 16 B, a ring of 4) exceeds shared memory: too many dQ != 0 atoms per chromophore");
   }
   std::vector<float> slot_dq((size_t)sys.n_sites * P, 0.f);
   std::fill(count.begin(), count.end(), 0);
