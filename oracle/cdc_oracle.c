@@ -170,3 +170,17 @@ long cgo_div1000_vs_atof_mismatches(unsigned n_lo, unsigned n_hi, unsigned step)
   }
   return bad;
 }
+
+/* Checker for K5 (the `.time` text formatted on the device): rows x ncol float32 printed the way the reference prints them,
+ * `stream << float` == printf("%g") (src/FMOparse.cpp:158-165), ',' between values and '\n' after each row.
+ * Returns the number of bytes written to out (the caller provides rows * ncol * 16 bytes). */
+long cgo_format_g_rows(const float *v, long rows, int ncol, char *out) {
+  char *p = out;
+  for (long r = 0; r < rows; r++) {
+    for (int j = 0; j < ncol; j++) {
+      p += sprintf(p, "%g", (double)v[r * ncol + j]);
+      *p++ = (j == ncol - 1) ? '\n' : ',';
+    }
+  }
+  return (long)(p - out);
+}

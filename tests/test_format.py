@@ -107,3 +107,19 @@ def test_cli_device_and_host_format_agree(small_inputs, tmp_path):
     ta = np.array([[float(v) for v in ln.split(",")] for ln in open(a + ".time").read().strip().split("\n")])
     tb = np.array([[float(v) for v in ln.split(",")] for ln in open(b + ".time").read().strip().split("\n")])
     assert ta.shape == tb.shape and np.allclose(ta, tb, rtol=3e-5, atol=1e-4)     # two runs: last-bit differences in the rows
+
+
+@pytest.mark.parametrize("exponent", [0, 19, -10])
+def test_device_g_exhaustive_binade(exponent, ctx, oracle_mod):
+    """EVERY float32 of a binade (2^23 values, both signs alternating) against glibc's printf("%g"): [1, 2);
+    [2^19, 2^20), which holds the switch to exponent notation at 1e6 and 2^19 exact rounding ties (x.5 with seven digits);
+    [2^-10, 2^-9), negative-exponent scaling."""
+    bits = (np.uint32((127 + exponent) << 23) + np.arange(1 << 23, dtype=np.uint32))
+    v = bits.view(np.float32).copy()
+    v[1::2] *= -1
+    v = v.reshape(-1, 1024)
+    want = oracle_mod.format_g_rows(v)
+    got, flag = ctx.format_text_device(v)
+    assert flag == 0
+    assert len(got) == len(want)
+    assert got == want
