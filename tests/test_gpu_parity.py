@@ -652,3 +652,46 @@ def test_python_driver_two_ranks_on_one_gpu(small_inputs, capi_mod, tmp_path):
     ma = np.array([[float(v) for v in ln.split(",")] for ln in open(one + ".mtx").read().strip().split("\n")])
     mb = np.array([[float(v) for v in ln.split(",")] for ln in open(two + ".mtx").read().strip().split("\n")])
     assert ma.shape == mb.shape and np.all(np.abs(ma - mb) <= 2e-5 * np.abs(ma).max() + 1e-12)
+
+
+def test_decode_every_8_3_value(small_inputs, capi_mod, torch_cuda):
+    """K1 on EVERY value a "%8.3f" field can hold — 0.000 .. 9999.999 and -0.001 .. -999.999, eleven million fields —
+    against (float)atof of the same text (reference src/grom2atomFMO.cpp:448-450): the correctly rounded double N/1000
+    rounded to float32."""
+    capi, torch = capi_mod, torch_cuda
+    from cgromcorrfmo_b200 import synth
+    from conftest import SMALL_SYSTEMS
+    traj, top, itp, _ = small_inputs("tiny")
+    cfg = SMALL_SYSTEMS["tiny"]
+    s = synth.make_system(cfg["n_atoms"], cfg["n_bcl"], cfg["seed"], cfg["solvent"])
+    n = s.n_atoms
+    milli = np.concatenate([np.arange(0, 10_000_000, dtype=np.int64), -np.arange(1, 1_000_000, dtype=np.int64)])
+    per_frame = 3 * n
+    frames = (milli.size + per_frame - 1) // per_frame
+    milli = np.concatenate([milli, np.zeros(frames * per_frame - milli.size, np.int64)]).reshape(frames, n, 3)
+    prefix = synth._static_prefix(s)
+    head = ("all values t= 0.0\n%5d\n" % n).encode()
+    tail = b"   1.0   1.0   1.0\n"
+    lines = np.empty((frames, n, 45), dtype=np.uint8)
+    lines[:, :, :20] = prefix
+    lines[:, :, 20:44] = synth._fmt_fixed(milli, 8, 3).reshape(frames, n, 24)
+    lines[:, :, 44] = ord("\n")
+    blob = b"".join(head + lines[f].tobytes() + tail for f in range(frames))
+    expect = (milli.astype(np.float64) / 1000.0).astype(np.float32)
+    text = np.frombuffer(blob, dtype=np.uint8)
+    d_text = torch.from_numpy(np.concatenate([text, np.zeros(64, np.uint8)])).cuda()
+    with capi.Context(top, itp, 0) as c:
+        c.open_memory(blob)
+        assert c.frame_count() == frames
+        got = np.empty((frames, n, 3), np.float32)
+        step = 256
+        c.set_option("batch_frames", step)
+        xyz = torch.empty((step, n, 3), dtype=torch.float32, device="cuda")
+        for f0 in range(0, frames, step):
+            k = min(step, frames - f0)
+            offs = [c.frame_atoms_offset(f) for f in range(f0, f0 + k)]
+            c.decode_device(d_text.data_ptr(), text.size, offs, k, xyz.data_ptr())
+            torch.cuda.synchronize()
+            got[f0:f0 + k] = xyz[:k].cpu().numpy()
+        assert c.decode_errors() == 0
+    assert np.array_equal(got.view(np.uint32), expect.view(np.uint32))
