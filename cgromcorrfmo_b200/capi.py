@@ -62,6 +62,7 @@ SIGNATURES = {
     "cgc_cov_partials": (c_int, [c_void_p, c_void_p]),
     "cgc_cov_set_shift_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "cgc_cov_accumulate_device": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "cgc_eigh": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, POINTER(c_int)]),
     "cgc_project": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "cgc_cov_finalize": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "cgc_write_time": (c_int, [c_char_p, c_int, c_void_p, c_int64, c_int]),
@@ -371,6 +372,18 @@ class Context:
         cov = np.empty((S, G, G), np.float64)
         self._check(self._lib.cgc_cov_finalize(self._h, int(ddof), _ptr(mean), _ptr(cov)))
         return mean, cov
+
+    def eigh(self, matrices):
+        """Batched symmetric eigen-decomposition on the device.  matrices (M, n, n) float64 -> (evals (M, n) ascending,
+        evecs (M, n, n) with eigenvectors as ROWS, sweeps)."""
+        a = np.ascontiguousarray(matrices, dtype=np.float64)
+        if a.ndim != 3 or a.shape[1] != a.shape[2]:
+            raise ValueError("eigh wants (M, n, n)")
+        ev = np.empty(a.shape[:2], dtype=np.float64)
+        vt = np.empty(a.shape, dtype=np.float64)
+        sw = c_int(0)
+        self._check(self._lib.cgc_eigh(self._h, _ptr(a), a.shape[0], a.shape[1], _ptr(ev), _ptr(vt), ctypes.byref(sw)))
+        return ev, vt, sw.value
 
     def project(self, dE_rows, mean, modes):
         """out[t, s, m] = sum_g (dE_rows[t, s, g] - mean[s, g]) * modes[s, m, g] on the device (FP64 tensor cores).

@@ -1429,6 +1429,51 @@ int cgc_cov_finalize(cgc_context* ctx, int ddof, double* mean, double* cov) {
   });
 }
 
+int cgc_eigh(cgc_context* ctx, const double* matrices, int n_mat, int n, double* evals, double* evecs, int* sweeps) {
+  if (sweeps) *sweeps = 0;
+  if (!ctx || !matrices || !evals || !evecs) return fail(ctx, CGC_ERR_ARG, "null argument");
+  if (n_mat < 1 || n < 1) return fail(ctx, CGC_ERR_ARG, "bad matrix count or size");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    if (!ctx->st_comp) CUDA_OK(cudaStreamCreateWithFlags(&ctx->st_comp, cudaStreamNonBlocking));
+    const size_t nn = (size_t)n_mat * n * n;
+    double *d_a = nullptr, *d_w = nullptr, *d_v = nullptr, *d_e = nullptr;
+    unsigned int* d_rot = nullptr;
+    cudaError_t err = cudaSuccess;
+    auto ok = [&](cudaError_t e) { if (err == cudaSuccess) err = e; return e == cudaSuccess; };
+    int sw = -2;
+    std::vector<double> ev((size_t)n_mat * n), vt;
+    if (ok(cudaMalloc(&d_a, sizeof(double) * nn)) && ok(cudaMalloc(&d_w, sizeof(double) * nn)) &&
+        ok(cudaMalloc(&d_v, sizeof(double) * nn)) && ok(cudaMalloc(&d_e, sizeof(double) * n_mat * n)) &&
+        ok(cudaMalloc(&d_rot, sizeof(unsigned int))) &&
+        ok(cudaMemcpyAsync(d_a, matrices, sizeof(double) * nn, cudaMemcpyHostToDevice, ctx->st_comp))) {
+      sw = eigh_jacobi(d_a, n_mat, n, d_w, d_v, d_e, d_rot, 40, ctx->st_comp, &ctx->launches);
+      ok(cudaGetLastError());
+      vt.resize(nn);
+      ok(cudaMemcpyAsync(ev.data(), d_e, sizeof(double) * n_mat * n, cudaMemcpyDeviceToHost, ctx->st_comp));
+      ok(cudaMemcpyAsync(vt.data(), d_v, sizeof(double) * nn, cudaMemcpyDeviceToHost, ctx->st_comp));
+      ok(cudaStreamSynchronize(ctx->st_comp));
+    }
+    cudaFree(d_a); cudaFree(d_w); cudaFree(d_v); cudaFree(d_e); cudaFree(d_rot);
+    CUDA_OK(err);
+    if (sw == -2) throw CudaError("eigh: the device reported an error during the Jacobi sweeps");
+    if (sw < 0) throw std::runtime_error("eigh: Jacobi did not converge in 40 sweeps");
+    if (sweeps) *sweeps = sw;
+    // ascending eigenvalues, eigenvectors as rows in the same order (numpy.linalg.eigh's order; its columns are our rows)
+    std::vector<int> order((size_t)n);
+    for (int k = 0; k < n_mat; k++) {
+      const double* e = ev.data() + (size_t)k * n;
+      for (int i = 0; i < n; i++) order[(size_t)i] = i;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return e[a] < e[b]; });
+      for (int i = 0; i < n; i++) {
+        evals[(size_t)k * n + i] = e[order[(size_t)i]];
+        memcpy(evecs + ((size_t)k * n + i) * n, vt.data() + ((size_t)k * n + order[(size_t)i]) * n, sizeof(double) * n);
+      }
+    }
+    return CGC_OK;
+  });
+}
+
 int cgc_project(cgc_context* ctx, const float* dE_rows, int64_t n_frames, const double* mean, const double* modes,
                 int n_modes, double* out) {
   if (!ctx || !dE_rows || !mean || !modes || !out) return fail(ctx, CGC_ERR_ARG, "null argument");

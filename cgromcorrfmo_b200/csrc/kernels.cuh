@@ -67,6 +67,9 @@ void launch_project(const float* x, int n_frames, const double* mean, const doub
 int64_t format_time_capacity(int64_t rows, int ncol);
 void launch_format_time(const float* d_x, int64_t rows, int ncol, bool to_cm, int64_t* d_row_off, char* d_out, int* d_flags,
                         cudaStream_t st);
+// K6 (eigh_kernel.cu): batched one-sided Jacobi.  Eigenvectors end up as the rows of d_Vt; d_evals is unsorted.
+int eigh_jacobi(const double* d_A, int n_mat, int n, double* d_Wt, double* d_Vt, double* d_evals, unsigned int* d_rot,
+                int max_sweeps, cudaStream_t st, int64_t* launches);
 void launch_narrow(const double* in, float* out, int64_t n, cudaStream_t st);   // out[i] = (float)in[i]
 void launch_cov_finalize(const double* buf, int S, int G, int ddof, double* mean, double* cov, cudaStream_t st);
 

@@ -9,7 +9,7 @@ what follows it (eigen-decomposition, projection) is plain numpy, as in depca.
 
     E_t_ia               = load_E_t_ia(traj, top, itp, num_frames)            # float32 (T, Nsites, Ncoarse), cm^-1
     Corr_i_ab, AvgEia    = AvgAndCorrelateSidechains_gpu(traj, top, itp, T)   # depca's return order
-    vi, wi, impact_i     = ComputeModes(Corr_i_ab)
+    vi, wi, impact_i     = ComputeModes(Corr_i_ab)                            # or ComputeModes_gpu(ctx, Corr_i_ab)
     proj_t_im            = ApplyPCA_gpu(ctx, E_t_ia, AvgEia, wi)              # (E - mean) . modes on FP64 tensor cores
 """
 from __future__ import annotations
@@ -81,6 +81,24 @@ def ComputeModes(corr, sort=True):
     for c in corr:
         v, w = np.linalg.eigh(c)
         w = w.T.copy()
+        n = w.sum(axis=1)
+        flip = ((v < 0) & (n > 0)) | ((v > 0) & (n < 0))
+        w[flip] *= -1
+        n[flip] *= -1
+        if sort:
+            order = np.argsort(v * n * n, kind="stable")
+            v, w, n = v[order], w[order], n[order]
+        vi.append(v); wi.append(w); imp.append(n)
+    return np.array(vi), np.array(wi), np.array(imp)
+
+
+def ComputeModes_gpu(ctx, corr, sort=True):
+    """ComputeModes with the eigen-decomposition on the device (K6, batched Jacobi; C-ABI cgc_eigh) instead of
+    numpy.linalg.eigh; the sign convention and the sort are depca's, as above."""
+    v_all, w_all, _ = ctx.eigh(np.asarray(corr, dtype=np.float64))
+    vi, wi, imp = [], [], []
+    for v, w in zip(v_all, w_all):
+        w = w.copy()
         n = w.sum(axis=1)
         flip = ((v < 0) & (n > 0)) | ((v > 0) & (n < 0))
         w[flip] *= -1

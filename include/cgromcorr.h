@@ -168,6 +168,12 @@ int cgc_cov_finalize(cgc_context *ctx, int ddof, double *mean, double *cov);
  * cgc_run returned, any unit), mean float64 [sites][numTot], modes float64 [sites][n_modes][numTot] (eigenvectors as
  * rows, as depca's ComputeModes returns them), out float64 [n_frames][sites][n_modes].  The eigen-decomposition itself
  * stays on the host (numpy.linalg.eigh in depca): it runs once per trajectory on 7..24 matrices. */
+/* Eigen-decomposition of symmetric matrices on the device (K6: batched one-sided Jacobi) — numpy.linalg.eigh in depca's
+ * ComputeModes (scripts/depca/depca/sidechain_corr.py:91-96).  HOST in, HOST out: matrices float64 [n_mat][n][n];
+ * evals [n_mat][n] ascending; evecs [n_mat][n][n] with ROW k the eigenvector of evals[k] (numpy returns them as columns:
+ * depca transposes, sidechain_corr.py:97).  *sweeps (nullable) = Jacobi sweeps used.  Signs of eigenvectors are arbitrary,
+ * as with LAPACK. */
+int cgc_eigh(cgc_context *ctx, const double *matrices, int n_mat, int n, double *evals, double *evecs, int *sweeps);
 int cgc_project(cgc_context *ctx, const float *dE_rows, int64_t n_frames, const double *mean, const double *modes,
                 int n_modes, double *out);
 

@@ -80,3 +80,51 @@ def test_gpu_projection_matches_numpy(n_modes, small_inputs):
         assert np.all(np.abs(got - ref) <= 1e-13 * scale + 1e-300)
         with pytest.raises(ValueError):
             c.project(X[:, :1], avg, W)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 2, 7, 64, 257])
+def test_gpu_eigh_matches_lapack(n, small_inputs):
+    """K6 (cgc_eigh, batched one-sided Jacobi) against numpy.linalg.eigh: eigenvalues, orthonormal eigenvectors, and
+    A = V^T diag(lambda) V — on covariance-like matrices (positive semi-definite, one exactly zero row/column like the
+    own-site column of a dE covariance), an indefinite one and a rank-deficient one (fewer frames than columns)."""
+    from cgromcorrfmo_b200 import capi
+    traj, top, itp, frames = small_inputs("tiny")
+    rng = np.random.default_rng(n)
+    mats = []
+    X = rng.normal(size=(4 * n + 3, n)) * (1.0 + 10.0 * rng.random(n))
+    c = np.cov(X, rowvar=False).reshape(n, n)
+    if n > 2:
+        c[0, :] = 0.0
+        c[:, 0] = 0.0
+    mats.append(c)
+    b = rng.normal(size=(n, n))
+    mats.append((b + b.T) / 2)                                         # indefinite
+    Y = rng.normal(size=(max(1, n // 3), n))
+    mats.append(Y.T @ Y)                                               # rank-deficient: a large null space
+    A = np.stack(mats)
+    with capi.Context(top, itp, 0) as ctx:
+        ctx.open(traj)
+        ev, vt, sweeps = ctx.eigh(A)
+    assert 1 <= sweeps <= 40
+    for k in range(len(mats)):
+        ref = np.linalg.eigvalsh(A[k])
+        scale = max(np.abs(ref).max(), 1e-300)
+        assert np.all(np.diff(ev[k]) >= 0)
+        assert np.all(np.abs(ev[k] - ref) <= 1e-12 * scale)
+        assert np.allclose(vt[k] @ vt[k].T, np.eye(n), atol=1e-12)
+        assert np.allclose(vt[k].T @ np.diag(ev[k]) @ vt[k], A[k], atol=1e-11 * scale)
+
+
+@pytest.mark.gpu
+def test_compute_modes_gpu_matches_numpy(small_inputs):
+    from cgromcorrfmo_b200 import capi
+    traj, top, itp, frames = small_inputs("tiny")
+    rng = np.random.default_rng(4)
+    E = (rng.normal(size=(400, 3, 12)) @ np.diag(np.linspace(3, 0.2, 12)) + 5.0).astype(np.float32)
+    corr, avg = pypca.AvgAndCorrelateSidechains(E)
+    vi, wi, imp = pypca.ComputeModes(corr)
+    with capi.Context(top, itp, 0) as ctx:
+        ctx.open(traj)
+        gv, gw, gi = pypca.ComputeModes_gpu(ctx, corr)
+    assert np.allclose(gv, vi, rtol=1e-10) and np.allclose(gi, imp, atol=1e-8) and np.allclose(gw, wi, atol=1e-8)
