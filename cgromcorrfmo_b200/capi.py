@@ -60,6 +60,9 @@ SIGNATURES = {
     "cgc_cov_bind": (c_int, [c_void_p, c_void_p]),
     "cgc_cov_reset": (c_int, [c_void_p]),
     "cgc_cov_partials": (c_int, [c_void_p, c_void_p]),
+    "cgc_cov_state_bytes": (c_int64, [c_void_p]),
+    "cgc_cov_save_state": (c_int, [c_void_p, c_void_p, c_int64]),
+    "cgc_cov_load_state": (c_int, [c_void_p, c_void_p, c_int64]),
     "cgc_cov_set_shift_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "cgc_cov_accumulate_device": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "cgc_eigh": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, POINTER(c_int)]),
@@ -359,6 +362,17 @@ class Context:
         out = np.empty(self.cov_size(), np.float64)
         self._check(self._lib.cgc_cov_partials(self._h, _ptr(out)))
         return out
+
+    def cov_save_state(self) -> bytes:
+        """Checkpoint of the Correlate sums (cgc_cov_save_state)."""
+        n = int(self._lib.cgc_cov_state_bytes(self._h))
+        buf = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.cgc_cov_save_state(self._h, _ptr(buf), n))
+        return buf.tobytes()
+
+    def cov_load_state(self, blob: bytes):
+        buf = np.frombuffer(blob, dtype=np.uint8)
+        self._check(self._lib.cgc_cov_load_state(self._h, _ptr(buf), buf.size))
 
     def cov_set_shift_device(self, d_row, stream=0):
         self._check(self._lib.cgc_cov_set_shift_device(self._h, _ptr(d_row), c_void_p(int(stream))))

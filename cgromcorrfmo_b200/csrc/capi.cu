@@ -1405,6 +1405,72 @@ int cgc_cov_partials(cgc_context* ctx, double* host_out) {
   });
 }
 
+// Checkpoint of the Correlate state: header, the flat partial-sum buffer, the two float32 compat sums.
+namespace {
+struct CovStateHeader {
+  char magic[8];        // "CGCCOV1"
+  int32_t sites, num_tot;
+  int64_t doubles;      // length of the flat buffer
+  int32_t shift_set, reserved;
+};
+}  // namespace
+
+int64_t cgc_cov_state_bytes(const cgc_context* ctx) {
+  if (!ctx || !ctx->opened || ctx->device < 0 || !cov_enabled(ctx)) return 0;
+  const int64_t SG = (int64_t)ctx->sys.n_sites * ctx->sys.num_tot;
+  return (int64_t)sizeof(CovStateHeader) + (int64_t)sizeof(double) * cov_doubles(ctx) + (int64_t)sizeof(float) * 2 * SG;
+}
+
+int cgc_cov_save_state(cgc_context* ctx, void* host_out, int64_t cap) {
+  if (!ctx || !host_out) return fail(ctx, CGC_ERR_ARG, "null argument");
+  if (!ctx->opened) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    ensure_cov(ctx);
+    if (!ctx->d_cov) throw std::invalid_argument("covariance is switched off for this trajectory");
+    if (cap < cgc_cov_state_bytes(ctx)) throw std::invalid_argument("buffer smaller than cgc_cov_state_bytes()");
+    const int64_t SG = (int64_t)ctx->sys.n_sites * ctx->sys.num_tot, nd = cov_doubles(ctx);
+    CovStateHeader h{};
+    memcpy(h.magic, "CGCCOV1", 8);
+    h.sites = ctx->sys.n_sites;
+    h.num_tot = ctx->sys.num_tot;
+    h.doubles = nd;
+    h.shift_set = ctx->shift_set ? 1 : 0;
+    char* p = (char*)host_out;
+    memcpy(p, &h, sizeof h);
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(p + sizeof h, ctx->d_cov, sizeof(double) * nd, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(p + sizeof h + sizeof(double) * nd, ctx->d_compat, sizeof(float) * 2 * SG, cudaMemcpyDeviceToHost));
+    return CGC_OK;
+  });
+}
+
+int cgc_cov_load_state(cgc_context* ctx, const void* host_in, int64_t nbytes) {
+  if (!ctx || !host_in) return fail(ctx, CGC_ERR_ARG, "null argument");
+  if (!ctx->opened) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    ensure_cov(ctx);
+    if (!ctx->d_cov) throw std::invalid_argument("covariance is switched off for this trajectory");
+    const int64_t SG = (int64_t)ctx->sys.n_sites * ctx->sys.num_tot, nd = cov_doubles(ctx);
+    CovStateHeader h;
+    if (nbytes < (int64_t)sizeof h) throw InputFileMalformed("Correlate checkpoint is truncated");
+    memcpy(&h, host_in, sizeof h);
+    if (memcmp(h.magic, "CGCCOV1", 8) != 0) throw InputFileMalformed("not a Correlate checkpoint");
+    if (h.sites != ctx->sys.n_sites || h.num_tot != ctx->sys.num_tot || h.doubles != nd) {
+      throw InputFileMalformed("Correlate checkpoint belongs to a different system (sites / columns differ)");
+    }
+    if (nbytes < cgc_cov_state_bytes(ctx)) throw InputFileMalformed("Correlate checkpoint is truncated");
+    const char* p = (const char*)host_in + sizeof h;
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(ctx->d_cov, p, sizeof(double) * nd, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(ctx->d_compat, p + sizeof(double) * nd, sizeof(float) * 2 * SG, cudaMemcpyHostToDevice));
+    ctx->shift_set = h.shift_set != 0;
+    ctx->cov_rows_pending = 0;
+    return CGC_OK;
+  });
+}
+
 int cgc_cov_finalize(cgc_context* ctx, int ddof, double* mean, double* cov) {
   if (!ctx || !mean || !cov) return fail(ctx, CGC_ERR_ARG, "null argument");
   return guarded(ctx, [&]() {

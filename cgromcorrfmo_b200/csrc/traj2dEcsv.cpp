@@ -12,6 +12,9 @@
 //     trjconv step (reference scripts/2014-09-trr2dEcsv.sh:22) and its 45-69 bytes of text per atom are skipped.
 //   * csv_out.time is formatted on the device (cgc_run_write_time); --host-format uses the host formatter instead
 //     (cgc_run + cgc_write_time, what the first version did; the bytes are the same);
+//   * --checkpoint FILE saves, after every chunk of frames, how far the run got together with the Correlate sums;
+//     --resume FILE continues such a run: csv_out.time is cut back to the checkpointed length and appended to, the sums
+//     carry on (the reference loses its accumulators when it is killed);
 //   * --npy additionally writes csv_out.time.npy: the same rows as raw float32 (frames, sites, numTot) in kcal/mol, the
 //     array the pyPCA scripts rebuild from the text (reference scripts/2014-06-csv2hdf5.py:56-74) without the text.
 // Extra flags come AFTER the five positionals.
@@ -53,6 +56,41 @@ static bool write_npy_header(FILE* f, long long frames, int sites, int num_tot) 
   return fseek(f, 0, SEEK_SET) == 0 && fwrite(head, 1, sizeof head, f) == sizeof head;
 }
 
+// Checkpoint file: header + the blob of cgc_cov_save_state.  Written to FILE.tmp and renamed, so a kill leaves either the
+// previous checkpoint or the new one.
+struct CkptHeader {
+  char magic[8];          // "CGCCKPT1"
+  int64_t frames_done;    // frames processed since frame `first`
+  int64_t first_frame;
+  int64_t time_bytes;     // length of csv_out.time at that point
+  int32_t sites, num_tot;
+  int64_t state_bytes;    // 0: covariance off
+};
+
+static bool save_checkpoint(cgc_context* ctx, const std::string& path, long long frames_done, long long first,
+                            const std::string& time_path, int sites, int num_tot) {
+  CkptHeader h{};
+  memcpy(h.magic, "CGCCKPT1", 8);
+  h.frames_done = frames_done;
+  h.first_frame = first;
+  FILE* t = fopen(time_path.c_str(), "rb");
+  if (!t) return false;
+  fseek(t, 0, SEEK_END);
+  h.time_bytes = ftell(t);
+  fclose(t);
+  h.sites = sites;
+  h.num_tot = num_tot;
+  h.state_bytes = cgc_cov_state_bytes(ctx);
+  std::vector<char> blob((size_t)h.state_bytes);
+  if (h.state_bytes > 0 && cgc_cov_save_state(ctx, blob.data(), h.state_bytes) != CGC_OK) return false;
+  const std::string tmp = path + ".tmp";
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return false;
+  bool ok = fwrite(&h, sizeof h, 1, f) == 1 && (blob.empty() || fwrite(blob.data(), 1, blob.size(), f) == blob.size());
+  ok = fclose(f) == 0 && ok;
+  return ok && rename(tmp.c_str(), path.c_str()) == 0;
+}
+
 static double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -74,14 +112,14 @@ int main(int argc, char** argv) {
     printf("Five inputs required for this program.\n");
     printf("Order of args: fmo_traj_path, fmo_top_path, bcx_itp_path, output_path, num_frames "
            "[--sites N] [--mtx-compat] [--no-mtx] [--device D] [--first-frame F] [--batch-frames B] [--verbose] "
-           "[--structure frame0.gro (traj_in is then a .trr)] [--npy] [--host-format]\n");
+           "[--structure frame0.gro (traj_in is then a .trr)] [--npy] [--host-format] [--checkpoint FILE] [--resume FILE]\n");
     return EXIT_FAILURE;
   }
   const std::string traj = argv[1], top = argv[2], itp = argv[3], out = argv[4];
   const long long num_frames = atoll(argv[5]);
   int sites = 0, device = 0, batch = 0;
   long long first = 0;
-  std::string structure;
+  std::string structure, ckpt_path, resume_path;
   bool compat = false, no_mtx = false, verbose = false, timing = false, npy = false, host_format = false;
   for (int i = 6; i < argc; i++) {
     std::string a = argv[i];
@@ -97,6 +135,8 @@ int main(int argc, char** argv) {
     else if (a == "--first-frame") first = atoll(val("--first-frame"));
     else if (a == "--batch-frames") batch = atoi(val("--batch-frames"));
     else if (a == "--structure") structure = val("--structure");
+    else if (a == "--checkpoint") ckpt_path = val("--checkpoint");
+    else if (a == "--resume") resume_path = val("--resume");
     else if (a == "--mtx-compat") compat = true;
     else if (a == "--no-mtx") no_mtx = true;
     else if (a == "--verbose") verbose = true;
@@ -140,15 +180,42 @@ int main(int argc, char** argv) {
   if (verbose) printf("atoms %d  nChromo %d  nGroups %d  sites %d\n", n_atoms, n_chromo, n_groups, S);
 
   const std::string time_path = out + ".time";
-  if (cgc_write_time(time_path.c_str(), 1, nullptr, 0, num_tot) != CGC_OK) {  // truncate (reference src/FMOparse.cpp:48-50)
+  long long resumed_frames = 0;
+  if (!resume_path.empty()) {
+    FILE* f = fopen(resume_path.c_str(), "rb");
+    CkptHeader h{};
+    std::vector<char> blob;
+    bool ok = f && fread(&h, sizeof h, 1, f) == 1 && memcmp(h.magic, "CGCCKPT1", 8) == 0 && h.sites == S && h.num_tot == num_tot &&
+              h.first_frame == first && h.state_bytes == cgc_cov_state_bytes(ctx);
+    if (ok && h.state_bytes > 0) {
+      blob.resize((size_t)h.state_bytes);
+      ok = fread(blob.data(), 1, blob.size(), f) == blob.size() && cgc_cov_load_state(ctx, blob.data(), h.state_bytes) == CGC_OK;
+    }
+    if (f) fclose(f);
+    if (!ok || truncate(time_path.c_str(), (off_t)h.time_bytes) != 0) {
+      fprintf(stderr, "traj2dEcsv: cannot resume from %s (missing, damaged, or written for other sites / columns / first frame)\n",
+              resume_path.c_str());
+      cgc_destroy(ctx);
+      return EXIT_FAILURE;
+    }
+    resumed_frames = h.frames_done;
+    if (verbose) printf("resuming after %lld frames\n", resumed_frames);
+  } else if (cgc_write_time(time_path.c_str(), 1, nullptr, 0, num_tot) != CGC_OK) {  // truncate (reference src/FMOparse.cpp:48-50)
     fprintf(stderr, "traj2dEcsv: cannot write %s\n", time_path.c_str());
     cgc_destroy(ctx);
     return EXIT_FAILURE;
   }
   FILE* npy_file = nullptr;
   if (npy) {
-    npy_file = fopen((time_path + ".npy").c_str(), "wb");
-    if (!npy_file || !write_npy_header(npy_file, 0, S, num_tot)) {
+    npy_file = fopen((time_path + ".npy").c_str(), resumed_frames > 0 ? "r+b" : "wb");
+    if (npy_file && resumed_frames > 0) {
+      // keep the rows of the frames already done; anything after them is rewritten
+      if (fseek(npy_file, 128L + (long)(resumed_frames * (long long)S * num_tot * 4), SEEK_SET) != 0) { fclose(npy_file); npy_file = nullptr; }
+    } else if (npy_file && !write_npy_header(npy_file, 0, S, num_tot)) {
+      fclose(npy_file);
+      npy_file = nullptr;
+    }
+    if (!npy_file) {
       fprintf(stderr, "traj2dEcsv: cannot write %s.npy\n", time_path.c_str());
       cgc_destroy(ctx);
       return EXIT_FAILURE;
@@ -166,7 +233,7 @@ int main(int argc, char** argv) {
   std::vector<float> buf[2];
   std::thread writer;
   int wrc = CGC_OK;
-  long long done_total = 0;
+  long long done_total = resumed_frames;
   int which = 0;
   bool eof = false;
   while (done_total < num_frames && g_keep_running && !eof) {
@@ -211,6 +278,13 @@ int main(int argc, char** argv) {
     });
     done_total += done;
     which ^= 1;
+    if (!ckpt_path.empty()) {
+      if (writer.joinable()) writer.join();   // the .time / .npy bytes of this chunk are in their files
+      if (npy_file) fflush(npy_file);
+      if (!save_checkpoint(ctx, ckpt_path, done_total, first, time_path, S, num_tot)) {
+        fprintf(stderr, "traj2dEcsv: cannot write the checkpoint %s\n", ckpt_path.c_str());
+      }
+    }
   }
   const double t_loop_end = now_s();
   if (writer.joinable()) writer.join();

@@ -153,6 +153,13 @@ int64_t cgc_cov_size(const cgc_context *ctx);                       /* number of
 int cgc_cov_bind(cgc_context *ctx, double *d_buffer);               /* DEVICE pointer, cgc_cov_size doubles, zeroed here */
 int cgc_cov_reset(cgc_context *ctx);
 int cgc_cov_partials(cgc_context *ctx, double *host_out);           /* copy the flat buffer to HOST */
+/* Checkpoint / resume of the Correlate state (the reference loses its accumulators when a run is killed; its `.time`
+ * prefix survives because the file only grows, src/FMOparse.cpp:48-50,158-165 — SURVEY.md section 5).  The blob holds
+ * the flat partial sums and the two float32 sums of the literal `.mtx`; loading it into a context opened on the same
+ * system continues the accumulation exactly where cgc_cov_save_state left off.  HOST buffers. */
+int64_t cgc_cov_state_bytes(const cgc_context *ctx);
+int cgc_cov_save_state(cgc_context *ctx, void *host_out, int64_t cap);
+int cgc_cov_load_state(cgc_context *ctx, const void *host_in, int64_t nbytes);
 /* Set the shift c from a DEVICE row float32 [sites][numTot] (the dE row of the trajectory's frame 0).  cgc_run does this
  * itself; cgc_cov_accumulate_device falls back to the first row it is given when no shift was set. */
 int cgc_cov_set_shift_device(cgc_context *ctx, const float *d_row, void *stream);

@@ -695,3 +695,33 @@ def test_decode_every_8_3_value(small_inputs, capi_mod, torch_cuda):
             got[f0:f0 + k] = xyz[:k].cpu().numpy()
         assert c.decode_errors() == 0
     assert np.array_equal(got.view(np.uint32), expect.view(np.uint32))
+
+
+def test_cli_checkpoint_and_resume(small_inputs, tmp_path):
+    """--checkpoint / --resume: a run stopped after some frames and continued gives the files of an uninterrupted run (the
+    reference loses its Correlate sums when it is killed; only the .time prefix survives)."""
+    import subprocess
+    from cgromcorrfmo_b200 import build
+    traj, top, itp, frames = small_inputs("tiny")
+    full, part, ck = str(tmp_path / "full"), str(tmp_path / "part"), str(tmp_path / "ck.bin")
+    r = subprocess.run([build.CLI, traj, top, itp, full, str(frames), "--npy"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([build.CLI, traj, top, itp, part, "1", "--npy", "--checkpoint", ck], capture_output=True, text=True)
+    assert r.returncode == 0 and os.path.exists(ck), r.stderr
+    # garbage appended after the checkpoint (a run killed in the middle of a chunk) is cut off again on resume
+    with open(part + ".time", "ab") as f:
+        f.write(b"1,2,3\n")
+    r = subprocess.run([build.CLI, traj, top, itp, part, str(frames), "--npy", "--resume", ck, "--checkpoint", ck],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    load = lambda p: np.array([[float(v) for v in ln.split(",")] for ln in open(p).read().strip().split("\n")])
+    a, b = load(full + ".time"), load(part + ".time")
+    assert a.shape == b.shape and np.allclose(a, b, rtol=3e-5, atol=1e-4)
+    ma, mb = load(full + ".mtx"), load(part + ".mtx")
+    assert ma.shape == mb.shape and np.all(np.abs(ma - mb) <= 2e-5 * np.abs(ma).max() + 1e-12)
+    ea, eb = np.load(full + ".time.npy"), np.load(part + ".time.npy")
+    assert ea.shape == eb.shape == (frames, ea.shape[1], ea.shape[2])
+    assert np.allclose(ea, eb, rtol=1e-5, atol=1e-6)
+    # a checkpoint of another run is refused
+    r = subprocess.run([build.CLI, traj, top, itp, part, str(frames), "--resume", ck, "--sites", "3"], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot resume" in r.stderr
