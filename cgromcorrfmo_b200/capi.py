@@ -67,6 +67,8 @@ SIGNATURES = {
     "cgc_cov_accumulate_device": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "cgc_eigh": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, POINTER(c_int)]),
     "cgc_project": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
+    "cgc_time_corr": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p,
+                      POINTER(c_double)]),
     "cgc_cov_finalize": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "cgc_write_time": (c_int, [c_char_p, c_int, c_void_p, c_int64, c_int]),
     "cgc_write_mtx": (c_int, [c_void_p, c_char_p, c_int]),
@@ -411,6 +413,23 @@ class Context:
         out = np.empty((x.shape[0], S, w.shape[1]), dtype=np.float64)
         self._check(self._lib.cgc_project(self._h, _ptr(x), x.shape[0], _ptr(mu), _ptr(w), w.shape[1], _ptr(out)))
         return out
+
+    def time_corr(self, series, pair_first, pair_second, corr_len: int, circular: bool = False, want_ms: bool = False):
+        """out[p, tau] = sum_t series[first[p], t] * series[second[p], t + tau] / (n - tau) for tau < corr_len, on the device
+        in FP64 (K7).  series float64 (n_series, n), mean-free; circular=True takes t + tau modulo n.  Returns float64
+        (n_pairs, corr_len) (and the device time of the kernels in ms when want_ms)."""
+        s = np.ascontiguousarray(series, dtype=np.float64)
+        if s.ndim != 2:
+            raise ValueError("time_corr wants series (n_series, n)")
+        a = np.ascontiguousarray(pair_first, dtype=np.int32).ravel()
+        b = np.ascontiguousarray(pair_second, dtype=np.int32).ravel()
+        if a.shape != b.shape:
+            raise ValueError("time_corr: pair_first and pair_second differ in length")
+        out = np.empty((a.size, int(corr_len)), dtype=np.float64)
+        ms = c_double(0.0)
+        self._check(self._lib.cgc_time_corr(self._h, _ptr(s), s.shape[0], s.shape[1], _ptr(a), _ptr(b), a.size, int(corr_len),
+                                            1 if circular else 0, _ptr(out), ctypes.byref(ms)))
+        return (out, ms.value) if want_ms else out
 
     def write_mtx(self, path: str, compat: bool = False):
         self._check(self._lib.cgc_write_mtx(self._h, os.fsencode(path), 1 if compat else 0))

@@ -15,6 +15,7 @@
 #include <mutex>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -1580,6 +1581,69 @@ int cgc_project(cgc_context* ctx, const float* dE_rows, int64_t n_frames, const 
     }
     cudaFree(d_x); cudaFree(d_c); cudaFree(d_o); cudaFree(d_mean); cudaFree(d_modes);
     CUDA_OK(err);
+    return CGC_OK;
+  });
+}
+
+int cgc_time_corr(cgc_context* ctx, const double* series, int n_series, int64_t n, const int32_t* pair_first,
+                  const int32_t* pair_second, int n_pairs, int64_t corr_len, int circular, double* out, double* kernel_ms) {
+  if (kernel_ms) *kernel_ms = 0.0;
+  if (!ctx || !series || !pair_first || !pair_second || !out) return fail(ctx, CGC_ERR_ARG, "null argument");
+  if (n_series < 1 || n < 1 || n_pairs < 0) return fail(ctx, CGC_ERR_ARG, "bad series or pair count");
+  if (corr_len < 1 || corr_len > n) return fail(ctx, CGC_ERR_ARG, "corr_len must be in [1, n]: lag n has no samples");
+  for (int p = 0; p < n_pairs; p++)
+    if (pair_first[p] < 0 || pair_first[p] >= n_series || pair_second[p] < 0 || pair_second[p] >= n_series)
+      return fail(ctx, CGC_ERR_ARG, "pair index outside the series");
+  if (n_pairs == 0) return CGC_OK;
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    if (!ctx->st_comp) CUDA_OK(cudaStreamCreateWithFlags(&ctx->st_comp, cudaStreamNonBlocking));
+    const int64_t stride = time_corr_series_stride(n);
+    // pairs per pass: the grid's z extent, and about 1 GiB of partial sums (CGC_TIMECORR_SCRATCH_DOUBLES: test hook)
+    int64_t scratch_cap = (int64_t)1 << 27;
+    if (const char* e = getenv("CGC_TIMECORR_SCRATCH_DOUBLES")) scratch_cap = std::max<int64_t>(1, atoll(e));
+    int batch = std::min(n_pairs, 65535);
+    int splits = 0, wsplits = 0;
+    int64_t scratch = 0;
+    for (;;) {
+      time_corr_plan(n, corr_len, batch, circular != 0, ctx->sm_count, &splits, &wsplits, &scratch);
+      if (batch == 1 || scratch <= scratch_cap) break;
+      batch = std::max(1, batch / 2);
+    }
+    double *d_s = nullptr, *d_part = nullptr, *d_o = nullptr;
+    int32_t* d_pairs = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t err = cudaSuccess;
+    auto ok = [&](cudaError_t e) { if (err == cudaSuccess) err = e; return e == cudaSuccess; };
+    float ms_total = 0.f;
+    if (ok(cudaMalloc(&d_s, sizeof(double) * n_series * stride)) && ok(cudaMalloc(&d_part, sizeof(double) * scratch)) &&
+        ok(cudaMalloc(&d_o, sizeof(double) * batch * corr_len)) && ok(cudaMalloc(&d_pairs, sizeof(int32_t) * 2 * batch)) &&
+        ok(cudaEventCreate(&e0)) && ok(cudaEventCreate(&e1)) &&
+        ok(cudaMemsetAsync(d_s, 0, sizeof(double) * n_series * stride, ctx->st_comp)) &&
+        ok(cudaMemcpy2DAsync(d_s, sizeof(double) * stride, series, sizeof(double) * n, sizeof(double) * n, (size_t)n_series,
+                             cudaMemcpyHostToDevice, ctx->st_comp))) {
+      for (int p0 = 0; p0 < n_pairs && err == cudaSuccess; p0 += batch) {
+        const int np = std::min(batch, n_pairs - p0);
+        if (!ok(cudaMemcpyAsync(d_pairs, pair_first + p0, sizeof(int32_t) * np, cudaMemcpyHostToDevice, ctx->st_comp)) ||
+            !ok(cudaMemcpyAsync(d_pairs + batch, pair_second + p0, sizeof(int32_t) * np, cudaMemcpyHostToDevice, ctx->st_comp)))
+          break;
+        ok(cudaEventRecord(e0, ctx->st_comp));
+        ctx->launches += launch_time_corr(d_s, n, d_pairs, d_pairs + batch, np, corr_len, circular != 0, ctx->sm_count, d_part,
+                                          d_o, ctx->st_comp);
+        ok(cudaGetLastError());
+        ok(cudaEventRecord(e1, ctx->st_comp));
+        ok(cudaMemcpyAsync(out + (int64_t)p0 * corr_len, d_o, sizeof(double) * np * corr_len, cudaMemcpyDeviceToHost,
+                           ctx->st_comp));
+        ok(cudaStreamSynchronize(ctx->st_comp));
+        float ms = 0.f;
+        if (err == cudaSuccess && ok(cudaEventElapsedTime(&ms, e0, e1))) ms_total += ms;
+      }
+    }
+    cudaFree(d_s); cudaFree(d_part); cudaFree(d_o); cudaFree(d_pairs);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    CUDA_OK(err);
+    if (kernel_ms) *kernel_ms = ms_total;
     return CGC_OK;
   });
 }

@@ -70,6 +70,14 @@ void launch_format_time(const float* d_x, int64_t rows, int ncol, bool to_cm, in
 // K6 (eigh_kernel.cu): batched one-sided Jacobi.  Eigenvectors end up as the rows of d_Vt; d_evals is unsorted.
 int eigh_jacobi(const double* d_A, int n_mat, int n, double* d_Wt, double* d_Vt, double* d_evals, unsigned int* d_rot,
                 int max_sweeps, cudaStream_t st, int64_t* launches);
+// K7 (timecorr_kernel.cu): out[p][tau] = sum_t f_first[t] * f_second[t + tau] / (n - tau), tau < corr_len (t + tau modulo n
+// when circular).  d_series: rows of time_corr_series_stride(n) doubles, ZERO from element n on.  d_scratch: the doubles
+// time_corr_plan asks for.  Returns the number of kernels launched.
+int64_t time_corr_series_stride(int64_t n);
+void time_corr_plan(int64_t n, int64_t corr_len, int n_pairs, bool circular, int sm_count, int* splits, int* wrap_splits,
+                    int64_t* scratch_doubles);
+int launch_time_corr(const double* d_series, int64_t n, const int32_t* d_first, const int32_t* d_second, int n_pairs,
+                     int64_t corr_len, bool circular, int sm_count, double* d_scratch, double* d_out, cudaStream_t st);
 void launch_narrow(const double* in, float* out, int64_t n, cudaStream_t st);   // out[i] = (float)in[i]
 void launch_cov_finalize(const double* buf, int S, int G, int ddof, double* mean, double* cov, cudaStream_t st);
 

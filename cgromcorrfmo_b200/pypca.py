@@ -11,6 +11,7 @@ what follows it (eigen-decomposition, projection) is plain numpy, as in depca.
     Corr_i_ab, AvgEia    = AvgAndCorrelateSidechains_gpu(traj, top, itp, T)   # depca's return order
     vi, wi, impact_i     = ComputeModes(Corr_i_ab)                            # or ComputeModes_gpu(ctx, Corr_i_ab)
     proj_t_im            = ApplyPCA_gpu(ctx, E_t_ia, AvgEia, wi)              # (E - mean) . modes on FP64 tensor cores
+    C_t                  = HDFStoreCt_v3(ctx, E_t_ia, site_a, site_b, chromo=1, nframes=T, corr_len=L)   # time correlation (K7)
 """
 from __future__ import annotations
 
@@ -121,3 +122,64 @@ def ApplyPCA_gpu(ctx, E_t_ia, AvgEia, wi):
     the means and the modes are host arrays as above.  Returns float64 (T, Nsites, Nmodes) == ApplyPCA(E_t_ia, AvgEia, wi)
     up to FP64 summation order (K4, DMMA; C-ABI cgc_project)."""
     return ctx.project(E_t_ia, AvgEia, wi)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# time-correlation functions (sidechain_corr.py:133-242) on the device: K7, C-ABI cgc_time_corr.  The reference reads the
+# (T, Nsites, Ncoarse) dataset from HDF5; here it is the array itself (load_E_t_ia / load_E_t_ia_npy), everything else —
+# argument names, 1-based `chromo`, the mean over the WHOLE series, the window [offset, offset + nframes), the error
+# texts — is the scripts'.
+# ---------------------------------------------------------------------------------------------------------------------
+def TimeCorr_gpu(ctx, f1, f2):
+    """depca TimeCorr (sidechain_corr.py:133-139): np.correlate(f1, f2, 'full')[n-1:] / (n - tau) for every lag, i.e.
+    sum_t f2[t] f1[t + tau] / (n - tau); None when both series are identically zero, as there."""
+    f1 = np.asarray(f1, dtype=np.float64).ravel()
+    f2 = np.asarray(f2, dtype=np.float64).ravel()
+    assert f1.size == f2.size
+    if not (np.any(f1 != 0.0) or np.any(f2 != 0.0)):
+        return None
+    return ctx.time_corr(np.stack([f1, f2]), [1], [0], f1.size)[0]
+
+
+def _ct_series(E_tij, columns, chromo, offset, nframes, check):
+    start, stop = offset, offset + nframes
+    if check:
+        if start >= E_tij.shape[0]:
+            raise RuntimeError("offset > len(E_tij) [{} > {}]; Use a smaller offset.".format(start, E_tij.shape[0]))
+        if stop > E_tij.shape[0]:
+            raise RuntimeError("offset + nframes > len(E_tij) [{} > {}]; Use a smaller offset or fewer frames.".format(
+                stop, E_tij.shape[0]))
+    cols = np.asarray(columns, dtype=np.int64)
+    X = np.asarray(E_tij[:, chromo - 1, :][:, cols], dtype=np.float64)          # (T, n_cols)
+    return np.ascontiguousarray((X[start:stop] - X.mean(axis=0)).T)               # mean over the whole series (:179-180)
+
+
+def HDFStoreCt_v1(ctx, E_tij, site_a, site_b, chromo=1, offset=0, nframes=200000):
+    """sidechain_corr.py:170-182: TimeCorr of the two columns, first tenth of the lags (no bounds checks there)."""
+    s = _ct_series(E_tij, [site_a, site_b], chromo, offset, nframes, check=False)
+    n = s.shape[1]
+    if not np.any(s != 0.0):
+        raise TypeError("'NoneType' object is not subscriptable")   # TimeCorr returned None in the script
+    return ctx.time_corr(s, [1], [0], n)[0][0:n // 10]
+
+
+def HDFStoreCt_v2(ctx, E_tij, site_a, site_b, chromo=1, offset=0, nframes=200000, corr_len=20000):
+    """sidechain_corr.py:190-218: mycorr[tc] = inner(f1[0:n-tc], f2[tc:n]) / (n - tc)."""
+    s = _ct_series(E_tij, [site_a, site_b], chromo, offset, nframes, check=True)
+    return ctx.time_corr(s, [0], [1], corr_len)[0]
+
+
+def HDFStoreCt_v3(ctx, E_tij, site_a, site_b, chromo=1, offset=0, nframes=200000, corr_len=20000):
+    """sidechain_corr.py:221-242: the FFT form, i.e. the circular sum over the window, / (n - tau)."""
+    s = _ct_series(E_tij, [site_a, site_b], chromo, offset, nframes, check=True)
+    return ctx.time_corr(s, [0], [1], corr_len, circular=True)[0]
+
+
+def StoreCt_pairs_gpu(ctx, E_tij, pairs, chromo=1, offset=0, nframes=200000, corr_len=20000, circular=True):
+    """Many (site_a, site_b) pairs of one chromophore in one call (the scripts loop over pairs in separate processes):
+    returns float64 (len(pairs), corr_len); circular=True is HDFStoreCt_v3, False HDFStoreCt_v2."""
+    pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+    cols, inv = np.unique(pairs, return_inverse=True)
+    inv = inv.reshape(-1, 2)
+    s = _ct_series(E_tij, cols, chromo, offset, nframes, check=True)
+    return ctx.time_corr(s, inv[:, 0], inv[:, 1], corr_len, circular=circular)

@@ -168,21 +168,33 @@ int cgc_cov_accumulate_device(cgc_context *ctx, const float *d_dE_kcal, int n_fr
 /* mean [S][G] and covariance [S][G][G] (HOST, double) from the partial sums; ddof 0 = population (the formula the
  * reference intends, src/FMOparse.cpp:189-206), 1 = np.cov as used by depca (scripts/depca/depca/sidechain_corr.py:67). */
 int cgc_cov_finalize(cgc_context *ctx, int ddof, double *mean, double *cov);
+/* Eigen-decomposition of symmetric matrices on the device (K6: batched one-sided Jacobi) — numpy.linalg.eigh in depca's
+ * ComputeModes (scripts/depca/depca/sidechain_corr.py:91-96).  HOST in, HOST out: matrices float64 [n_mat][n][n];
+ * evals [n_mat][n] ascending; evecs [n_mat][n][n] with ROW k the eigenvector of evals[k] (numpy returns them as columns:
+ * depca transposes, sidechain_corr.py:97).  *sweeps (nullable) = Jacobi sweeps used.  Signs of eigenvectors are arbitrary,
+ * as with LAPACK.  (Correct, but no faster than LAPACK on the host for 24 matrices of ~1100^2: the pyPCA shim's default
+ * stays numpy) */
+int cgc_eigh(cgc_context *ctx, const double *matrices, int n_mat, int n, double *evals, double *evecs, int *sweeps);
 /* Mode projection, the step that follows the covariance in the pyPCA pipeline (depca.convert.ApplyPCA_hdf5,
  * scripts/depca/depca/convert.py:84-125, and the np.inner at the end of sidechain_corr.py's usage): per site,
  *   out[t][s][m] = sum_g (dE_rows[t][s][g] - mean[s][g]) * modes[s][m][g]
  * computed on FP64 tensor cores (K4).  All pointers are HOST memory: dE_rows float32 [n_frames][sites][numTot] (what
  * cgc_run returned, any unit), mean float64 [sites][numTot], modes float64 [sites][n_modes][numTot] (eigenvectors as
- * rows, as depca's ComputeModes returns them), out float64 [n_frames][sites][n_modes].  The eigen-decomposition itself
- * stays on the host (numpy.linalg.eigh in depca): it runs once per trajectory on 7..24 matrices. */
-/* Eigen-decomposition of symmetric matrices on the device (K6: batched one-sided Jacobi) — numpy.linalg.eigh in depca's
- * ComputeModes (scripts/depca/depca/sidechain_corr.py:91-96).  HOST in, HOST out: matrices float64 [n_mat][n][n];
- * evals [n_mat][n] ascending; evecs [n_mat][n][n] with ROW k the eigenvector of evals[k] (numpy returns them as columns:
- * depca transposes, sidechain_corr.py:97).  *sweeps (nullable) = Jacobi sweeps used.  Signs of eigenvectors are arbitrary,
- * as with LAPACK. */
-int cgc_eigh(cgc_context *ctx, const double *matrices, int n_mat, int n, double *evals, double *evecs, int *sweeps);
+ * rows, as depca's ComputeModes returns them), out float64 [n_frames][sites][n_modes]. */
 int cgc_project(cgc_context *ctx, const float *dE_rows, int64_t n_frames, const double *mean, const double *modes,
                 int n_modes, double *out);
+/* Time-correlation functions of dE series (K7), the last step of the pyPCA chain: depca's TimeCorr and HDFStoreCt_v1/v2/v3
+ * (scripts/depca/depca/sidechain_corr.py:133-139, 170-182, 190-218, 221-242).  For every pair p,
+ *   out[p][tau] = sum_t  s_first[t] * s_second[t + tau] / (n - tau),      tau = 0 .. corr_len - 1,
+ * the sum over t = 0 .. n - tau - 1 (circular == 0: np.correlate / the np.inner loop of v2), or over t = 0 .. n - 1 with
+ * t + tau taken modulo n (circular != 0: what v3's ifft(fft(f2) * conj(fft(f1))) evaluates).  v2 and v3 correlate
+ * (first, second) = (f1, f2); TimeCorr / v1 is the same call with the pair swapped.  Evaluated directly in FP64 (n * corr_len
+ * fused multiply-adds per pair), deterministic.  HOST in, HOST out: series float64 [n_series][n], already mean-free (the
+ * scripts subtract the mean of the WHOLE stored series before windowing, :179-180); pair_first / pair_second int32
+ * [n_pairs] indices into the series; out float64 [n_pairs][corr_len]; 1 <= corr_len <= n.  *kernel_ms (nullable) = device
+ * time of the correlation kernels (CUDA events).  Needs no open trajectory. */
+int cgc_time_corr(cgc_context *ctx, const double *series, int n_series, int64_t n, const int32_t *pair_first,
+                  const int32_t *pair_second, int n_pairs, int64_t corr_len, int circular, double *out, double *kernel_ms);
 
 /* ---- writers ----------------------------------------------------------------------------------------------------
  * cgc_write_time appends rows to <path> exactly as src/FMOparse.cpp:151-165 does: value = float(double(kcal)*349.7),
