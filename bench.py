@@ -81,6 +81,24 @@ def calibrate_fp64_tensor(torch, dev):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
+def time_corr_leg(capi, top, itp, device, fp64_peak):
+    """K7 (cgc_time_corr), the last step of the pyPCA chain, outside the timed region: 64 pairs of 200 000-sample series
+    over 20 000 lags (the scripts' defaults, scripts/depca/depca/sidechain_corr.py:190), device time of its kernels."""
+    n, L, n_pairs = 200000, 20000, 64
+    series = np.random.default_rng(7).normal(size=(16, n))
+    a = np.arange(n_pairs) % 16
+    b = (np.arange(n_pairs) // 16 + a + 1) % 16
+    with capi.Context(top, itp, device) as c:
+        c.time_corr(series[:2], [0], [1], 1024)
+        ms = min(c.time_corr(series, a, b, L, want_ms=True)[1] for _ in range(3))
+        launches = c.launch_count
+    flop = 2.0 * (n * L - L * (L - 1) / 2.0) * n_pairs
+    return {"kernel": "time_corr_kernel (K7, pyPCA time correlation; post-processing, not in the step)", "bound": "fp64 tensor (DMMA)",
+            "achieved": flop / ms / 1e9, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (flop / ms / 1e9 / fp64_peak) if fp64_peak else None,
+            "peak_source": "cuBLAS DGEMM 4096^3 measured in this run", "algorithmic_flop_per_call": flop, "call_ms": ms,
+            "workload": "%d pairs, n %d, corr_len %d, linear sums" % (n_pairs, n, L)}, launches
+
+
 def calibrate_h2d(torch, host, d_text):
     """Yard-stick for the end-to-end leg: pinned host -> device copy of the same text buffer, best of 5, GB/s."""
     best = 1e9
@@ -430,6 +448,12 @@ def run_ours(args):
         trr_scale = float(np.abs(out_host).max())
         ctx2.close()
         fp64_peak = calibrate_fp64_tensor(torch, dev) if rank == 0 else None
+        k7 = None
+        if rank == 0:
+            try:
+                k7, _ = time_corr_leg(capi, top, itp, local, fp64_peak)
+            except Exception as e:  # reported, never required
+                log("bench: time-correlation leg failed:", e)
 
     if rank != 0:
         if world > 1:
@@ -473,6 +497,8 @@ def run_ours(args):
          "share_of_kernel_time": k3_ms / kern_total if kern_total else None},
     ]
 
+    if k7:
+        others.append(k7)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         with tempfile.TemporaryDirectory(prefix="cgc_cpu_") as d:
