@@ -69,6 +69,8 @@ SIGNATURES = {
     "cgc_project": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "cgc_time_corr": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p,
                       POINTER(c_double)]),
+    "cgc_parse_text": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_int), c_void_p, c_int64, POINTER(c_int64),
+                       POINTER(c_double)]),
     "cgc_cov_finalize": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "cgc_write_time": (c_int, [c_char_p, c_int, c_void_p, c_int64, c_int]),
     "cgc_write_mtx": (c_int, [c_void_p, c_char_p, c_int]),
@@ -429,6 +431,25 @@ class Context:
         ms = c_double(0.0)
         self._check(self._lib.cgc_time_corr(self._h, _ptr(s), s.shape[0], s.shape[1], _ptr(a), _ptr(b), a.size, int(corr_len),
                                             1 if circular else 0, _ptr(out), ctypes.byref(ms)))
+        return (out, ms.value) if want_ms else out
+
+    def parse_text(self, text, num_col: int = 0, want_ms: bool = False):
+        """`.time` / `.mtx` text -> float64 (rows, num_col), every value bit-identical to float(token) (K8).  text: bytes, or a
+        uint8 numpy array / memmap of the file; num_col 0 = the width of the first row."""
+        if isinstance(text, (bytes, bytearray, memoryview)):
+            buf = np.frombuffer(text, dtype=np.uint8)
+        else:
+            buf = np.ascontiguousarray(text).view(np.uint8).ravel()
+        ncol = c_int(int(num_col))
+        rows = c_int64(0)
+        ms = c_double(0.0)
+        if buf.size == 0:
+            return (np.empty((0, 0)), 0.0) if want_ms else np.empty((0, 0))
+        self._check(self._lib.cgc_parse_text(self._h, _ptr(buf), buf.size, ctypes.byref(ncol), None, 0, ctypes.byref(rows), None))
+        out = np.empty((rows.value, ncol.value), dtype=np.float64)
+        if rows.value:
+            self._check(self._lib.cgc_parse_text(self._h, _ptr(buf), buf.size, ctypes.byref(ncol), _ptr(out), out.size,
+                                                 ctypes.byref(rows), ctypes.byref(ms)))
         return (out, ms.value) if want_ms else out
 
     def write_mtx(self, path: str, compat: bool = False):

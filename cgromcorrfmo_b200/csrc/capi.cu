@@ -1649,6 +1649,202 @@ int cgc_time_corr(cgc_context* ctx, const double* series, int n_series, int64_t 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// K8: `.time` / `.mtx` text -> float64
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+// strtod of every token of lines [text + b, text + e) (each line ends with '\n' or at e): the path for chunks that hold
+// tokens the device does not take (nan, inf, long mantissas, huge exponents) — and the one that names a bad token.
+// Returns the number of rows, or throws InputFileMalformed.
+int64_t parse_rows_host(const char* text, int64_t b, int64_t e, int num_col, double* out, int64_t cap_rows, int64_t row0) {
+  std::vector<int64_t> starts;
+  for (int64_t p = b; p < e;) {
+    starts.push_back(p);
+    const void* nl = memchr(text + p, '\n', (size_t)(e - p));
+    p = nl ? (const char*)nl - text + 1 : e;
+  }
+  const int64_t rows = (int64_t)starts.size();
+  if (rows > cap_rows) throw std::runtime_error("parse_text: output buffer too small");
+  starts.push_back(e);
+  const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(16u, std::max(1u, std::thread::hardware_concurrency())), rows / 64));
+  std::vector<std::string> errs((size_t)nt);
+  std::vector<int64_t> err_row((size_t)nt, INT64_MAX);
+  auto work = [&](int t) {
+    const int64_t r0 = rows * t / nt, r1 = rows * (t + 1) / nt;
+    std::string tok;
+    for (int64_t r = r0; r < r1; r++) {
+      int64_t p = starts[(size_t)r], end = starts[(size_t)r + 1];
+      if (end > p && text[end - 1] == '\n') end--;
+      int col = 0;
+      while (p <= end) {
+        const void* cm = p < end ? memchr(text + p, ',', (size_t)(end - p)) : nullptr;
+        const int64_t q = cm ? (const char*)cm - text : end;
+        tok.assign(text + p, (size_t)(q - p));
+        char* stop = nullptr;
+        const double v = strtod(tok.c_str(), &stop);
+        while (stop && (*stop == ' ' || *stop == '\t' || *stop == '\r')) stop++;
+        // Python's float() takes neither hexadecimal floats nor nan(payload), both of which strtod would accept
+        const bool foreign = tok.find_first_of("xXpP(") != std::string::npos;
+        if (stop == tok.c_str() || !stop || *stop != 0 || foreign) {
+          err_row[(size_t)t] = r;
+          errs[(size_t)t] = "could not convert string to float: '" + tok + "' (row " + std::to_string(row0 + r) + ")";
+          return;
+        }
+        if (col < num_col) out[r * num_col + col] = v;
+        col++;
+        p = q + 1;
+      }
+      if (col != num_col) {
+        err_row[(size_t)t] = r;
+        errs[(size_t)t] = "row " + std::to_string(row0 + r) + " has " + std::to_string(col) + " values, expected " + std::to_string(num_col);
+        return;
+      }
+    }
+  };
+  if (nt == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back(work, t);
+    for (auto& t : th) t.join();
+  }
+  int best = -1;
+  for (int t = 0; t < nt; t++)
+    if (err_row[(size_t)t] != INT64_MAX && (best < 0 || err_row[(size_t)t] < err_row[(size_t)best])) best = t;
+  if (best >= 0) throw InputFileMalformed(errs[(size_t)best]);
+  return rows;
+}
+
+}  // namespace
+
+int cgc_parse_text(cgc_context* ctx, const char* text, int64_t nbytes, int* num_col, double* values, int64_t cap_values,
+                   int64_t* rows_out, double* kernel_ms) {
+  if (rows_out) *rows_out = 0;
+  if (kernel_ms) *kernel_ms = 0.0;
+  if (!ctx || !text || !num_col || !rows_out) return fail(ctx, CGC_ERR_ARG, "null argument");
+  if (nbytes < 0 || *num_col < 0 || cap_values < 0) return fail(ctx, CGC_ERR_ARG, "negative size");
+  return guarded(ctx, [&]() {
+    // what f.strip() does in the reference's reader (scripts/2014-06-csv2hdf5.py:57): surrounding whitespace goes
+    int64_t b = 0, e = nbytes;
+    auto is_space = [](char c) { return c == ' ' || c == '\n' || c == '\r' || c == '\t' || c == '\f' || c == '\v'; };
+    while (b < e && is_space(text[b])) b++;
+    while (e > b && is_space(text[e - 1])) e--;
+    if (b == e) return CGC_OK;   // no rows
+    int ncol = *num_col;
+    if (ncol == 0) {   // columns of the first line
+      const void* nl = memchr(text + b, '\n', (size_t)(e - b));
+      const int64_t le = nl ? (const char*)nl - text : e;
+      ncol = 1;
+      for (int64_t p = b; p < le; p++) ncol += text[p] == ',';
+      *num_col = ncol;
+    }
+    need_device(ctx);
+    if (!ctx->st_comp) CUDA_OK(cudaStreamCreateWithFlags(&ctx->st_comp, cudaStreamNonBlocking));
+    cudaStream_t st = ctx->st_comp;
+    // chunks of at most ~1 GiB of text, cut behind a newline
+    int64_t chunk_cap = (int64_t)1 << 30;
+    if (const char* env = getenv("CGC_PARSE_CHUNK_BYTES")) chunk_cap = std::max<int64_t>(64, atoll(env));   // test hook
+    const int64_t biggest = std::min<int64_t>(e - b, chunk_cap) + 1;
+    char* d_text = nullptr;
+    int* d_counts = nullptr;
+    int64_t* d_offsets = nullptr;
+    unsigned long long* d_tot = nullptr;   // [0] delimiters [1] newlines [2] first bad row
+    int* d_flags = nullptr;
+    double* d_out = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t err = cudaSuccess;
+    auto ok = [&](cudaError_t x) { if (err == cudaSuccess) err = x; return x == cudaSuccess; };
+    std::string problem;
+    int problem_code = CGC_OK;
+    int64_t rows_done = 0;
+    int64_t out_cap = 0;
+    float ms_total = 0.f;
+    const int64_t tiles_max = parse_text_tiles(biggest);
+    if (ok(cudaMalloc(&d_text, (size_t)parse_text_padded_bytes(biggest))) && ok(cudaMalloc(&d_counts, sizeof(int) * (size_t)tiles_max)) &&
+        ok(cudaMalloc(&d_offsets, sizeof(int64_t) * (size_t)tiles_max)) && ok(cudaMalloc(&d_tot, sizeof(unsigned long long) * 3)) &&
+        ok(cudaMalloc(&d_flags, sizeof(int))) && ok(cudaEventCreate(&e0)) && ok(cudaEventCreate(&e1))) {
+      for (int64_t p = b; p < e && err == cudaSuccess && problem_code == CGC_OK;) {
+        // this chunk: [p, q) of the text plus a final newline if the text does not supply one
+        int64_t q = std::min(e, p + chunk_cap);
+        if (q < e) {
+          const void* last = memrchr(text + p, '\n', (size_t)(q - p));
+          if (last) q = (const char*)last - text + 1;
+          else {   // a line longer than the chunk: take it whole
+            const void* nl = memchr(text + q, '\n', (size_t)(e - q));
+            q = nl ? (const char*)nl - text + 1 : e;
+          }
+        }
+        const bool add_nl = text[q - 1] != '\n';
+        const int64_t n = q - p + (add_nl ? 1 : 0);
+        if (parse_text_padded_bytes(n) > parse_text_padded_bytes(biggest)) {   // only after the long-line case above
+          problem = "parse_text: a single line exceeds the chunk size";
+          problem_code = CGC_ERR_UNSUPPORTED;
+          break;
+        }
+        const char nlc = '\n';
+        if (!ok(cudaMemcpyAsync(d_text, text + p, (size_t)(q - p), cudaMemcpyHostToDevice, st))) break;
+        if (add_nl && !ok(cudaMemcpyAsync(d_text + (q - p), &nlc, 1, cudaMemcpyHostToDevice, st))) break;
+        if (!ok(cudaMemsetAsync(d_text + n, 0, (size_t)(parse_text_padded_bytes(n) - n), st))) break;
+        ok(cudaEventRecord(e0, st));
+        launch_parse_count(d_text, n, d_counts, d_tot, ctx->sm_count, st);
+        ctx->launches += 1;
+        unsigned long long tot[2] = {0, 0};
+        ok(cudaMemcpyAsync(tot, d_tot, sizeof(tot), cudaMemcpyDeviceToHost, st));
+        if (!ok(cudaStreamSynchronize(st)) || !ok(cudaGetLastError())) break;
+        const int64_t rows = (int64_t)tot[1];
+        if (values) {
+          if ((rows_done + rows) * ncol > cap_values) {
+            problem = "parse_text: output buffer too small";
+            problem_code = CGC_ERR_ARG;
+            break;
+          }
+          const int64_t nvals = rows * ncol;
+          if (nvals > out_cap) {
+            if (d_out) cudaFree(d_out);
+            d_out = nullptr;
+            if (!ok(cudaMalloc(&d_out, sizeof(double) * (size_t)nvals))) break;
+            out_cap = nvals;
+          }
+          launch_parse(d_text, n, d_counts, d_offsets, ncol, nvals, d_out, d_flags, d_tot + 2, ctx->sm_count, st);
+          ctx->launches += 2;
+          ok(cudaEventRecord(e1, st));
+          int flags = 0;
+          unsigned long long bad_row = 0;
+          ok(cudaMemcpyAsync(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+          ok(cudaMemcpyAsync(&bad_row, d_tot + 2, sizeof(bad_row), cudaMemcpyDeviceToHost, st));
+          ok(cudaMemcpyAsync(values + rows_done * ncol, d_out, sizeof(double) * (size_t)nvals, cudaMemcpyDeviceToHost, st));
+          if (!ok(cudaStreamSynchronize(st)) || !ok(cudaGetLastError())) break;
+          float ms = 0.f;
+          if (ok(cudaEventElapsedTime(&ms, e0, e1))) ms_total += ms;
+          if (flags != 0 || (int64_t)tot[0] != nvals) {
+            // a token for strtod, or a ragged row: the host parses this chunk and either fills it in or names the culprit
+            try {
+              parse_rows_host(text, p, q, ncol, values + rows_done * ncol, (cap_values / ncol) - rows_done, rows_done);
+            } catch (const std::exception& ex) {
+              problem = ex.what();
+              problem_code = CGC_ERR_INPUT_MALFORMED;
+              break;
+            }
+          }
+        }
+        rows_done += rows;
+        p = q;
+      }
+    }
+    cudaFree(d_text); cudaFree(d_counts); cudaFree(d_offsets); cudaFree(d_tot); cudaFree(d_flags); cudaFree(d_out);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    CUDA_OK(err);
+    if (problem_code != CGC_OK) {
+      ctx->err = problem;
+      return problem_code;
+    }
+    *rows_out = rows_done;
+    if (kernel_ms) *kernel_ms = ms_total;
+    return CGC_OK;
+  });
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // writers
 // ---------------------------------------------------------------------------------------------------------------------
 namespace {

@@ -78,6 +78,16 @@ void time_corr_plan(int64_t n, int64_t corr_len, int n_pairs, bool circular, int
                     int64_t* scratch_doubles);
 int launch_time_corr(const double* d_series, int64_t n, const int32_t* d_first, const int32_t* d_second, int n_pairs,
                      int64_t corr_len, bool circular, int sm_count, double* d_scratch, double* d_out, cudaStream_t st);
+// K8 (parse_kernel.cu): "%g" CSV text -> float64, bit-exact with strtod.  d_text: parse_text_padded_bytes(n_bytes) bytes,
+// ZERO behind the text, 16-byte aligned.  launch_parse_count fills d_tile_counts (parse_text_tiles ints) and d_totals
+// ([0] delimiters, [1] newlines); launch_parse writes value i = token i into d_out (cap doubles) and sets *d_flags (1: a
+// token needs the host's strtod, 2: a row does not have num_col values, *d_bad_row = the first such row).
+int64_t parse_text_padded_bytes(int64_t n_bytes);
+int64_t parse_text_tiles(int64_t n_bytes);
+void launch_parse_count(const char* d_text, int64_t n_bytes, int* d_tile_counts, unsigned long long* d_totals, int sm_count,
+                        cudaStream_t st);
+void launch_parse(const char* d_text, int64_t n_bytes, const int* d_tile_counts, int64_t* d_tile_offsets, int num_col,
+                  int64_t cap, double* d_out, int* d_flags, unsigned long long* d_bad_row, int sm_count, cudaStream_t st);
 void launch_narrow(const double* in, float* out, int64_t n, cudaStream_t st);   // out[i] = (float)in[i]
 void launch_cov_finalize(const double* buf, int S, int G, int ddof, double* mean, double* cov, cudaStream_t st);
 

@@ -53,6 +53,22 @@ def load_E_t_ia_npy(time_npy_path, units="cm-1"):
     return (np.asarray(E, dtype=np.float64) * CM_PER_KCAL).astype(np.float32)
 
 
+def load_E_t_ia_csv(ctx, csv_file, frames_per_file=None, Nsites=7, dtype=np.float32):
+    """A `.time` text file as depca's E_t_ia, for files that exist only as text (earlier runs of the reference): what
+    scripts/2014-06-csv2hdf5.py:56-74 does — every token through float(), reshape to (frames_per_file, 7, 357), stored in an
+    HDF5 dataset of h5py's default dtype float32 — with the text parsed on the device (K8, C-ABI cgc_parse_text; values
+    bit-identical to float(token)).  frames_per_file=None takes what the file holds; a number must be right, as in the
+    script ("must be correct for script to function").  dtype=np.float64 keeps what float() returned."""
+    text = np.memmap(csv_file, dtype=np.uint8, mode="r") if not isinstance(csv_file, (bytes, bytearray)) else csv_file
+    rows = ctx.parse_text(text)
+    if rows.shape[0] % Nsites:
+        raise ValueError("%d rows are not a whole number of frames of %d sites" % (rows.shape[0], Nsites))
+    frames = rows.shape[0] // Nsites
+    if frames_per_file is not None and frames_per_file != frames:
+        raise ValueError("cannot reshape array of size %d into shape (%d,%d,%d)" % (rows.size, frames_per_file, Nsites, rows.shape[1]))
+    return rows.reshape(frames, Nsites, rows.shape[1]).astype(dtype, copy=False)
+
+
 def AvgAndCorrelateSidechains_gpu(traj, top, itp, num_frames, sites=7, device=0, units="cm-1"):
     """depca.sidechain_corr.AvgAndCorrelateSidechains (sidechain_corr.py:36-72) without materialising the time series on
     the host: returns (Corr_i_ab [Nsites, Ncoarse, Ncoarse], AvgEia [Nsites, Ncoarse]) — np.cov(rowvar=0) (ddof 1) and the

@@ -196,6 +196,20 @@ int cgc_project(cgc_context *ctx, const float *dE_rows, int64_t n_frames, const 
 int cgc_time_corr(cgc_context *ctx, const double *series, int n_series, int64_t n, const int32_t *pair_first,
                   const int32_t *pair_second, int n_pairs, int64_t corr_len, int circular, double *out, double *kernel_ms);
 
+/* `.time` / `.mtx` text back into numbers (K8, the inverse of the device formatter): what the reference's consumers do with
+ * `[[float(x) for x in l.split(',')] for l in f.strip().split("\n")]` (scripts/2014-06-csv2hdf5.py:56-65) and genfromtxt
+ * (scripts/depca/depca/dedata.py:96-120).  HOST in, HOST out.  text: rows of values separated by ',' and ended by '\n'
+ * (surrounding whitespace is stripped, a missing final newline is supplied).  *num_col in: expected values per row, 0 = take
+ * the count of the first row; out: the count used.  values: float64 [rows][*num_col], every entry BIT-IDENTICAL to strtod /
+ * Python float of its token; NULL = count only (*rows_out is then the number of rows, for sizing the buffer).  Tokens of the
+ * form [-+]digits[.digits][e[-+]digits] with <= 15 significant digits and |decimal exponent| <= 22 — everything "%g" prints
+ * for finite values between 1e-17 and 1e27 — are converted on the device (one correctly rounded multiply or divide by an exact
+ * power of ten); a chunk holding anything else (nan, inf, longer tokens) is re-read by the host with strtod.
+ * CGC_ERR_INPUT_MALFORMED when a row has another number of values or a token is not a number (the message names the row).
+ * *kernel_ms (nullable) = device time of the kernels.  Needs no open trajectory. */
+int cgc_parse_text(cgc_context *ctx, const char *text, int64_t nbytes, int *num_col, double *values, int64_t cap_values,
+                   int64_t *rows_out, double *kernel_ms);
+
 /* ---- writers ----------------------------------------------------------------------------------------------------
  * cgc_write_time appends rows to <path> exactly as src/FMOparse.cpp:151-165 does: value = float(double(kcal)*349.7),
  * printed with "%g" (6 significant digits), ',' separated, one line per (frame, site).  truncate != 0 empties the file
