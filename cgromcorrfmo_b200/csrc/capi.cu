@@ -1737,6 +1737,24 @@ int cgc_parse_text(cgc_context* ctx, const char* text, int64_t nbytes, int* num_
       for (int64_t p = b; p < le; p++) ncol += text[p] == ',';
       *num_col = ncol;
     }
+    if (!values) {   // count only: the rows are the newlines (plus a last line without one), counted on the host
+      const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(8, (e - b) >> 24));
+      std::vector<int64_t> part((size_t)nt, 0);
+      auto count = [&](int t) {
+        const int64_t p0 = b + (e - b) * t / nt, p1 = b + (e - b) * (t + 1) / nt;
+        part[(size_t)t] = std::count(text + p0, text + p1, '\n');
+      };
+      if (nt == 1) count(0);
+      else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back(count, t);
+        for (auto& t : th) t.join();
+      }
+      int64_t rows = 1;   // the stripped text does not end with a newline
+      for (int64_t v : part) rows += v;
+      *rows_out = rows;
+      return CGC_OK;
+    }
     need_device(ctx);
     if (!ctx->st_comp) CUDA_OK(cudaStreamCreateWithFlags(&ctx->st_comp, cudaStreamNonBlocking));
     cudaStream_t st = ctx->st_comp;
@@ -1750,7 +1768,7 @@ int cgc_parse_text(cgc_context* ctx, const char* text, int64_t nbytes, int* num_
     unsigned long long* d_tot = nullptr;   // [0] delimiters [1] newlines [2] first bad row
     int* d_flags = nullptr;
     double* d_out = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     cudaError_t err = cudaSuccess;
     auto ok = [&](cudaError_t x) { if (err == cudaSuccess) err = x; return x == cudaSuccess; };
     std::string problem;
@@ -1760,8 +1778,8 @@ int cgc_parse_text(cgc_context* ctx, const char* text, int64_t nbytes, int* num_
     float ms_total = 0.f;
     const int64_t tiles_max = parse_text_tiles(biggest);
     if (ok(cudaMalloc(&d_text, (size_t)parse_text_padded_bytes(biggest))) && ok(cudaMalloc(&d_counts, sizeof(int) * (size_t)tiles_max)) &&
-        ok(cudaMalloc(&d_offsets, sizeof(int64_t) * (size_t)tiles_max)) && ok(cudaMalloc(&d_tot, sizeof(unsigned long long) * 3)) &&
-        ok(cudaMalloc(&d_flags, sizeof(int))) && ok(cudaEventCreate(&e0)) && ok(cudaEventCreate(&e1))) {
+        ok(cudaMalloc(&d_offsets, (size_t)parse_text_scan_bytes(biggest))) && ok(cudaMalloc(&d_tot, sizeof(unsigned long long) * 3)) &&
+        ok(cudaMalloc(&d_flags, sizeof(int))) && ok(cudaEventCreate(&e0)) && ok(cudaEventCreate(&e1)) && ok(cudaEventCreate(&e2))) {
       for (int64_t p = b; p < e && err == cudaSuccess && problem_code == CGC_OK;) {
         // this chunk: [p, q) of the text plus a final newline if the text does not supply one
         int64_t q = std::min(e, p + chunk_cap);
@@ -1787,11 +1805,12 @@ int cgc_parse_text(cgc_context* ctx, const char* text, int64_t nbytes, int* num_
         ok(cudaEventRecord(e0, st));
         launch_parse_count(d_text, n, d_counts, d_tot, ctx->sm_count, st);
         ctx->launches += 1;
+        ok(cudaEventRecord(e1, st));
         unsigned long long tot[2] = {0, 0};
         ok(cudaMemcpyAsync(tot, d_tot, sizeof(tot), cudaMemcpyDeviceToHost, st));
         if (!ok(cudaStreamSynchronize(st)) || !ok(cudaGetLastError())) break;
         const int64_t rows = (int64_t)tot[1];
-        if (values) {
+        {
           if ((rows_done + rows) * ncol > cap_values) {
             problem = "parse_text: output buffer too small";
             problem_code = CGC_ERR_ARG;
@@ -1804,9 +1823,12 @@ int cgc_parse_text(cgc_context* ctx, const char* text, int64_t nbytes, int* num_
             if (!ok(cudaMalloc(&d_out, sizeof(double) * (size_t)nvals))) break;
             out_cap = nvals;
           }
+          float ms_count = 0.f;
+          ok(cudaEventElapsedTime(&ms_count, e0, e1));
+          ok(cudaEventRecord(e0, st));
           launch_parse(d_text, n, d_counts, d_offsets, ncol, nvals, d_out, d_flags, d_tot + 2, ctx->sm_count, st);
-          ctx->launches += 2;
-          ok(cudaEventRecord(e1, st));
+          ctx->launches += 3;
+          ok(cudaEventRecord(e2, st));
           int flags = 0;
           unsigned long long bad_row = 0;
           ok(cudaMemcpyAsync(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1814,7 +1836,7 @@ int cgc_parse_text(cgc_context* ctx, const char* text, int64_t nbytes, int* num_
           ok(cudaMemcpyAsync(values + rows_done * ncol, d_out, sizeof(double) * (size_t)nvals, cudaMemcpyDeviceToHost, st));
           if (!ok(cudaStreamSynchronize(st)) || !ok(cudaGetLastError())) break;
           float ms = 0.f;
-          if (ok(cudaEventElapsedTime(&ms, e0, e1))) ms_total += ms;
+          if (ok(cudaEventElapsedTime(&ms, e0, e2))) ms_total += ms + ms_count;
           if (flags != 0 || (int64_t)tot[0] != nvals) {
             // a token for strtod, or a ragged row: the host parses this chunk and either fills it in or names the culprit
             try {
@@ -1833,6 +1855,7 @@ int cgc_parse_text(cgc_context* ctx, const char* text, int64_t nbytes, int* num_
     cudaFree(d_text); cudaFree(d_counts); cudaFree(d_offsets); cudaFree(d_tot); cudaFree(d_flags); cudaFree(d_out);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
+    if (e2) cudaEventDestroy(e2);
     CUDA_OK(err);
     if (problem_code != CGC_OK) {
       ctx->err = problem;

@@ -84,6 +84,7 @@ int launch_time_corr(const double* d_series, int64_t n, const int32_t* d_first, 
 // token needs the host's strtod, 2: a row does not have num_col values, *d_bad_row = the first such row).
 int64_t parse_text_padded_bytes(int64_t n_bytes);
 int64_t parse_text_tiles(int64_t n_bytes);
+int64_t parse_text_scan_bytes(int64_t n_bytes);   // scratch of launch_parse (d_tile_offsets)
 void launch_parse_count(const char* d_text, int64_t n_bytes, int* d_tile_counts, unsigned long long* d_totals, int sm_count,
                         cudaStream_t st);
 void launch_parse(const char* d_text, int64_t n_bytes, const int* d_tile_counts, int64_t* d_tile_offsets, int num_col,

@@ -33,7 +33,7 @@ def main():
                 best_ms = min(best_ms, ms)
             alg = 2.0 * text.size + 8.0 * got.size     # the text is read by both passes, every value written once
             print("kernels %.3f ms: %.1f GB/s of text, %.0f GB/s algorithmic traffic (2 x text + 8 B/value); call %.1f ms wall "
-                  "(two H2D copies of the text from pageable memory + D2H of the values)"
+                  "(H2D of the text from pageable memory + D2H of the values into fresh pages)"
                   % (best_ms, text.size / best_ms / 1e6, alg / best_ms / 1e6, best_wall * 1e3))
         sample_rows = 24 * 8
         sample = bytes(text[: 0]) + b"\n".join(text.tobytes().split(b"\n", sample_rows)[:sample_rows]) + b"\n"

@@ -131,5 +131,5 @@ def test_gpu_chunked_like_whole(gpu_ctx, oracle_mod, monkeypatch):
     assert np.array_equal(_bits(whole), _bits(want)) and np.array_equal(_bits(cut), _bits(want))
     bad = text.replace(b"\n", b",1\n", 1)
     monkeypatch.setenv("CGC_PARSE_CHUNK_BYTES", "5000")
-    with pytest.raises(capi.CgcError, match="row 0 has 42 values"):
+    with pytest.raises(capi.CgcError, match="row 1 has 41 values, expected 42"):
         gpu_ctx.parse_text(bad)
