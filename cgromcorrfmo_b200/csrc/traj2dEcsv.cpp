@@ -236,7 +236,11 @@ int main(int argc, char** argv) {
   long long done_total = resumed_frames;
   int which = 0;
   bool eof = false;
+  const char* pause_env = getenv("CGC_CLI_CHUNK_PAUSE_MS");   // test hook: lets a test land a SIGINT inside the loop
+  const int pause_ms = pause_env ? atoi(pause_env) : 0;
   while (done_total < num_frames && g_keep_running && !eof) {
+    if (pause_ms > 0 && done_total > resumed_frames) std::this_thread::sleep_for(std::chrono::milliseconds(pause_ms));
+    if (!g_keep_running) break;
     const long long n = std::min(chunk, num_frames - done_total);
     if (host_format || verbose || npy_file != nullptr) buf[which].resize((size_t)n * row);
     int64_t done = 0;

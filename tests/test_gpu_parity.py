@@ -725,3 +725,40 @@ def test_cli_checkpoint_and_resume(small_inputs, tmp_path):
     # a checkpoint of another run is refused
     r = subprocess.run([build.CLI, traj, top, itp, part, str(frames), "--resume", ck, "--sites", "3"], capture_output=True, text=True)
     assert r.returncode == 1 and "cannot resume" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_sigint_stops_after_the_current_chunk(small_inputs, tmp_path):
+    """SIGINT: the reference finishes the frame in hand, writes the .mtx of the frames seen and exits 0
+    (src/FMOparse.cpp:24-29,62,68); so does the CLI, chunk-wise.  The rows written are whole and are a prefix of a full run."""
+    import signal
+    import subprocess
+    import time
+    from cgromcorrfmo_b200 import build
+    traj, top, itp, frames = small_inputs("tiny")
+    blob = open(traj, "rb").read()
+    reps = 40
+    long_traj = str(tmp_path / "long.gro")
+    with open(long_traj, "wb") as f:
+        for _ in range(reps):
+            f.write(blob)
+    total = frames * reps
+    full, part = str(tmp_path / "full"), str(tmp_path / "part")
+    r = subprocess.run([build.CLI, long_traj, top, itp, full, str(total), "--batch-frames", "1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    env = dict(os.environ, CGC_CLI_CHUNK_PAUSE_MS="400")
+    p = subprocess.Popen([build.CLI, long_traj, top, itp, part, str(total), "--batch-frames", "1"], env=env,
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    deadline = time.time() + 60
+    while time.time() < deadline and not (os.path.exists(part + ".time") and os.path.getsize(part + ".time") > 0):
+        time.sleep(0.02)
+    p.send_signal(signal.SIGINT)
+    out, err = p.communicate(timeout=60)
+    assert p.returncode == 0, err
+    assert "Received cancellation" in err
+    want = open(full + ".time", "rb").read()
+    got = open(part + ".time", "rb").read()
+    assert 0 < len(got) < len(want) and want.startswith(got) and got.endswith(b"\n")
+    n_rows = got.count(b"\n")
+    assert n_rows % 8 == 0 and n_rows // 8 < total          # whole frames (8 chromophores), fewer than asked for
+    assert os.path.exists(part + ".mtx")
