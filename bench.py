@@ -4,10 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames-per-step F]
 
 Workload (BASELINE.json configs[1], "C2"): synthetic FMO trimer, 100 000 atoms, 24 BCL chromophores, ~1.1k residue
-groups, fixed-column .gro text (45 B per atom line), seed 1002.  One STEP = one batch of F frames (default 128) pushed
+groups, fixed-column .gro text (45 B per atom line), seed 1002.  One STEP = one batch of F frames (default 256) pushed
 through the whole hot path: K1 text decode -> K2 CDC pair sums for all 24 sites -> float32 dE rows -> K3 Correlate sums.
 The F frames are distinct pre-generated frames; every step re-streams them (a 10 000-frame file would be 45 GB), which
-keeps the per-step input (F x 4.5 MB = 576 MB at F = 128) far above the 126 MB L2.
+keeps the per-step input (F x 4.5 MB = 1.15 GB at F = 256) far above the 126 MB L2.
 
   value   frames/s, whole job, text resident in HBM when the timed region starts (cgc_run_device + K3)
   e2e     frames/s through the C-ABI call a user makes (cgc_run) with HOST buffers: pinned text in, H2D copies, kernels,
@@ -548,12 +548,12 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=128)
+    ap.add_argument("--frames-per-step", type=int, default=256)
     ap.add_argument("--e2e-batch", type=int, default=32, help="frames per device batch inside cgc_run (e2e leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--device-leg-only", action="store_true",
                     help="profiling aid: run only the device-resident leg (the ncu launch list then holds nothing but "
-                         "the 128-frame launches whose shares bench.py reports in kernel_ms); prints a reduced JSON line")
+                         "the whole-step launches whose shares bench.py reports in kernel_ms); prints a reduced JSON line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
