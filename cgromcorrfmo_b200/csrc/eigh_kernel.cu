@@ -4,13 +4,14 @@
 // (reference scripts/depca/depca/sidechain_corr.py:91-96) before sorting the modes.  Here: one-sided (Hestenes) Jacobi,
 // batched over the matrices.  W starts as A and V as I, both stored transposed (row p = column p); a rotation of the pair
 // (p, q) makes the columns w_p, w_q orthogonal and is applied to v_p, v_q as well; when all columns of W = A V are
-// mutually orthogonal, V holds the eigenvectors and |lambda_p| = |w_p| with the sign of v_p . w_p.  The n/2 disjoint
-// pairs of a round-robin round are independent: one CTA per (pair, matrix), one launch per round, n - 1 rounds per sweep,
-// sweeps until a whole sweep rotates nothing.  The work is memory traffic (every round reads and writes W and V once:
-// 32 n^2 bytes per matrix), not arithmetic: 24 matrices of 1099^2 take 14 sweeps = 14 TB of traffic = 2.65 s at 5.4 TB/s,
-// against 1.9 s for LAPACK's tridiagonalisation on the box's 16 host cores (scripts/dev_eigh_check.py).  A version that
-// kept pairs of 2-6 column blocks in shared memory (1/b of the traffic) was slower still (2.8-3.9 s: the pair loop inside a
-// CTA is a chain of block-wide reductions).  So this kernel is the device-only option, not the default of the pyPCA shim.
+// mutually orthogonal, V holds the eigenvectors and |lambda_p| = |w_p| with the sign of v_p . w_p.
+// First version (jacobi_round_kernel, kept behind CGC_EIGH_UNBLOCKED for comparison): the n/2 disjoint column pairs of a
+// round-robin round are independent, one CTA per (pair, matrix), one launch per round, n - 1 rounds per sweep.  Every round
+// reads and writes W and V once (32 n^2 bytes per matrix): 24 matrices of 1099^2 took 14 sweeps = 14 TB of traffic = 2.65 s,
+// against 1.9 s for LAPACK on the box's 16 host cores.
+// Block version (jacobi_block_round_kernel, the default): pairs of 16-column BLOCKS, the 32 x 32 Gram matrix of a pair
+// rotated in shared memory — 69 rounds per sweep instead of 1098, 1/16 of the traffic: 0.73-0.80 s for the same matrices
+// (15 sweeps, transfers included; scripts/dev_eigh_check.py), eigenvalues within 4e-13 of lambda_max of LAPACK's.
 #include "kernels.cuh"
 
 #include <algorithm>
@@ -81,6 +82,185 @@ jacobi_round_kernel(double* __restrict__ Wt, double* __restrict__ Vt, int n, int
   if (threadIdx.x == 0) atomicAdd(rotations, 1u);
 }
 
+// ---- block version: one CTA per pair of 16-column blocks -------------------------------------------------------------
+// The 32 columns of a block pair are orthogonalised against each other in one visit: the CTA forms their 32 x 32 Gram
+// matrix G = [Wp Wq]^T [Wp Wq] (one pass over the columns), runs ONE cyclic Jacobi sweep on G in shared memory (31 rounds of
+// 16 disjoint rotations, the same rotation formula as above — a one-sided rotation of two columns IS a two-sided rotation
+// of their Gram matrix), accumulating the rotations in J, and applies J to the 32 rows of Wt and Vt (a second pass).
+// A round-robin over the 69 blocks of n = 1099 has 69 rounds instead of 1098, each still touching W and V once: 1/16 of the
+// memory traffic, and the arithmetic is register-tiled 4 x 4 out of shared memory.
+constexpr int kJb = 16;                 // columns per block
+constexpr int kJc = 2 * kJb;            // columns per CTA
+constexpr int kJChunk = 128;            // elements of every column staged per step
+constexpr int kJLd = kJChunk + 2;       // row stride of the staged tile (keeps 16-byte alignment, spreads the banks)
+constexpr int kJThreads = 256;
+constexpr size_t kJSmemBytes = sizeof(double) * (kJc * kJLd + kJc * (kJc + 1) + kJc * kJc + 2 * 16) + sizeof(int) * (2 * 16 + 4);
+
+__global__ void __launch_bounds__(kJThreads)
+jacobi_block_round_kernel(double* __restrict__ Wt, double* __restrict__ Vt, int n, int nb_pad, int r, double tol,
+                          int inner_sweeps, unsigned int* __restrict__ rotations) {
+  extern __shared__ __align__(16) unsigned char jsm[];
+  double* tile = reinterpret_cast<double*>(jsm);                       // [kJc][kJLd]
+  double (*G)[kJc + 1] = reinterpret_cast<double (*)[kJc + 1]>(tile + kJc * kJLd);
+  double (*J)[kJc] = reinterpret_cast<double (*)[kJc]>(&G[kJc][0]);
+  double* rot_c = &J[kJc][0];
+  double* rot_s = rot_c + 16;
+  int* rot_p = reinterpret_cast<int*>(rot_s + 16);
+  int* rot_q = rot_p + 16;
+  int* any_rot = rot_q + 16;
+  const int tid = threadIdx.x;
+  int P, Q;
+  tournament_pair(nb_pad, r, blockIdx.x, P, Q);
+  if (P > Q) { const int t = P; P = Q; Q = t; }
+  const size_t base = (size_t)blockIdx.y * n * n;
+  auto gcol = [&](int l) { return l < kJb ? P * kJb + l : Q * kJb + (l - kJb); };   // global column of local column l
+  auto stage = [&](const double* __restrict__ M, int i0) {
+    for (int e = tid; e < kJc * kJChunk; e += kJThreads) {
+      const int row = e / kJChunk, col = e - row * kJChunk;
+      const int gc = gcol(row), i = i0 + col;
+      tile[row * kJLd + col] = (gc < n && i < n) ? M[base + (size_t)gc * n + i] : 0.0;
+    }
+  };
+
+  // 1. Gram matrix: thread = (rows rg + 8a, columns cg + 8b, a quarter of the staged elements); the interleaving keeps the
+  //    eight rows a warp reads at once in different shared-memory banks
+  {
+    const int rg = (tid >> 3) & 7, cg = tid & 7, quarter = tid >> 6;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+    for (int i0 = 0; i0 < n; i0 += kJChunk) {
+      __syncthreads();
+      stage(Wt, i0);
+      __syncthreads();
+      const double* ta = tile + rg * kJLd + quarter * (kJChunk / 4);
+      const double* tb = tile + cg * kJLd + quarter * (kJChunk / 4);
+#pragma unroll 4
+      for (int i = 0; i < kJChunk / 4; i++) {
+        double x[4], y[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) { x[a] = ta[8 * a * kJLd + i]; y[a] = tb[8 * a * kJLd + i]; }
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int b = 0; b < 4; b++) acc[a][b] = fma(x[a], y[b], acc[a][b]);
+      }
+    }
+    __syncthreads();
+    // the four quarters are added in a fixed order through the (now free) tile
+    double* part = tile;   // [4][32][32]
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) part[(quarter * kJc + rg + 8 * a) * kJc + cg + 8 * b] = acc[a][b];
+    __syncthreads();
+    for (int e = tid; e < kJc * kJc; e += kJThreads) {
+      const int row = e / kJc, col = e - row * kJc;
+      G[row][col] = ((part[e] + part[kJc * kJc + e]) + part[2 * kJc * kJc + e]) + part[3 * kJc * kJc + e];
+      J[row][col] = row == col ? 1.0 : 0.0;
+    }
+    if (tid == 0) any_rot[0] = any_rot[1] = 0;
+    __syncthreads();
+  }
+
+  // 2. one cyclic sweep over the 32 columns on G, rotations accumulated in J
+  unsigned int my_rot = 0;
+  for (int rr = 0; rr < inner_sweeps * (kJc - 1); rr++) {
+    if (rr > 0 && rr % (kJc - 1) == 0) {   // a further sweep only if the last one still rotated something
+      if (any_rot[1] == 0) break;
+      __syncthreads();
+      if (tid == 0) any_rot[1] = 0;
+      __syncthreads();
+    }
+    if (tid < 16) {
+      int p, q;
+      tournament_pair(kJc, rr % (kJc - 1), tid, p, q);
+      if (p > q) { const int t = p; p = q; q = t; }
+      const double app = G[p][p], aqq = G[q][q], apq = G[p][q];
+      double c = 1.0, s = 0.0;
+      if (fabs(apq) > tol * sqrt(app * aqq)) {
+        const double zeta = (aqq - app) / (2.0 * apq);
+        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        c = 1.0 / sqrt(1.0 + t * t);
+        s = c * t;
+        my_rot++;
+        any_rot[0] = 1;
+        any_rot[1] = 1;
+      }
+      rot_c[tid] = c; rot_s[tid] = s; rot_p[tid] = p; rot_q[tid] = q;
+    }
+    __syncthreads();
+    const int k = tid >> 4, i = tid & 15;
+    const double c = rot_c[k], s = rot_s[k];
+    const int p = rot_p[k], q = rot_q[k];
+    if (s != 0.0) {   // columns p, q of G and of J:  X <- X R
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int ii = i + 16 * h;
+        const double gp = G[ii][p], gq = G[ii][q];
+        G[ii][p] = c * gp - s * gq;
+        G[ii][q] = s * gp + c * gq;
+        const double jp = J[ii][p], jq = J[ii][q];
+        J[ii][p] = c * jp - s * jq;
+        J[ii][q] = s * jp + c * jq;
+      }
+    }
+    __syncthreads();
+    if (s != 0.0) {   // rows p, q of G:  G <- R^T G
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int jj = i + 16 * h;
+        const double gp = G[p][jj], gq = G[q][jj];
+        G[p][jj] = c * gp - s * gq;
+        G[q][jj] = s * gp + c * gq;
+      }
+    }
+    __syncthreads();
+  }
+  if (my_rot) atomicAdd(rotations, my_rot);
+  if (*any_rot == 0) return;   // these 32 columns are already orthogonal: nothing to write
+
+  // 3. rows <- J^T rows for Wt and Vt: thread = (4 columns c, elements ig + 32 b), out[c][i] = sum_k J[k][c] tile[k][i];
+  //    the elements are interleaved so that a warp's stores are 32 consecutive doubles
+  const int cg = tid >> 5, ig = tid & 31;
+  for (int which = 0; which < 2; which++) {
+    double* M = which == 0 ? Wt : Vt;
+    for (int i0 = 0; i0 < n; i0 += kJChunk) {
+      __syncthreads();
+      stage(M, i0);
+      __syncthreads();
+      double out[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) out[a][b] = 0.0;
+#pragma unroll 4
+      for (int kk = 0; kk < kJc; kk++) {
+        const double2 j01 = *reinterpret_cast<const double2*>(&J[kk][4 * cg]);
+        const double2 j23 = *reinterpret_cast<const double2*>(&J[kk][4 * cg + 2]);
+        const double* trow = tile + kk * kJLd + ig;
+        const double jv[4] = {j01.x, j01.y, j23.x, j23.y}, tv[4] = {trow[0], trow[32], trow[64], trow[96]};
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int b = 0; b < 4; b++) out[a][b] = fma(jv[a], tv[b], out[a][b]);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const int gc = gcol(4 * cg + a);
+        if (gc >= n) continue;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          const int i = i0 + ig + 32 * b;
+          if (i < n) M[base + (size_t)gc * n + i] = out[a][b];
+        }
+      }
+    }
+  }
+}
+
 __global__ void eigh_init_kernel(const double* __restrict__ A, double* __restrict__ Wt, double* __restrict__ Vt, int n,
                                  int64_t total) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -116,21 +296,40 @@ int eigh_jacobi(const double* d_A, int n_mat, int n, double* d_Wt, double* d_Vt,
   const int64_t total = (int64_t)n_mat * n * n;
   eigh_init_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(d_A, d_Wt, d_Vt, n, total);
   if (launches) (*launches)++;
-  const int m = (n + 1) & ~1;
   const double tol = 1e-15;
   int sweeps = -1;
-  for (int sweep = 0; sweep < max_sweeps; sweep++) {
-    cudaMemsetAsync(d_rot, 0, sizeof(unsigned int), st);
-    if (m >= 2) {
-      for (int r = 0; r < m - 1; r++) {
-        jacobi_round_kernel<<<dim3(m / 2, n_mat), kEighThreads, 0, st>>>(d_Wt, d_Vt, n, m, r, tol, d_rot);
+  static const bool unblocked = getenv("CGC_EIGH_UNBLOCKED") != nullptr;   // the first version, kept for comparison
+  if (unblocked) {
+    const int m = (n + 1) & ~1;
+    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+      cudaMemsetAsync(d_rot, 0, sizeof(unsigned int), st);
+      if (m >= 2) {
+        for (int r = 0; r < m - 1; r++) {
+          jacobi_round_kernel<<<dim3(m / 2, n_mat), kEighThreads, 0, st>>>(d_Wt, d_Vt, n, m, r, tol, d_rot);
+        }
+        if (launches) *launches += m - 1;
       }
-      if (launches) *launches += m - 1;
+      unsigned int rot = 0;
+      cudaMemcpyAsync(&rot, d_rot, sizeof(unsigned int), cudaMemcpyDeviceToHost, st);
+      if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
+      if (rot == 0) { sweeps = sweep + 1; break; }
     }
-    unsigned int rot = 0;
-    cudaMemcpyAsync(&rot, d_rot, sizeof(unsigned int), cudaMemcpyDeviceToHost, st);
-    if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
-    if (rot == 0) { sweeps = sweep + 1; break; }
+  } else {
+    cudaFuncSetAttribute(jacobi_block_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJSmemBytes);
+    const int nb = (n + kJb - 1) / kJb;
+    const int nb_pad = std::max(2, (nb + 1) & ~1);
+    static const int inner = getenv("CGC_EIGH_INNER_SWEEPS") ? std::max(1, atoi(getenv("CGC_EIGH_INNER_SWEEPS"))) : 1;   // tuning hook (more inner sweeps per visit were measured: no fewer outer sweeps, slower)
+    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+      cudaMemsetAsync(d_rot, 0, sizeof(unsigned int), st);
+      for (int r = 0; r < nb_pad - 1; r++) {
+        jacobi_block_round_kernel<<<dim3(nb_pad / 2, n_mat), kJThreads, kJSmemBytes, st>>>(d_Wt, d_Vt, n, nb_pad, r, tol, inner, d_rot);
+      }
+      if (launches) *launches += nb_pad - 1;
+      unsigned int rot = 0;
+      cudaMemcpyAsync(&rot, d_rot, sizeof(unsigned int), cudaMemcpyDeviceToHost, st);
+      if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
+      if (rot == 0) { sweeps = sweep + 1; break; }
+    }
   }
   eigh_values_kernel<<<dim3(n, n_mat), kEighThreads, 0, st>>>(d_Wt, d_Vt, n, d_evals);
   if (launches) (*launches)++;
