@@ -10,8 +10,9 @@
 // reads and writes W and V once (32 n^2 bytes per matrix): 24 matrices of 1099^2 took 14 sweeps = 14 TB of traffic = 2.65 s,
 // against 1.9 s for LAPACK on the box's 16 host cores.
 // Block version (jacobi_block_round_kernel, the default): pairs of 16-column BLOCKS, the 32 x 32 Gram matrix of a pair
-// rotated in shared memory — 69 rounds per sweep instead of 1098, 1/16 of the traffic: 0.73-0.80 s for the same matrices
-// (15 sweeps, transfers included; scripts/dev_eigh_check.py), eigenvalues within 4e-13 of lambda_max of LAPACK's.
+// rotated in shared memory — 69 rounds per sweep instead of 1098, 1/16 of the traffic, Gram and apply passes on DMMA:
+// 0.60 s for the same matrices (15 sweeps, transfers included; scripts/dev_eigh_check.py), eigenvalues within 4e-13 of
+// lambda_max of LAPACK's.
 #include "kernels.cuh"
 
 #include <algorithm>
@@ -88,27 +89,36 @@ jacobi_round_kernel(double* __restrict__ Wt, double* __restrict__ Vt, int n, int
 // 16 disjoint rotations, the same rotation formula as above — a one-sided rotation of two columns IS a two-sided rotation
 // of their Gram matrix), accumulating the rotations in J, and applies J to the 32 rows of Wt and Vt (a second pass).
 // A round-robin over the 69 blocks of n = 1099 has 69 rounds instead of 1098, each still touching W and V once: 1/16 of the
-// memory traffic, and the arithmetic is register-tiled 4 x 4 out of shared memory.
+// memory traffic; the Gram matrix and the application of J are DMMA m8n8k4 contractions.
 constexpr int kJb = 16;                 // columns per block
 constexpr int kJc = 2 * kJb;            // columns per CTA
 constexpr int kJChunk = 128;            // elements of every column staged per step
-constexpr int kJLd = kJChunk + 2;       // row stride of the staged tile (keeps 16-byte alignment, spreads the banks)
+constexpr int kJLd = kJChunk + 4;       // row stride of the staged tile: DMMA fragment loads (8 rows x 4 elements, or 4 x 8) hit 16 banks
+constexpr int kJLdJ = kJc + 4;          // row stride of J, for the same reason
 constexpr int kJThreads = 256;
-constexpr size_t kJSmemBytes = sizeof(double) * (kJc * kJLd + kJc * (kJc + 1) + kJc * kJc + 2 * 16) + sizeof(int) * (2 * 16 + 4);
+constexpr size_t kJSmemBytes =
+    sizeof(double) * (kJc * kJLd + kJc * (kJc + 1) + kJc * kJLdJ + 2 * 16) + sizeof(int) * (2 * 16 + 4);
 
-__global__ void __launch_bounds__(kJThreads)
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kJThreads, 4)
 jacobi_block_round_kernel(double* __restrict__ Wt, double* __restrict__ Vt, int n, int nb_pad, int r, double tol,
                           int inner_sweeps, unsigned int* __restrict__ rotations) {
   extern __shared__ __align__(16) unsigned char jsm[];
   double* tile = reinterpret_cast<double*>(jsm);                       // [kJc][kJLd]
   double (*G)[kJc + 1] = reinterpret_cast<double (*)[kJc + 1]>(tile + kJc * kJLd);
-  double (*J)[kJc] = reinterpret_cast<double (*)[kJc]>(&G[kJc][0]);
+  double (*J)[kJLdJ] = reinterpret_cast<double (*)[kJLdJ]>(&G[kJc][0]);
   double* rot_c = &J[kJc][0];
   double* rot_s = rot_c + 16;
   int* rot_p = reinterpret_cast<int*>(rot_s + 16);
   int* rot_q = rot_p + 16;
   int* any_rot = rot_q + 16;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tig = lane & 3;   // DMMA fragment coordinates: A[gid][tig], B[tig][gid], C[gid][2 tig + {0, 1}]
   int P, Q;
   tournament_pair(nb_pad, r, blockIdx.x, P, Q);
   if (P > Q) { const int t = P; P = Q; Q = t; }
@@ -122,50 +132,38 @@ jacobi_block_round_kernel(double* __restrict__ Wt, double* __restrict__ Vt, int 
     }
   };
 
-  // 1. Gram matrix: thread = (rows rg + 8a, columns cg + 8b, a quarter of the staged elements); the interleaving keeps the
-  //    eight rows a warp reads at once in different shared-memory banks
+  // 1. Gram matrix G = T T^T on the FP64 tensor pipe: 4 x 4 tiles of 8 x 8, warp w owns tiles (w / 2, 2 (w % 2) + {0, 1})
   {
-    const int rg = (tid >> 3) & 7, cg = tid & 7, quarter = tid >> 6;
-    double acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-      for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+    const int tr = warp >> 1, tc = (warp & 1) * 2;
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    const double* pa = tile + (8 * tr + gid) * kJLd + tig;          // A[m = gid][k = tig] = T[8 tr + gid][i + tig]
+    const double* pb0 = tile + (8 * tc + gid) * kJLd + tig;         // B[k = tig][n = gid] = T[8 tc + gid][i + tig]
+    const double* pb1 = pb0 + 8 * kJLd;
     for (int i0 = 0; i0 < n; i0 += kJChunk) {
       __syncthreads();
       stage(Wt, i0);
       __syncthreads();
-      const double* ta = tile + rg * kJLd + quarter * (kJChunk / 4);
-      const double* tb = tile + cg * kJLd + quarter * (kJChunk / 4);
-#pragma unroll 4
-      for (int i = 0; i < kJChunk / 4; i++) {
-        double x[4], y[4];
-#pragma unroll
-        for (int a = 0; a < 4; a++) { x[a] = ta[8 * a * kJLd + i]; y[a] = tb[8 * a * kJLd + i]; }
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-          for (int b = 0; b < 4; b++) acc[a][b] = fma(x[a], y[b], acc[a][b]);
+#pragma unroll 8
+      for (int i = 0; i < kJChunk; i += 4) {
+        const double fa = pa[i], fb0 = pb0[i], fb1 = pb1[i];
+        dmma_884(acc[0][0], acc[0][1], fa, fb0);
+        dmma_884(acc[1][0], acc[1][1], fa, fb1);
       }
     }
-    __syncthreads();
-    // the four quarters are added in a fixed order through the (now free) tile
-    double* part = tile;   // [4][32][32]
 #pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-      for (int b = 0; b < 4; b++) part[(quarter * kJc + rg + 8 * a) * kJc + cg + 8 * b] = acc[a][b];
-    __syncthreads();
+    for (int t = 0; t < 2; t++) {
+      G[8 * tr + gid][8 * (tc + t) + 2 * tig] = acc[t][0];
+      G[8 * tr + gid][8 * (tc + t) + 2 * tig + 1] = acc[t][1];
+    }
     for (int e = tid; e < kJc * kJc; e += kJThreads) {
       const int row = e / kJc, col = e - row * kJc;
-      G[row][col] = ((part[e] + part[kJc * kJc + e]) + part[2 * kJc * kJc + e]) + part[3 * kJc * kJc + e];
       J[row][col] = row == col ? 1.0 : 0.0;
     }
     if (tid == 0) any_rot[0] = any_rot[1] = 0;
     __syncthreads();
   }
 
-  // 2. one cyclic sweep over the 32 columns on G, rotations accumulated in J
+  // 2. cyclic sweep(s) over the 32 columns on G, rotations accumulated in J
   unsigned int my_rot = 0;
   for (int rr = 0; rr < inner_sweeps * (kJc - 1); rr++) {
     if (rr > 0 && rr % (kJc - 1) == 0) {   // a further sweep only if the last one still rotated something
@@ -220,41 +218,43 @@ jacobi_block_round_kernel(double* __restrict__ Wt, double* __restrict__ Vt, int 
     __syncthreads();
   }
   if (my_rot) atomicAdd(rotations, my_rot);
-  if (*any_rot == 0) return;   // these 32 columns are already orthogonal: nothing to write
+  if (any_rot[0] == 0) return;   // these 32 columns are already orthogonal: nothing to write
 
-  // 3. rows <- J^T rows for Wt and Vt: thread = (4 columns c, elements ig + 32 b), out[c][i] = sum_k J[k][c] tile[k][i];
-  //    the elements are interleaved so that a warp's stores are 32 consecutive doubles
-  const int cg = tid >> 5, ig = tid & 31;
+  // 3. rows <- J^T rows for Wt and Vt on the tensor pipe: out[c][i] = sum_k J[k][c] T[k][i], M = c (4 tiles), N = i (16 tiles
+  //    per chunk, warp w owns 2w and 2w + 1), K = k (8 steps of 4)
+  const double* pj = &J[tig][gid];   // A[m = gid][k = tig] = J[4 ks + tig][8 ct + gid]
   for (int which = 0; which < 2; which++) {
     double* M = which == 0 ? Wt : Vt;
     for (int i0 = 0; i0 < n; i0 += kJChunk) {
       __syncthreads();
       stage(M, i0);
       __syncthreads();
-      double out[4][4];
+      double out[4][2][2];
 #pragma unroll
-      for (int a = 0; a < 4; a++)
+      for (int ct = 0; ct < 4; ct++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) out[a][b] = 0.0;
-#pragma unroll 4
-      for (int kk = 0; kk < kJc; kk++) {
-        const double2 j01 = *reinterpret_cast<const double2*>(&J[kk][4 * cg]);
-        const double2 j23 = *reinterpret_cast<const double2*>(&J[kk][4 * cg + 2]);
-        const double* trow = tile + kk * kJLd + ig;
-        const double jv[4] = {j01.x, j01.y, j23.x, j23.y}, tv[4] = {trow[0], trow[32], trow[64], trow[96]};
+        for (int it = 0; it < 2; it++) out[ct][it][0] = out[ct][it][1] = 0.0;
+      const double* pb = tile + tig * kJLd + 16 * warp + gid;   // B[k = tig][n = gid] = T[4 ks + tig][16 warp + 8 it + gid]
 #pragma unroll
-        for (int a = 0; a < 4; a++)
+      for (int ks = 0; ks < 8; ks++) {
+        const double fb0 = pb[4 * ks * kJLd], fb1 = pb[4 * ks * kJLd + 8];
 #pragma unroll
-          for (int b = 0; b < 4; b++) out[a][b] = fma(jv[a], tv[b], out[a][b]);
+        for (int ct = 0; ct < 4; ct++) {
+          const double fa = pj[4 * ks * kJLdJ + 8 * ct];
+          dmma_884(out[ct][0][0], out[ct][0][1], fa, fb0);
+          dmma_884(out[ct][1][0], out[ct][1][1], fa, fb1);
+        }
       }
 #pragma unroll
-      for (int a = 0; a < 4; a++) {
-        const int gc = gcol(4 * cg + a);
+      for (int ct = 0; ct < 4; ct++) {
+        const int gc = gcol(8 * ct + gid);
         if (gc >= n) continue;
+        double* row = M + base + (size_t)gc * n + i0 + 16 * warp + 2 * tig;
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-          const int i = i0 + ig + 32 * b;
-          if (i < n) M[base + (size_t)gc * n + i] = out[a][b];
+        for (int it = 0; it < 2; it++) {
+          const int i = i0 + 16 * warp + 8 * it + 2 * tig;
+          if (i < n) row[8 * it] = out[ct][it][0];
+          if (i + 1 < n) row[8 * it + 1] = out[ct][it][1];
         }
       }
     }
@@ -316,6 +316,7 @@ int eigh_jacobi(const double* d_A, int n_mat, int n, double* d_Wt, double* d_Vt,
     }
   } else {
     cudaFuncSetAttribute(jacobi_block_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJSmemBytes);
+    cudaFuncSetAttribute(jacobi_block_round_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // four CTAs of 52 KB per SM
     const int nb = (n + kJb - 1) / kJb;
     const int nb_pad = std::max(2, (nb + 1) & ~1);
     static const int inner = getenv("CGC_EIGH_INNER_SWEEPS") ? std::max(1, atoi(getenv("CGC_EIGH_INNER_SWEEPS"))) : 1;   // tuning hook (more inner sweeps per visit were measured: no fewer outer sweeps, slower)
