@@ -10,6 +10,7 @@ t0 = time.time()
 s = synth.named_system("C4")
 d = "/tmp/dev_c4"; os.makedirs(d, exist_ok=True)
 frames = 16
+e2e_frames = 16
 prefix = synth._static_prefix(s)
 top, itp = d + "/topol.top", d + "/bcx.itp"
 synth.write_top(top, s); synth.write_itp(itp, s)
@@ -43,10 +44,20 @@ with capi.Context(top, itp, 0) as c:
     print("device-resident, %d frames per launch: kernel ms %s" % (frames, {k: round(v[0] / reps, 3) for k, v in kt.items()}), flush=True)
     print("K2: %.1f Gpairs/s -> %.3f of ceiling ; K1: %.1f GB/s" % (pairs / k2 / 1e6, pairs / k2 / 1e6 / 4653.1,
           frames * c.n_atoms * 57 / (kt["decode"][0] / reps) / 1e6))
+    out = np.empty((frames, S, G), dtype=np.float32)
+    out[:] = 0                                    # touch the pages: the timed calls should not pay for page faults
+    c.set_option("batch_frames", 4)               # several batches per call, so that copies and kernels overlap
     t0 = time.time()
-    dE, done, rc = c.run(0, frames)
-    dt = time.time() - t0
-    print("cgc_run (host text -> host rows, %d frames, ramped batches): %.1f ms -> %.0f frames/s" % (frames, dt * 1e3, frames / dt), flush=True)
+    dE, done, rc = c.run(0, frames, out=out)      # first call: allocates the ring (pinned staging)
+    first = time.time() - t0
+    best = 1e9
+    for _ in range(3):
+        t0 = time.time()
+        dE, done, rc = c.run(0, frames, out=out)
+        best = min(best, time.time() - t0)
+    print("cgc_run (pinned host text -> host rows, %d frames in 4-frame batches): first call %.1f ms (ring allocation), then %.1f ms "
+          "-> %.0f frames/s = %.1f GB/s of text H2D + %.1f GB/s of rows D2H" % (frames, first * 1e3, best * 1e3, frames / best,
+          text.size / best / 1e9, out.nbytes / best / 1e9), flush=True)
 open(d + "/one.gro", "wb").write(blob[: len(blob) // frames])
 t0 = time.time()
 ref = O.run(d + "/one.gro", top, itp, 1, n_sites=3)
