@@ -11,7 +11,7 @@
 // against 1.9 s for LAPACK on the box's 16 host cores.
 // Block version (jacobi_block_round_kernel, the default): pairs of 16-column BLOCKS, the 32 x 32 Gram matrix of a pair
 // rotated in shared memory — 69 rounds per sweep instead of 1098, 1/16 of the traffic, Gram and apply passes on DMMA:
-// 0.60 s for the same matrices (15 sweeps, transfers included; scripts/dev_eigh_check.py), eigenvalues within 4e-13 of
+// 0.55 s for the same matrices (15 sweeps, transfers included; scripts/dev_eigh_check.py), eigenvalues within 4e-13 of
 // lambda_max of LAPACK's.
 #include "kernels.cuh"
 
@@ -92,12 +92,22 @@ jacobi_round_kernel(double* __restrict__ Wt, double* __restrict__ Vt, int n, int
 // memory traffic; the Gram matrix and the application of J are DMMA m8n8k4 contractions.
 constexpr int kJb = 16;                 // columns per block
 constexpr int kJc = 2 * kJb;            // columns per CTA
-constexpr int kJChunk = 128;            // elements of every column staged per step
+constexpr int kJChunk = 64;             // elements of every column staged per step (two such tiles: the copy of the next runs under the DMMAs of this one)
 constexpr int kJLd = kJChunk + 4;       // row stride of the staged tile: DMMA fragment loads (8 rows x 4 elements, or 4 x 8) hit 16 banks
 constexpr int kJLdJ = kJc + 4;          // row stride of J, for the same reason
 constexpr int kJThreads = 256;
 constexpr size_t kJSmemBytes =
-    sizeof(double) * (kJc * kJLd + kJc * (kJc + 1) + kJc * kJLdJ + 2 * 16) + sizeof(int) * (2 * 16 + 4);
+    sizeof(double) * (2 * kJc * kJLd + kJc * (kJc + 1) + kJc * kJLdJ + 2 * 16) + sizeof(int) * (2 * 16 + 4);
+
+__device__ __forceinline__ void jb_cp_async_8(void* smem_dst, const void* gsrc, bool valid) {
+  const int nbytes = valid ? 8 : 0;   // src-size 0 -> the 8 bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc),
+               "r"(nbytes)
+               : "memory");
+}
+__device__ __forceinline__ void jb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void jb_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -109,8 +119,8 @@ __global__ void __launch_bounds__(kJThreads, 4)
 jacobi_block_round_kernel(double* __restrict__ Wt, double* __restrict__ Vt, int n, int nb_pad, int r, double tol,
                           int inner_sweeps, unsigned int* __restrict__ rotations) {
   extern __shared__ __align__(16) unsigned char jsm[];
-  double* tile = reinterpret_cast<double*>(jsm);                       // [kJc][kJLd]
-  double (*G)[kJc + 1] = reinterpret_cast<double (*)[kJc + 1]>(tile + kJc * kJLd);
+  double* tiles = reinterpret_cast<double*>(jsm);                      // [2][kJc][kJLd]
+  double (*G)[kJc + 1] = reinterpret_cast<double (*)[kJc + 1]>(tiles + 2 * kJc * kJLd);
   double (*J)[kJLdJ] = reinterpret_cast<double (*)[kJLdJ]>(&G[kJc][0]);
   double* rot_c = &J[kJc][0];
   double* rot_s = rot_c + 16;
@@ -124,31 +134,49 @@ jacobi_block_round_kernel(double* __restrict__ Wt, double* __restrict__ Vt, int 
   if (P > Q) { const int t = P; P = Q; Q = t; }
   const size_t base = (size_t)blockIdx.y * n * n;
   auto gcol = [&](int l) { return l < kJb ? P * kJb + l : Q * kJb + (l - kJb); };   // global column of local column l
-  auto stage = [&](const double* __restrict__ M, int i0) {
+  const int n_chunks = (n + kJChunk - 1) / kJChunk;
+  // asynchronous copy of chunk ch of the 32 rows into tile buffer ch & 1 (zero beyond the matrix)
+  auto stage = [&](const double* __restrict__ M, int ch) {
+    double* tile = tiles + (ch & 1) * kJc * kJLd;
+    const int i0 = ch * kJChunk;
+#pragma unroll
     for (int e = tid; e < kJc * kJChunk; e += kJThreads) {
       const int row = e / kJChunk, col = e - row * kJChunk;
       const int gc = gcol(row), i = i0 + col;
-      tile[row * kJLd + col] = (gc < n && i < n) ? M[base + (size_t)gc * n + i] : 0.0;
+      const bool valid = gc < n && i < n;
+      jb_cp_async_8(&tile[row * kJLd + col], M + base + (valid ? (size_t)gc * n + i : 0), valid);
     }
+    jb_cp_async_commit();
+  };
+  // chunk ch is in its buffer and visible to the CTA; the copy of chunk ch + 1 is in flight
+  auto advance = [&](const double* __restrict__ M, int ch) {
+    if (ch + 1 < n_chunks) {
+      stage(M, ch + 1);
+      jb_cp_async_wait<1>();
+    } else {
+      jb_cp_async_wait<0>();
+    }
+    __syncthreads();
   };
 
   // 1. Gram matrix G = T T^T on the FP64 tensor pipe: 4 x 4 tiles of 8 x 8, warp w owns tiles (w / 2, 2 (w % 2) + {0, 1})
   {
     const int tr = warp >> 1, tc = (warp & 1) * 2;
     double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-    const double* pa = tile + (8 * tr + gid) * kJLd + tig;          // A[m = gid][k = tig] = T[8 tr + gid][i + tig]
-    const double* pb0 = tile + (8 * tc + gid) * kJLd + tig;         // B[k = tig][n = gid] = T[8 tc + gid][i + tig]
-    const double* pb1 = pb0 + 8 * kJLd;
-    for (int i0 = 0; i0 < n; i0 += kJChunk) {
-      __syncthreads();
-      stage(Wt, i0);
-      __syncthreads();
+    stage(Wt, 0);
+    for (int ch = 0; ch < n_chunks; ch++) {
+      advance(Wt, ch);
+      const double* tile = tiles + (ch & 1) * kJc * kJLd;
+      const double* pa = tile + (8 * tr + gid) * kJLd + tig;          // A[m = gid][k = tig] = T[8 tr + gid][i + tig]
+      const double* pb0 = tile + (8 * tc + gid) * kJLd + tig;         // B[k = tig][n = gid] = T[8 tc + gid][i + tig]
+      const double* pb1 = pb0 + 8 * kJLd;
 #pragma unroll 8
       for (int i = 0; i < kJChunk; i += 4) {
         const double fa = pa[i], fb0 = pb0[i], fb1 = pb1[i];
         dmma_884(acc[0][0], acc[0][1], fa, fb0);
         dmma_884(acc[1][0], acc[1][1], fa, fb1);
       }
+      __syncthreads();   // the buffer is free before the copy two chunks ahead lands in it
     }
 #pragma unroll
     for (int t = 0; t < 2; t++) {
@@ -220,43 +248,35 @@ jacobi_block_round_kernel(double* __restrict__ Wt, double* __restrict__ Vt, int 
   if (my_rot) atomicAdd(rotations, my_rot);
   if (any_rot[0] == 0) return;   // these 32 columns are already orthogonal: nothing to write
 
-  // 3. rows <- J^T rows for Wt and Vt on the tensor pipe: out[c][i] = sum_k J[k][c] T[k][i], M = c (4 tiles), N = i (16 tiles
-  //    per chunk, warp w owns 2w and 2w + 1), K = k (8 steps of 4)
+  // 3. rows <- J^T rows for Wt and Vt on the tensor pipe: out[c][i] = sum_k J[k][c] T[k][i], M = c (4 tiles), N = i (8 tiles
+  //    per chunk, one per warp), K = k (8 steps of 4)
   const double* pj = &J[tig][gid];   // A[m = gid][k = tig] = J[4 ks + tig][8 ct + gid]
   for (int which = 0; which < 2; which++) {
     double* M = which == 0 ? Wt : Vt;
-    for (int i0 = 0; i0 < n; i0 += kJChunk) {
-      __syncthreads();
-      stage(M, i0);
-      __syncthreads();
-      double out[4][2][2];
+    stage(M, 0);
+    for (int ch = 0; ch < n_chunks; ch++) {
+      advance(M, ch);
+      const double* tile = tiles + (ch & 1) * kJc * kJLd;
+      double out[4][2];
 #pragma unroll
-      for (int ct = 0; ct < 4; ct++)
-#pragma unroll
-        for (int it = 0; it < 2; it++) out[ct][it][0] = out[ct][it][1] = 0.0;
-      const double* pb = tile + tig * kJLd + 16 * warp + gid;   // B[k = tig][n = gid] = T[4 ks + tig][16 warp + 8 it + gid]
+      for (int ct = 0; ct < 4; ct++) out[ct][0] = out[ct][1] = 0.0;
+      const double* pb = tile + tig * kJLd + 8 * warp + gid;   // B[k = tig][n = gid] = T[4 ks + tig][8 warp + gid]
 #pragma unroll
       for (int ks = 0; ks < 8; ks++) {
-        const double fb0 = pb[4 * ks * kJLd], fb1 = pb[4 * ks * kJLd + 8];
+        const double fb = pb[4 * ks * kJLd];
 #pragma unroll
-        for (int ct = 0; ct < 4; ct++) {
-          const double fa = pj[4 * ks * kJLdJ + 8 * ct];
-          dmma_884(out[ct][0][0], out[ct][0][1], fa, fb0);
-          dmma_884(out[ct][1][0], out[ct][1][1], fa, fb1);
-        }
+        for (int ct = 0; ct < 4; ct++) dmma_884(out[ct][0], out[ct][1], pj[4 * ks * kJLdJ + 8 * ct], fb);
       }
+      const int i = ch * kJChunk + 8 * warp + 2 * tig;
 #pragma unroll
       for (int ct = 0; ct < 4; ct++) {
         const int gc = gcol(8 * ct + gid);
         if (gc >= n) continue;
-        double* row = M + base + (size_t)gc * n + i0 + 16 * warp + 2 * tig;
-#pragma unroll
-        for (int it = 0; it < 2; it++) {
-          const int i = i0 + 16 * warp + 8 * it + 2 * tig;
-          if (i < n) row[8 * it] = out[ct][it][0];
-          if (i + 1 < n) row[8 * it + 1] = out[ct][it][1];
-        }
+        double* row = M + base + (size_t)gc * n + i;
+        if (i < n) row[0] = out[ct][0];
+        if (i + 1 < n) row[1] = out[ct][1];
       }
+      __syncthreads();   // the buffer is free before the copy two chunks ahead lands in it
     }
   }
 }

@@ -172,7 +172,7 @@ int cgc_cov_finalize(cgc_context *ctx, int ddof, double *mean, double *cov);
  * ComputeModes (scripts/depca/depca/sidechain_corr.py:91-96).  HOST in, HOST out: matrices float64 [n_mat][n][n];
  * evals [n_mat][n] ascending; evecs [n_mat][n][n] with ROW k the eigenvector of evals[k] (numpy returns them as columns:
  * depca transposes, sidechain_corr.py:97).  *sweeps (nullable) = Jacobi sweeps used.  Signs of eigenvectors are arbitrary,
- * as with LAPACK.  24 matrices of 1099^2: 0.60 s against 1.9 s for LAPACK on the box's 16 host cores. */
+ * as with LAPACK.  24 matrices of 1099^2: 0.55 s against 1.9 s for LAPACK on the box's 16 host cores. */
 int cgc_eigh(cgc_context *ctx, const double *matrices, int n_mat, int n, double *evals, double *evecs, int *sweeps);
 /* Mode projection, the step that follows the covariance in the pyPCA pipeline (depca.convert.ApplyPCA_hdf5,
  * scripts/depca/depca/convert.py:84-125, and the np.inner at the end of sidechain_corr.py's usage): per site,
