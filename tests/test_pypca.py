@@ -128,3 +128,41 @@ def test_compute_modes_gpu_matches_numpy(small_inputs):
         ctx.open(traj)
         gv, gw, gi = pypca.ComputeModes_gpu(ctx, corr)
     assert np.allclose(gv, vi, rtol=1e-10) and np.allclose(gi, imp, atol=1e-8) and np.allclose(gw, wi, atol=1e-8)
+
+
+@pytest.mark.gpu
+def test_whole_pypca_chain_on_the_device(tmp_path):
+    """trajectory -> E_t_ia -> per-site covariance (K3) -> modes (K6) -> projections (K4) -> time correlation of mode
+    amplitudes (K7), every step against the numpy formulation of the depca scripts on the same rows."""
+    from cgromcorrfmo_b200 import capi, synth
+    s = synth.make_system(1200, 7, 11, "shared")
+    frames = 48
+    traj, top, itp = synth.write_inputs(str(tmp_path), s, frames)
+    E = pypca.load_E_t_ia(traj, top, itp, frames, sites=7)                     # float32 (T, 7, Ncoarse), cm^-1
+    corr, avg = pypca.AvgAndCorrelateSidechains_gpu(traj, top, itp, frames, sites=7)
+    rc, ra = pypca.AvgAndCorrelateSidechains(E)
+    # the device reduces the kcal/mol rows and scales by 349.7^2; numpy reduces the rounded cm^-1 rows: float32 rounding apart
+    assert np.allclose(corr, rc, rtol=2e-5, atol=1e-6 * np.abs(rc).max()) and np.allclose(avg, ra, rtol=1e-6, atol=1e-6)
+    with capi.Context(top, itp, 0) as ctx:
+        ctx.open(traj)
+        ctx.set_option("sites", 7)
+        vi, wi, imp = pypca.ComputeModes_gpu(ctx, rc)
+        rv, rw, ri = pypca.ComputeModes(rc)
+        assert np.allclose(vi, rv, rtol=0, atol=1e-10 * np.abs(rv).max())
+        proj = pypca.ApplyPCA_gpu(ctx, E, ra, wi)
+        assert np.allclose(proj, pypca.ApplyPCA(E, ra, wi), rtol=0, atol=1e-9 * np.abs(proj).max())
+        # modes diagonalise the covariance of the rows they were computed from (rank <= frames - 1: most eigenvalues are 0)
+        for i in range(7):
+            c = np.cov(proj[:, i, :], rowvar=False)
+            assert np.allclose(np.diag(c), vi[i], atol=1e-8 * np.abs(vi[i]).max())
+        # time correlation of the two strongest modes of chromophore 1 (sorted last), the scripts' v3 and v2 forms
+        M = proj.shape[2]
+        for fn, circ in ((pypca.HDFStoreCt_v3, True), (pypca.HDFStoreCt_v2, False)):
+            got = fn(ctx, proj, M - 1, M - 2, chromo=1, offset=0, nframes=frames, corr_len=16)
+            f1 = proj[:, 0, M - 1] - proj[:, 0, M - 1].mean()
+            f2 = proj[:, 0, M - 2] - proj[:, 0, M - 2].mean()
+            if circ:
+                want = np.real(np.fft.ifft(np.fft.fft(f2) * np.conj(np.fft.fft(f1)))[:16]) / (frames - np.arange(16))
+            else:
+                want = np.array([np.inner(f1[:frames - t], f2[t:]) / (frames - t) for t in range(16)])
+            assert np.allclose(got, want, rtol=0, atol=1e-11 * np.sqrt(np.dot(f1, f1) * np.dot(f2, f2)))
