@@ -15,6 +15,7 @@ from . import build as _build
 
 CGC_OK = 0
 CGC_EOF = 1
+CGC_STOPPED = 2
 CGC_ERR_INPUT_MALFORMED = -1
 CGC_ERR_INPUT_MINOR = -2
 CGC_ERR_READ = -3
@@ -49,6 +50,8 @@ SIGNATURES = {
     "cgc_set_option": (c_int, [c_void_p, c_char_p, c_double]),
     "cgc_get_option": (c_double, [c_void_p, c_char_p]),
     "cgc_run": (c_int, [c_void_p, c_int64, c_int64, c_void_p, POINTER(c_int64)]),
+    "cgc_request_stop": (None, [c_void_p]),
+    "cgc_cov_allreduce": (c_int, [POINTER(c_void_p), c_int]),
     "cgc_run_write_time": (c_int, [c_void_p, c_int64, c_int64, c_char_p, c_int, c_void_p, POINTER(c_int64)]),
     "cgc_format_text_device": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, POINTER(c_int64), POINTER(c_int)]),
     "cgc_run_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
@@ -290,6 +293,10 @@ class Context:
     def get_option(self, key: str) -> float:
         return float(self._lib.cgc_get_option(self._h, key.encode()))
 
+    def request_stop(self):
+        """Ask the run in progress (or the next one) to stop after the batches under way (the reference's SIGINT flag)."""
+        self._lib.cgc_request_stop(self._h)
+
     # -- hot path
     def run(self, first_frame: int, n_frames: int, want_dE: bool = True, out=None):
         """Returns (dE float32 [frames_done, sites, numTot] or None, frames_done, status)."""
@@ -298,7 +305,8 @@ class Context:
             out = np.empty((int(n_frames), S, G), np.float32)
         done = c_int64()
         rc = self._lib.cgc_run(self._h, int(first_frame), int(n_frames), _ptr(out) if want_dE else None, ctypes.byref(done))
-        self._check(rc, ok=(CGC_OK, CGC_EOF))
+        self.last_frames_done = done.value          # also meaningful when the call raises: the frames delivered before the error
+        self._check(rc, ok=(CGC_OK, CGC_EOF, CGC_STOPPED))
         if want_dE:
             out = out[: done.value]
         return (out if want_dE else None), done.value, rc
@@ -311,7 +319,8 @@ class Context:
         done = c_int64(0)
         rc = self._lib.cgc_run_write_time(self._h, first_frame, n_frames, os.fsencode(time_path), 1 if truncate else 0,
                                           _ptr(dE), ctypes.byref(done))
-        self._check(rc, ok=(CGC_OK, CGC_EOF))
+        self.last_frames_done = done.value
+        self._check(rc, ok=(CGC_OK, CGC_EOF, CGC_STOPPED))
         return (dE[:done.value] if dE is not None else None), done.value, rc
 
     def format_text_device(self, values, to_cm: bool = False):
@@ -454,6 +463,17 @@ class Context:
 
     def write_mtx(self, path: str, compat: bool = False):
         self._check(self._lib.cgc_write_mtx(self._h, os.fsencode(path), 1 if compat else 0))
+
+
+def cov_allreduce(contexts):
+    """The one collective for several contexts of THIS process (one per GPU): ncclCommInitAll + one grouped
+    ncclAllReduce(sum, double) over n, sum(x-c), sum (x-c)(x-c)^T (cgc_cov_allreduce).  Afterwards every context holds the
+    sums of all frame ranges."""
+    lib = load()
+    arr = (c_void_p * len(contexts))(*[c._h for c in contexts])
+    rc = lib.cgc_cov_allreduce(arr, len(contexts))
+    if rc != CGC_OK:
+        contexts[0]._check(rc)
 
 
 def write_time(path: str, dE_kcal, truncate: bool = True):

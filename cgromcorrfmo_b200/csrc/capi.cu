@@ -2,7 +2,9 @@
 #include "../../include/cgromcorr.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <fcntl.h>
+#include <nccl.h>     // types and enums only: the functions are bound with dlopen (cgc_cov_allreduce)
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -46,6 +48,86 @@ struct CudaError : std::runtime_error {
     }                                                                                                         \
   } while (0)
 
+// Copies byte ranges on a few background threads (page cache / pageable memory -> pinned staging, pinned rows -> caller).
+// A job is cut into chunks that the workers pull from one FIFO queue, so two jobs submitted one after the other finish in
+// that order and every worker stays busy across the boundary between them.
+class CopyPool {
+ public:
+  struct Job {
+    std::atomic<int64_t> left{0};   // chunks not yet copied
+  };
+  explicit CopyPool(int n_threads) {
+    for (int i = 0; i < std::max(1, n_threads); i++) th_.emplace_back([this] { loop(); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int threads() const { return (int)th_.size(); }
+  // drop_src_pages: src is a file mapping that is read once — give its page-table entries back as soon as a chunk is
+  // copied (MADV_DONTNEED on a shared file mapping keeps the page cache, it only unmaps), so that the cost of unmapping
+  // gigabytes does not pile up at the end of the run.
+  void submit(Job* job, char* dst, const char* src, int64_t n, bool drop_src_pages) {
+    const int64_t kChunk = 4 << 20;
+    const int64_t chunks = std::max<int64_t>(1, (n + kChunk - 1) / kChunk);
+    job->left.store(chunks);
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      for (int64_t i = 0; i < chunks; i++) {
+        const int64_t b = i * kChunk, e = std::min(n, b + kChunk);
+        q_.push_back({job, dst + b, src + b, e - b, drop_src_pages});
+      }
+    }
+    cv_.notify_all();
+  }
+  void wait(Job* job) {
+    std::unique_lock<std::mutex> g(done_mu_);
+    done_cv_.wait(g, [job] { return job->left.load() <= 0; });
+  }
+  void copy(char* dst, const char* src, int64_t n) {   // synchronous, for the caller's convenience
+    if (n < (8 << 20)) {
+      memcpy(dst, src, (size_t)n);
+      return;
+    }
+    Job j;
+    submit(&j, dst, src, n, false);
+    wait(&j);
+  }
+
+ private:
+  struct Item { Job* job; char* dst; const char* src; int64_t n; bool drop; };
+  void loop() {
+    for (;;) {
+      Item it;
+      {
+        std::unique_lock<std::mutex> g(mu_);
+        cv_.wait(g, [this] { return stop_ || !q_.empty(); });
+        if (q_.empty()) return;
+        it = q_.front();
+        q_.pop_front();
+      }
+      memcpy(it.dst, it.src, (size_t)it.n);
+      if (it.drop) {
+        const uintptr_t a = ((uintptr_t)it.src + 4095) & ~(uintptr_t)4095, b = ((uintptr_t)it.src + (uintptr_t)it.n) & ~(uintptr_t)4095;
+        if (b > a) madvise((void*)a, (size_t)(b - a), MADV_DONTNEED);
+      }
+      if (it.job->left.fetch_sub(1) == 1) {
+        std::lock_guard<std::mutex> g(done_mu_);
+        done_cv_.notify_all();
+      }
+    }
+  }
+  std::mutex mu_, done_mu_;
+  std::condition_variable cv_, done_cv_;
+  std::deque<Item> q_;
+  bool stop_ = false;
+  std::vector<std::thread> th_;
+};
+
 // One slot of the streaming ring (cgc_context::kSlots of them): text in, dE out.
 struct Slot {
   char* h_text = nullptr;   // pinned staging (file path only)
@@ -54,20 +136,25 @@ struct Slot {
   int64_t* h_off = nullptr;  // pinned
   float* d_xyz8 = nullptr;
   float4* d_sites = nullptr;
-  double* d_acc = nullptr;
+  long long* d_acc = nullptr;   // K2's fixed-point bins
   float* d_dE = nullptr;
   float* h_dE = nullptr;     // pinned
   // `.time` text of the batch, formatted on the device (cgc_run_write_time); allocated on first use
   char* d_ttext = nullptr;
-  char* h_ttext = nullptr;      // pinned
   int64_t* d_rowoff = nullptr;  // rows + 1
   int64_t* h_tinfo = nullptr;   // pinned [2]: total bytes, format flags
+  int* d_fmt_flag = nullptr;    // K5: this batch held a value outside the device formatter's range
   int64_t ttext_cap = 0;
-  std::atomic<bool>* write_pending = nullptr;   // h_ttext is still being written to the file
   cudaEvent_t ev_copied = nullptr, ev_done = nullptr;
-  int frames = 0;            // frames of the batch in flight
+  cudaEvent_t ev_text_out = nullptr;   // the D2H copy of d_ttext has finished (the next batch may overwrite d_ttext)
+  bool text_out_pending = false;
+  CopyPool::Job stage_job;   // staging copy of the batch planned into this slot
+  bool staged_here = false;  // the H2D copy reads h_text (else the caller's pinned text directly)
+  const char* src = nullptr; // where the H2D copy reads from
+  int64_t nb = 0;            // bytes of text of the batch
+  int frames = 0;            // frames of the batch planned / in flight
   int64_t out_frame = 0;     // where its rows go in the caller's dE block
-  bool busy = false;
+  bool busy = false;         // enqueued on the device, not yet drained
 };
 
 }  // namespace
@@ -103,15 +190,27 @@ struct cgc_context {
   int batch_frames = 0;
 
   // pipeline
-  static constexpr int kSlots = 3;   // batches in flight: one being copied in, one computing, one being drained
+  // batches in the ring: up to two staged ahead by the background copiers, up to two on the device (one in its H2D copy or
+  // queued, one computing) — the host thread only enqueues and drains
+  static constexpr int kSlots = 4;
+  static constexpr int kStageAhead = 2, kInFlight = 2;
   Slot slot[kSlots];
   bool dev_pipeline = false;
   int alloc_batch = 0;
   int64_t alloc_text = 0;
   cudaStream_t st_copy = nullptr, st_comp = nullptr, st_out = nullptr;
   int* d_err = nullptr;
-  int* d_fmt_flags = nullptr;   // K5: a value outside the device formatter's range was met
+  int* d_fmt_flags = nullptr;   // K5 flag word of the one-shot formatter calls (cgc_write_mtx); the ring has one per slot
   int64_t launches = 0;
+  int stage_threads = 0;        // option "stage_threads"; 0 = default
+  CopyPool* pool = nullptr;     // created on first use
+  std::atomic<bool> stop_requested{false};   // cgc_request_stop
+  // pinned buffers the `.time` sink writes from (the device text of a batch is copied into one of them; the writer thread
+  // hands it back once the bytes are in the file), kept across calls
+  static constexpr int kSinkBufs = 6;
+  char* sink_buf[kSinkBufs] = {};
+  cudaEvent_t sink_ev[kSinkBufs] = {};
+  int64_t sink_cap = 0;
 
   // optional per-kernel timing (option "profile"): event pairs around each launch of the hot path
   bool profile = false;
@@ -161,14 +260,24 @@ void free_pipeline(cgc_context* c) {
     if (s.d_dE) cudaFree(s.d_dE);
     if (s.h_dE) cudaFreeHost(s.h_dE);
     if (s.d_ttext) cudaFree(s.d_ttext);
-    if (s.h_ttext) cudaFreeHost(s.h_ttext);
     if (s.d_rowoff) cudaFree(s.d_rowoff);
     if (s.h_tinfo) cudaFreeHost(s.h_tinfo);
-    delete s.write_pending;
+    if (s.d_fmt_flag) cudaFree(s.d_fmt_flag);
     if (s.ev_copied) cudaEventDestroy(s.ev_copied);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
-    s = Slot();
+    if (s.ev_text_out) cudaEventDestroy(s.ev_text_out);
+    s.h_text = nullptr; s.d_text = nullptr; s.d_off = nullptr; s.h_off = nullptr; s.d_xyz8 = nullptr; s.d_sites = nullptr;
+    s.d_acc = nullptr; s.d_dE = nullptr; s.h_dE = nullptr; s.d_ttext = nullptr; s.d_rowoff = nullptr; s.h_tinfo = nullptr;
+    s.d_fmt_flag = nullptr; s.ttext_cap = 0; s.ev_copied = s.ev_done = s.ev_text_out = nullptr;
+    s.text_out_pending = false; s.staged_here = false; s.src = nullptr; s.nb = 0; s.frames = 0; s.out_frame = 0; s.busy = false;
   }
+  for (int i = 0; i < cgc_context::kSinkBufs; i++) {
+    if (c->sink_buf[i]) cudaFreeHost(c->sink_buf[i]);
+    if (c->sink_ev[i]) cudaEventDestroy(c->sink_ev[i]);
+    c->sink_buf[i] = nullptr;
+    c->sink_ev[i] = nullptr;
+  }
+  c->sink_cap = 0;
   c->dev_pipeline = false;
   c->alloc_batch = 0;
   c->alloc_text = 0;
@@ -200,6 +309,8 @@ void free_static(cgc_context* c) {
 }  // namespace
 
 cgc_context::~cgc_context() {
+  delete pool;
+  pool = nullptr;
   free_pipeline(this);
   free_static(this);
   if (device >= 0) {
@@ -404,12 +515,13 @@ void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_ho
     CUDA_OK(cudaHostAlloc(&s.h_off, sizeof(int64_t) * batch, cudaHostAllocDefault));
     CUDA_OK(cudaMalloc(&s.d_xyz8, sizeof(float) * 3 * (size_t)sys.n_pad * batch));
     CUDA_OK(cudaMalloc(&s.d_sites, (size_t)16 * sys.n_sites * sys.site_cap * batch));
-    CUDA_OK(cudaMalloc(&s.d_acc, sizeof(double) * sg * batch));
-    CUDA_OK(cudaMemset(s.d_acc, 0, sizeof(double) * sg * batch));
+    CUDA_OK(cudaMalloc(&s.d_acc, sizeof(long long) * sg * batch));
+    CUDA_OK(cudaMemset(s.d_acc, 0, sizeof(long long) * sg * batch));
     CUDA_OK(cudaMalloc(&s.d_dE, sizeof(float) * sg * batch));
     CUDA_OK(cudaHostAlloc(&s.h_dE, sizeof(float) * sg * batch, cudaHostAllocDefault));
     CUDA_OK(cudaEventCreateWithFlags(&s.ev_copied, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&s.ev_text_out, cudaEventDisableTiming));
     launch_init_sites(sys, s.d_sites, batch, c->st_comp);
     c->launches++;
   }
@@ -419,71 +531,122 @@ void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_ho
   c->alloc_text = text_bytes;
 }
 
+CopyPool* copy_pool(cgc_context* c) {
+  if (!c->pool) {
+    // 16 copier threads moved 68-83 GB/s from a fresh file mapping into pinned memory on the B200 box, 8 threads about half
+    // (profiles/r01_host_staging_paths.log); with several contexts in one process (one per GPU) the caller divides the
+    // cores with the "stage_threads" option
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int n = c->stage_threads > 0 ? c->stage_threads : (int)std::min(16u, hw);
+    c->pool = new CopyPool(n);
+  }
+  return c->pool;
+}
+
 // Appends byte ranges to a file from a background thread.  Every range gets its file offset when it is queued (the sizes
-// are known then) and is written with pwrite().  One thread is the default: page-cache writes ran at 3.4-5.6 GB/s from one
-// thread on the B200 box and no faster from four (they serialise on the inode), while the `.time` text of the C2 workload
-// needs 240 kB per frame — 2.6 GB/s at 11k frames/s.
+// are known then) and is written with pwrite().  One thread: page-cache writes ran at 3.4-5.6 GB/s from one thread on the
+// B200 box and no faster from four (they serialise on the inode), while the `.time` text of the C2 workload needs 240 kB
+// per frame — 2.6 GB/s at 11k frames/s.  The bytes of a batch come either from one of the context's pinned sink buffers
+// (filled by a D2H copy the writer waits for through `ready`; handed back to the free list once written) or from a
+// heap string (the host-formatted fallback).
 class TextSink {
  public:
-  explicit TextSink(int fd, int n_threads = 1) : fd_(fd) {
+  TextSink(int fd, cgc_context* c) : fd_(fd), c_(c) {
     const off_t end = lseek(fd, 0, SEEK_END);
     next_off_ = end < 0 ? 0 : (int64_t)end;
-    for (int i = 0; i < n_threads; i++) th_.emplace_back([this] { loop(); });
+    for (int i = 0; i < cgc_context::kSinkBufs; i++) free_.push_back(i);
+    th_ = std::thread([this] { loop(); });
   }
   ~TextSink() { finish(); }
-  // `done` is set to false here and to true once the bytes are written (or the sink has failed)
-  void push(const char* p, int64_t n, std::atomic<bool>* done) {
-    if (done) done->store(false);
+  // a free pinned buffer (index into cgc_context::sink_buf); waits for the writer when all of them are queued
+  int acquire() {
+    std::unique_lock<std::mutex> g(mu_);
+    free_cv_.wait(g, [this] { return !free_.empty(); });
+    const int i = free_.back();
+    free_.pop_back();
+    return i;
+  }
+  void push_buffer(int buf, int64_t n) {
     {
       std::lock_guard<std::mutex> g(mu_);
-      q_.push_back({p, n, next_off_, done});
+      q_.push_back({buf, std::string(), n, next_off_});
       next_off_ += n;
     }
     cv_.notify_one();
   }
-  static void wait(std::atomic<bool>* done) {
-    while (done && !done->load()) std::this_thread::yield();
+  void push_string(std::string&& text) {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      const int64_t n = (int64_t)text.size();
+      q_.push_back({-1, std::move(text), n, next_off_});
+      next_off_ += n;
+    }
+    cv_.notify_one();
   }
-  bool finish() {   // drains the queue, joins the threads; returns false when a write failed
+  bool finish() {   // drains the queue, joins the thread; returns false when a write failed
     {
       std::lock_guard<std::mutex> g(mu_);
       stop_ = true;
     }
     cv_.notify_all();
-    for (auto& t : th_)
-      if (t.joinable()) t.join();
+    if (th_.joinable()) th_.join();
     return ok_;
   }
 
  private:
-  struct Item { const char* p; int64_t n; int64_t off; std::atomic<bool>* done; };
+  struct Item { int buf; std::string text; int64_t n; int64_t off; };
   void loop() {
+    if (c_->device >= 0) cudaSetDevice(c_->device);
     for (;;) {
       Item it;
       {
         std::unique_lock<std::mutex> g(mu_);
         cv_.wait(g, [this] { return stop_ || !q_.empty(); });
         if (q_.empty()) return;
-        it = q_.front();
+        it = std::move(q_.front());
         q_.pop_front();
+      }
+      const char* p = it.text.data();
+      if (it.buf >= 0) {
+        if (cudaEventSynchronize(c_->sink_ev[it.buf]) != cudaSuccess) ok_ = false;   // the D2H copy into the buffer
+        p = c_->sink_buf[it.buf];
       }
       int64_t off = 0;
       while (ok_ && off < it.n) {
-        ssize_t w = pwrite(fd_, it.p + off, (size_t)(it.n - off), (off_t)(it.off + off));
+        ssize_t w = pwrite(fd_, p + off, (size_t)(it.n - off), (off_t)(it.off + off));
         if (w <= 0) ok_ = false; else off += w;
       }
-      if (it.done) it.done->store(true);
+      if (it.buf >= 0) {
+        {
+          std::lock_guard<std::mutex> g(mu_);
+          free_.push_back(it.buf);
+        }
+        free_cv_.notify_one();
+      }
     }
   }
   int fd_;
+  cgc_context* c_;
   int64_t next_off_ = 0;
   std::mutex mu_;
-  std::condition_variable cv_;
+  std::condition_variable cv_, free_cv_;
   std::deque<Item> q_;
+  std::vector<int> free_;
   bool stop_ = false;
   std::atomic<bool> ok_{true};
-  std::vector<std::thread> th_;
+  std::thread th_;
 };
+
+void ensure_sink_bufs(cgc_context* c, int64_t cap) {
+  if (c->sink_cap >= cap) return;
+  for (int i = 0; i < cgc_context::kSinkBufs; i++) {
+    if (c->sink_buf[i]) CUDA_OK(cudaFreeHost(c->sink_buf[i]));
+    c->sink_buf[i] = nullptr;
+    CUDA_OK(cudaHostAlloc(&c->sink_buf[i], (size_t)cap, cudaHostAllocDefault));
+    if (!c->sink_ev[i]) CUDA_OK(cudaEventCreateWithFlags(&c->sink_ev[i], cudaEventDisableTiming));
+  }
+  c->sink_cap = cap;
+}
 
 void ensure_time_text(cgc_context* c, int batch) {
   const int64_t rows = (int64_t)batch * c->sys.n_sites;
@@ -491,16 +654,15 @@ void ensure_time_text(cgc_context* c, int batch) {
   for (auto& s : c->slot) {
     if (s.ttext_cap >= cap) continue;
     if (s.d_ttext) CUDA_OK(cudaFree(s.d_ttext));
-    if (s.h_ttext) CUDA_OK(cudaFreeHost(s.h_ttext));
     if (s.d_rowoff) CUDA_OK(cudaFree(s.d_rowoff));
-    s.d_ttext = nullptr; s.h_ttext = nullptr; s.d_rowoff = nullptr; s.ttext_cap = 0;
+    s.d_ttext = nullptr; s.d_rowoff = nullptr; s.ttext_cap = 0;
     CUDA_OK(cudaMalloc(&s.d_ttext, (size_t)cap));
-    CUDA_OK(cudaHostAlloc(&s.h_ttext, (size_t)cap, cudaHostAllocDefault));
     CUDA_OK(cudaMalloc(&s.d_rowoff, sizeof(int64_t) * (size_t)(rows + 1)));
     if (!s.h_tinfo) CUDA_OK(cudaHostAlloc(&s.h_tinfo, sizeof(int64_t) * 2, cudaHostAllocDefault));
-    if (!s.write_pending) s.write_pending = new std::atomic<bool>(true);
+    if (!s.d_fmt_flag) CUDA_OK(cudaMalloc(&s.d_fmt_flag, sizeof(int)));
     s.ttext_cap = cap;
   }
+  ensure_sink_bufs(c, cap);
 }
 
 // "%g" of a float, as std::ostream << float prints it (precision 6)
@@ -552,27 +714,6 @@ int64_t index_upto(cgc_context* c, int64_t upto) {
     c->frames.push_back(sp);
   }
   return (int64_t)c->frames.size();
-}
-
-// Threaded memcpy.  For trajectory text the source is the read-only mmap of the file: on the B200 box 16 threads copying
-// from a fresh mapping (page faults with fault-around included) move 68-83 GB/s into pinned memory, threaded pread() of
-// the same pages 51-53 GB/s, and cudaHostRegister of a file mapping is refused (scripts/dev_hostregister.cu,
-// profiles/r01_host_staging_paths.log).
-void parallel_copy(char* dst, const char* src, int64_t n, unsigned max_threads = 8) {
-  const int64_t kMin = 8 << 20;
-  int nt = (int)std::min<int64_t>(std::max(1u, std::min(max_threads, std::thread::hardware_concurrency())), std::max<int64_t>(1, n / kMin));
-  if (nt <= 1) {
-    memcpy(dst, src, (size_t)n);
-    return;
-  }
-  std::vector<std::thread> th;
-  const int64_t chunk = ((n + nt - 1) / nt + 4095) & ~(int64_t)4095;
-  for (int i = 0; i < nt; i++) {
-    int64_t b = (int64_t)i * chunk, e = std::min(n, b + chunk);
-    if (b >= e) break;
-    th.emplace_back([=] { memcpy(dst + b, src + b, (size_t)(e - b)); });
-  }
-  for (auto& t : th) t.join();
 }
 
 cudaEvent_t take_event(cgc_context* c) {
@@ -676,7 +817,7 @@ void accumulate_rows(cgc_context* c, const float* d_dE, int n_frames, cudaStream
 
 // K1 -> K2 -> finish (-> K3) for one batch whose text is already in d_text; everything on `st`
 void enqueue_compute(cgc_context* c, const char* d_text, int64_t text_bytes, const int64_t* d_off, int n_frames,
-                     float* d_xyz8, float4* d_sites, double* d_acc, float* d_dE, bool accumulate, cudaStream_t st) {
+                     float* d_xyz8, float4* d_sites, long long* d_acc, float* d_dE, bool accumulate, cudaStream_t st) {
   const DeviceSystem& sys = c->sys;
   {
     ScopedKernelTimer t(c, 0, st);
@@ -684,7 +825,7 @@ void enqueue_compute(cgc_context* c, const char* d_text, int64_t text_bytes, con
   }
   {
     ScopedKernelTimer t(c, 1, st);
-    launch_cdc(sys, d_xyz8, d_sites, d_acc, n_frames, c->sm_count, st);
+    launch_cdc(sys, d_xyz8, d_sites, d_acc, c->d_err, n_frames, c->sm_count, st);
   }
   {
     ScopedKernelTimer t(c, 2, st);
@@ -837,7 +978,7 @@ int cgc_open(cgc_context* ctx, const char* traj_path) {
       throw ReadError("mmap of the trajectory failed");
     }
     // the mapping serves the frame-0 pass, the frame index, and the bulk text: several threads memcpy it into the pinned
-    // staging buffers (see parallel_copy)
+    // staging buffers (see CopyPool)
     ctx->text = (const char*)p;
     ctx->nbytes = sb.st_size;
     ctx->mapped = true;
@@ -987,6 +1128,13 @@ int cgc_set_option(cgc_context* ctx, const char* key, double value) {
     } else if (k == "batch_frames") {
       if (value < 1 || value > 65535) throw std::invalid_argument("batch_frames must be within 1..65535");
       ctx->batch_frames = (int)value;
+    } else if (k == "stage_threads") {
+      if (value < 1 || value > 256) throw std::invalid_argument("stage_threads must be within 1..256");
+      if ((int)value != ctx->stage_threads) {
+        delete ctx->pool;   // idle between calls
+        ctx->pool = nullptr;
+        ctx->stage_threads = (int)value;
+      }
     } else {
       throw std::invalid_argument("unknown option '" + k + "'");
     }
@@ -1000,6 +1148,7 @@ double cgc_get_option(const cgc_context* ctx, const char* key) {
   if (k == "sites") return ctx->n_sites;
   if (k == "covariance") return ctx->device >= 0 && ctx->dev_static ? (cov_enabled(ctx) ? 1 : 0) : ctx->cov_opt;
   if (k == "batch_frames") return ctx->batch_frames > 0 ? ctx->batch_frames : default_batch(ctx);
+  if (k == "stage_threads") return ctx->pool ? ctx->pool->threads() : ctx->stage_threads;
   if (k == "site_cap") return ctx->sys.site_cap;
   if (k == "n_pad") return ctx->sys.n_pad;
   return NAN;
@@ -1039,6 +1188,14 @@ namespace {
 
 // The streaming loop behind cgc_run and cgc_run_write_time.  sink != nullptr: the `.time` text of every batch is formatted
 // on the device (K5) and appended through the sink.
+//
+// Three parties work on a ring of kSlots batches:
+//   * the copier threads (CopyPool) move the text of batches b+1, b+2 from the file mapping / pageable memory into the
+//     slots' pinned staging buffers (skipped when the caller's text is already page-locked),
+//   * the device has up to kInFlight batches enqueued: H2D copy on st_copy, K1 -> K2 -> rows (-> K3, K5) on st_comp,
+//   * this thread plans batches, hands staged ones to the device and drains finished ones (rows to the caller, device text
+//     to a sink buffer by a D2H copy on st_out that the writer thread waits for).
+// It blocks only on the staging of the batch it wants to enqueue next and on the oldest batch on the device.
 int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_kcal, int64_t* frames_done, TextSink* sink) {
   if (frames_done) *frames_done = 0;
   if (!ctx) return CGC_ERR_ARG;
@@ -1047,6 +1204,7 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
   return guarded(ctx, [&]() {
     need_device(ctx);
     const DeviceSystem& sys = ctx->sys;
+    constexpr int K = cgc_context::kSlots;
     const int B = ctx->batch_frames > 0 ? ctx->batch_frames : default_batch(ctx);
     const int64_t frame_text_max = std::max<int64_t>((int64_t)sys.n_atoms * sys.line_bytes, ctx->frame_span_max) + 4096;
     // is the text already page-locked (caller-pinned memory given to cgc_open_memory)?
@@ -1059,7 +1217,18 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
     ensure_pipeline(ctx, B, frame_text_max * B, !direct);
     ensure_cov(ctx);
     if (sink) ensure_time_text(ctx, B);
-    ctx->cov_rows_pending = 0;   // non-zero only after a call that ended in an error
+    CopyPool* pool = copy_pool(ctx);
+    // a previous call that ended in an error may have left batches on the device: nothing of theirs is delivered
+    for (auto& sl : ctx->slot) {
+      if (sl.busy || sl.text_out_pending) {
+        CUDA_OK(cudaStreamSynchronize(ctx->st_copy));
+        CUDA_OK(cudaStreamSynchronize(ctx->st_comp));
+        CUDA_OK(cudaStreamSynchronize(ctx->st_out));
+      }
+      sl.busy = false;
+      sl.text_out_pending = false;
+    }
+    ctx->cov_rows_pending = 0;
     const int64_t sg = (int64_t)sys.n_sites * sys.num_tot;
     const bool want_rows = dE_kcal != nullptr || sink != nullptr;   // the text path keeps the rows for its host fallback
 
@@ -1083,57 +1252,33 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
 
     // host-side time of this call by phase, printed when CGC_TRACE is set (developer aid)
     const bool trace = getenv("CGC_TRACE") != nullptr;
-    double t_wait_gpu = 0, t_rows = 0, t_text = 0, t_stage = 0, t_enqueue = 0, t_wait_file = 0;
+    double t_wait_gpu = 0, t_rows = 0, t_text = 0, t_wait_stage = 0, t_enqueue = 0;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_call0 = now();
-    std::string fallback_text;
-    auto drain = [&](Slot& s) {
-      if (!s.busy) return;
-      double t0 = now();
-      CUDA_OK(cudaEventSynchronize(s.ev_done));
-      t_wait_gpu += now() - t0;
-      t0 = now();
-      if (dE_kcal) {
-        parallel_copy((char*)(dE_kcal + s.out_frame * sg), (const char*)s.h_dE, (int64_t)sizeof(float) * sg * s.frames);
-      }
-      t_rows += now() - t0;
-      t0 = now();
-      if (sink) {
-        const int64_t total = s.h_tinfo[0];
-        if (s.h_tinfo[1] != 0 || total < 0 || total > s.ttext_cap) {
-          // a value the device formatter does not cover (non-finite, or outside [1e-16, 1e16)): this batch on the host
-          CUDA_OK(cudaMemset(ctx->d_fmt_flags, 0, sizeof(int)));
-          format_rows(s.h_dE, 0, (int64_t)s.frames * sys.n_sites, sys.num_tot, true, fallback_text);
-          std::atomic<bool> done(false);
-          sink->push(fallback_text.data(), (int64_t)fallback_text.size(), &done);
-          TextSink::wait(&done);
-        } else {
-          // the kernels of this batch are done (ev_done); later batches keep st_comp busy, so the copy goes on its own stream
-          CUDA_OK(cudaMemcpyAsync(s.h_ttext, s.d_ttext, (size_t)total, cudaMemcpyDeviceToHost, ctx->st_out));
-          CUDA_OK(cudaStreamSynchronize(ctx->st_out));
-          sink->push(s.h_ttext, total, s.write_pending);
-        }
-      }
-      t_text += now() - t0;
-      if (frames_done) *frames_done += s.frames;
-      s.busy = false;
-    };
+    int64_t delivered = 0;   // frames whose rows / text have been handed over
 
     // crude per-frame model: host->device copy at ~45 GB/s against the pair kernel at ~0.8 of its 16 pairs/clk/SM ceiling
     const double copy_s = (double)frame_text_max / 45e9;
     const double pair_s = (double)sys.n_sites * sys.site_cap * sys.n_atoms / (0.8 * 16.0 * ctx->sm_count * 1.9e9);
     const bool ramp_down = copy_s > pair_s;
-    int64_t done = 0;
-    int which = 0;
-    bool eof = false;
-    while (done < n_frames && !eof) {
-      const int64_t f_begin = first_frame + done;
+    int64_t planned = 0;                       // frames planned so far
+    int64_t n_staged = 0, n_enq = 0, n_drained = 0;   // batches planned (+ staging started) / on the device / delivered
+    bool eof = false, stopped = false;
+
+    // plan the next batch into its slot and start its staging copy; false when there is nothing left to plan
+    auto plan_and_stage = [&]() -> bool {
+      if (eof || stopped || planned >= n_frames) return false;
+      if (ctx->stop_requested.load()) {
+        stopped = true;
+        return false;
+      }
+      const int64_t f_begin = first_frame + planned;
       // Batch size ramps up at the start of a call (the first H2D copy is not hidden behind any compute) and down at
       // its end (neither are the last batch's kernels and D2H copy): B/4, B/2, B, ..., B, then halving.
-      int want = (int)std::min<int64_t>(B, n_frames - done);
+      int want = (int)std::min<int64_t>(B, n_frames - planned);
       {
-        const int64_t min_b = std::max<int64_t>(1, B / 4), left = n_frames - done;
-        want = (int)std::min<int64_t>(want, done + min_b);
+        const int64_t min_b = std::max<int64_t>(1, B / 4), left = n_frames - planned;
+        want = (int)std::min<int64_t>(want, planned + min_b);
         // the ramp down only pays when the copies are the bottleneck (text): a compute-bound stream (.trr) would just
         // finish on small, less efficient launches
         if (ramp_down && left > min_b) want = (int)std::min<int64_t>(want, std::max<int64_t>(min_b, (left + 1) / 2));
@@ -1142,15 +1287,9 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       if (known < f_begin + want) {
         want = (int)std::max<int64_t>(0, known - f_begin);
         eof = true;
-        if (want == 0) break;
+        if (want == 0) return false;
       }
-      Slot& s = ctx->slot[which];
-      drain(s);  // the slot's previous batch must have left before its buffers are reused
-      if (sink) {   // ... and its text must be in the file before h_ttext is refilled
-        const double t0 = now();
-        TextSink::wait(s.write_pending);
-        t_wait_file += now() - t0;
-      }
+      Slot& s = ctx->slot[n_staged % K];
       const FrameSpan& fa = ctx->frames[(size_t)f_begin];
       const FrameSpan& fb = ctx->frames[(size_t)(f_begin + want - 1)];
       const int64_t b0 = fa.atoms & ~(int64_t)15;
@@ -1159,67 +1298,161 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       const int64_t nb = b1 - b0;
       if (nb > ctx->alloc_text) throw std::runtime_error("internal: batch text larger than the staging buffer");
       for (int i = 0; i < want; i++) s.h_off[i] = ctx->frames[(size_t)(f_begin + i)].atoms - b0;
-      const char* src = ctx->text + b0;
-      const double t_stage0 = now();
-      if (!direct) {
-        // page cache / pageable memory -> pinned
-        parallel_copy(s.h_text, src, nb, 16);
-        src = s.h_text;
+      s.frames = want;
+      s.out_frame = planned;
+      s.nb = nb;
+      s.staged_here = !direct;
+      if (direct) {
+        s.src = ctx->text + b0;
+      } else {
+        s.src = s.h_text;
+        pool->submit(&s.stage_job, s.h_text, ctx->text + b0, nb, ctx->mapped);   // page cache / pageable memory -> pinned
       }
-      t_stage += now() - t_stage0;
-      const double t_enq0 = now();
-      CUDA_OK(cudaMemcpyAsync(s.d_text, src, (size_t)nb, cudaMemcpyHostToDevice, ctx->st_copy));
+      planned += want;
+      n_staged++;
+      return true;
+    };
+
+    auto enqueue = [&](Slot& s) {
+      const int want = s.frames;
+      CUDA_OK(cudaMemcpyAsync(s.d_text, s.src, (size_t)s.nb, cudaMemcpyHostToDevice, ctx->st_copy));
       CUDA_OK(cudaMemcpyAsync(s.d_off, s.h_off, sizeof(int64_t) * want, cudaMemcpyHostToDevice, ctx->st_copy));
       CUDA_OK(cudaEventRecord(s.ev_copied, ctx->st_copy));
       CUDA_OK(cudaStreamWaitEvent(ctx->st_comp, s.ev_copied, 0));
-      enqueue_compute(ctx, s.d_text, nb, s.d_off, want, s.d_xyz8, s.d_sites, s.d_acc, s.d_dE, true, ctx->st_comp);
+      enqueue_compute(ctx, s.d_text, s.nb, s.d_off, want, s.d_xyz8, s.d_sites, s.d_acc, s.d_dE, true, ctx->st_comp);
       if (want_rows) {
         CUDA_OK(cudaMemcpyAsync(s.h_dE, s.d_dE, sizeof(float) * (size_t)(sg * want), cudaMemcpyDeviceToHost, ctx->st_comp));
       }
       if (sink) {
         const int64_t rows = (int64_t)want * sys.n_sites;
-        launch_format_time(s.d_dE, rows, sys.num_tot, true, s.d_rowoff, s.d_ttext, ctx->d_fmt_flags, ctx->st_comp);
+        if (s.text_out_pending) {   // the slot's previous text must have left d_ttext
+          CUDA_OK(cudaStreamWaitEvent(ctx->st_comp, s.ev_text_out, 0));
+          s.text_out_pending = false;
+        }
+        CUDA_OK(cudaMemsetAsync(s.d_fmt_flag, 0, sizeof(int), ctx->st_comp));
+        launch_format_time(s.d_dE, rows, sys.num_tot, true, s.d_rowoff, s.d_ttext, s.d_fmt_flag, ctx->st_comp);
         ctx->launches += 3;
         CUDA_OK(cudaMemcpyAsync(&s.h_tinfo[0], s.d_rowoff + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->st_comp));
         s.h_tinfo[1] = 0;
-        CUDA_OK(cudaMemcpyAsync(&s.h_tinfo[1], ctx->d_fmt_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->st_comp));
+        CUDA_OK(cudaMemcpyAsync(&s.h_tinfo[1], s.d_fmt_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->st_comp));
       }
       CUDA_OK(cudaEventRecord(s.ev_done, ctx->st_comp));
-      t_enqueue += now() - t_enq0;
-      s.frames = want;
-      s.out_frame = done;
       s.busy = true;
-      done += want;
-      which = (which + 1) % cgc_context::kSlots;
-    }
-    flush_cov_rows(ctx, ctx->st_comp);   // rows still gathered for K3
-    for (int i = 0; i < cgc_context::kSlots; i++) drain(ctx->slot[(which + i) % cgc_context::kSlots]);   // oldest first
-    CUDA_OK(cudaStreamSynchronize(ctx->st_comp));
-    if (sink) {
-      const double t0 = now();
-      for (auto& sl : ctx->slot) TextSink::wait(sl.write_pending);
-      t_wait_file += now() - t0;
+    };
+
+    auto drain = [&](Slot& s) {
+      if (!s.busy) return;
+      double t0 = now();
+      CUDA_OK(cudaEventSynchronize(s.ev_done));
+      t_wait_gpu += now() - t0;
+      t0 = now();
+      if (dE_kcal) {
+        pool->copy((char*)(dE_kcal + s.out_frame * sg), (const char*)s.h_dE, (int64_t)sizeof(float) * sg * s.frames);
+      }
+      t_rows += now() - t0;
+      t0 = now();
+      if (sink) {
+        const int64_t total = s.h_tinfo[0];
+        if (s.h_tinfo[1] != 0 || total < 0 || total > s.ttext_cap) {
+          // a value the device formatter does not cover (non-finite, or outside [1e-16, 1e16)): this batch on the host
+          std::string text;
+          format_rows(s.h_dE, 0, (int64_t)s.frames * sys.n_sites, sys.num_tot, true, text);
+          sink->push_string(std::move(text));
+        } else {
+          // the kernels of this batch are done (ev_done); later batches keep st_comp busy, so the copy goes on its own
+          // stream, and the writer thread — not this one — waits for it
+          const int b = sink->acquire();
+          CUDA_OK(cudaMemcpyAsync(ctx->sink_buf[b], s.d_ttext, (size_t)total, cudaMemcpyDeviceToHost, ctx->st_out));
+          CUDA_OK(cudaEventRecord(ctx->sink_ev[b], ctx->st_out));
+          CUDA_OK(cudaEventRecord(s.ev_text_out, ctx->st_out));
+          s.text_out_pending = true;
+          sink->push_buffer(b, total);
+        }
+      }
+      t_text += now() - t0;
+      delivered += s.frames;
+      if (frames_done) *frames_done = delivered;
+      s.busy = false;
+    };
+
+    try {
+      for (;;) {
+        while (n_staged < n_drained + K && n_staged < n_enq + cgc_context::kStageAhead + 1) {
+          if (!plan_and_stage()) break;
+        }
+        if (n_enq == n_staged) break;   // everything planned is on the device, and there is nothing left to plan
+        Slot& s = ctx->slot[n_enq % K];
+        double t0 = now();
+        if (s.staged_here) pool->wait(&s.stage_job);
+        t_wait_stage += now() - t0;
+        t0 = now();
+        enqueue(s);
+        t_enqueue += now() - t0;
+        n_enq++;
+        while (n_enq - n_drained > cgc_context::kInFlight) {
+          drain(ctx->slot[n_drained % K]);
+          n_drained++;
+        }
+      }
+      flush_cov_rows(ctx, ctx->st_comp);   // rows still gathered for K3
+      while (n_drained < n_enq) {
+        drain(ctx->slot[n_drained % K]);
+        n_drained++;
+      }
+      CUDA_OK(cudaStreamSynchronize(ctx->st_comp));
+    } catch (...) {
+      // An error while planning a later batch (malformed frame) leaves sound batches on the device whose rows are already
+      // in the Correlate sums: deliver them, so that *frames_done, the caller's rows, the `.time` text and the sums stay
+      // in step.  Whatever cannot be delivered (the device itself failed) is dropped by the next call's entry check.
+      for (int64_t b = n_enq; b < n_staged; b++) {
+        Slot& s = ctx->slot[b % K];
+        if (s.staged_here) pool->wait(&s.stage_job);   // no copier may still write into a slot the next call reuses
+      }
+      try {
+        flush_cov_rows(ctx, ctx->st_comp);
+        while (n_drained < n_enq) {
+          drain(ctx->slot[n_drained % K]);
+          n_drained++;
+        }
+        cudaStreamSynchronize(ctx->st_comp);
+      } catch (...) {
+      }
+      throw;
     }
     if (trace) {
-      fprintf(stderr, "cgc trace: %lld frames in %.1f ms | host: staging copy %.1f, enqueue %.1f, wait for GPU %.1f, rows to caller %.1f, "
-                      "text D2H+queue %.1f, wait for file %.1f ms\n", (long long)done, (now() - t_call0) * 1e3, t_stage * 1e3,
-              t_enqueue * 1e3, t_wait_gpu * 1e3, t_rows * 1e3, t_text * 1e3, t_wait_file * 1e3);
+      fprintf(stderr, "cgc trace: %lld frames in %.1f ms | host thread: wait for staging %.1f, enqueue %.1f, wait for GPU %.1f, "
+                      "rows to caller %.1f, text D2H + queue %.1f ms | %d copier threads\n", (long long)delivered,
+              (now() - t_call0) * 1e3, t_wait_stage * 1e3, t_enqueue * 1e3, t_wait_gpu * 1e3, t_rows * 1e3, t_text * 1e3,
+              pool->threads());
     }
     int flags = 0;
     CUDA_OK(cudaMemcpy(&flags, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
     if (flags) {
       CUDA_OK(cudaMemset(ctx->d_err, 0, sizeof(int)));
+      if (flags & kCdcRange) {
+        throw InputFileMalformed("a pair sum is not finite or beyond +-4e6 kcal/mol: an environment atom coincides with a "
+                                 "chromophore atom (the reference would print inf/nan here); the Correlate sums of this "
+                                 "call are not usable");
+      }
       std::string m = "device decode found malformed coordinate text:";
       if (flags & kDecBadChar) m += " unexpected character in a coordinate field;";
       if (flags & kDecBadPoint) m += " decimal point not at the column found in frame 0;";
       if (flags & kDecBadNewline) m += " atom line of a different length than in frame 0;";
       throw InputFileMalformed(m);
     }
-    return done < n_frames ? CGC_EOF : CGC_OK;
+    if (stopped) {
+      ctx->stop_requested.store(false);
+      return CGC_STOPPED;
+    }
+    return delivered < n_frames ? CGC_EOF : CGC_OK;
   });
 }
 
 }  // namespace
+
+void cgc_request_stop(cgc_context* ctx) {
+  if (ctx) ctx->stop_requested.store(true);   // one atomic store: safe to call from a signal handler
+}
 
 int cgc_run(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_kcal, int64_t* frames_done) {
   return run_impl(ctx, first_frame, n_frames, dE_kcal, frames_done, nullptr);
@@ -1234,12 +1467,12 @@ int cgc_run_write_time(cgc_context* ctx, int64_t first_frame, int64_t n_frames, 
   int rc;
   bool wrote;
   {
-    TextSink sink(fd);
+    TextSink sink(fd, ctx);
     rc = run_impl(ctx, first_frame, n_frames, dE_kcal, frames_done, &sink);
     wrote = sink.finish();
   }
   if (close(fd) != 0) wrote = false;
-  if (!wrote && (rc == CGC_OK || rc == CGC_EOF)) return fail(ctx, CGC_ERR_READ, std::string("write to ") + time_path + " failed");
+  if (!wrote && (rc == CGC_OK || rc == CGC_EOF || rc == CGC_STOPPED)) return fail(ctx, CGC_ERR_READ, std::string("write to ") + time_path + " failed");
   return rc;
 }
 
@@ -1408,6 +1641,109 @@ int cgc_cov_partials(cgc_context* ctx, double* host_out) {
     if (!ctx->d_cov) throw std::invalid_argument("no covariance sums on this context");
     CUDA_OK(cudaDeviceSynchronize());
     CUDA_OK(cudaMemcpy(host_out, ctx->d_cov, sizeof(double) * cov_doubles(ctx), cudaMemcpyDeviceToHost));
+    return CGC_OK;
+  });
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The one collective of the hot path, for several contexts living in ONE process (one host thread and one context per GPU,
+// the layout SURVEY.md section 5 names): ncclCommInitAll + ncclAllReduce(sum, double) over the partial sums.  NCCL is
+// bound at run time (dlopen), so the library carries no link-time dependency on it and a process that already holds a
+// libnccl.so.2 (torch) shares that one.
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string problem;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (!api.lib) {
+      api.problem = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "?");
+      return;
+    }
+    auto sym = [&](const char* n) {
+      void* p = dlsym(api.lib, n);
+      if (!p && api.problem.empty()) api.problem = std::string("libnccl has no symbol ") + n;
+      return p;
+    };
+    api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+  });
+  return api;
+}
+}  // namespace
+
+int cgc_cov_allreduce(cgc_context** ctxs, int n) {
+  if (!ctxs || n < 1) return CGC_ERR_ARG;
+  cgc_context* c0 = ctxs[0];
+  if (!c0) return CGC_ERR_ARG;
+  return guarded(c0, [&]() {
+    for (int i = 0; i < n; i++) {
+      cgc_context* c = ctxs[i];
+      if (!c || !c->opened || c->device < 0) throw std::invalid_argument("allreduce: every context needs an open trajectory and a device");
+      if (!c->d_cov) throw std::invalid_argument("allreduce: covariance is switched off on one of the contexts");
+      if (c->sys.n_sites != c0->sys.n_sites || c->sys.num_tot != c0->sys.num_tot) {
+        throw std::invalid_argument("allreduce: the contexts do not describe the same system (sites / columns differ)");
+      }
+      for (int j = 0; j < i; j++)
+        if (ctxs[j]->device == c->device) throw std::invalid_argument("allreduce: two contexts share a device");
+    }
+    if (n == 1) return CGC_OK;
+    NcclApi& api = nccl_api();
+    if (!api.problem.empty()) throw Unsupported(api.problem);
+    auto NCCL_OK = [&](ncclResult_t r, const char* what) {
+      if (r != ncclSuccess) throw CudaError(std::string(what) + ": " + (api.GetErrorString ? api.GetErrorString(r) : "NCCL error"));
+    };
+    const int64_t SG = (int64_t)c0->sys.n_sites * c0->sys.num_tot;
+    std::vector<int> devs((size_t)n);
+    for (int i = 0; i < n; i++) {
+      devs[(size_t)i] = ctxs[i]->device;
+      CUDA_OK(cudaSetDevice(ctxs[i]->device));
+      flush_cov_rows(ctxs[i], ctxs[i]->st_comp);
+      CUDA_OK(cudaStreamSynchronize(ctxs[i]->st_comp));
+    }
+    std::vector<ncclComm_t> comms((size_t)n, nullptr);
+    NCCL_OK(api.CommInitAll(comms.data(), n, devs.data()), "ncclCommInitAll");
+    bool failed = false;
+    std::string msg;
+    try {
+      // [ n | shift c | sum(x-c) | sum (x-c)(x-c)^T ]: the shift block is identical on every rank and stays as it is;
+      // n, and the two sum blocks (contiguous), are added — as one grouped operation
+      NCCL_OK(api.GroupStart(), "ncclGroupStart");
+      for (int i = 0; i < n; i++) {
+        double* b = ctxs[i]->d_cov;
+        NCCL_OK(api.AllReduce(b, b, 1, ncclDouble, ncclSum, comms[(size_t)i], ctxs[i]->st_comp), "ncclAllReduce");
+        NCCL_OK(api.AllReduce(b + 1 + SG, b + 1 + SG, (size_t)(SG + SG * c0->sys.num_tot), ncclDouble, ncclSum, comms[(size_t)i],
+                              ctxs[i]->st_comp), "ncclAllReduce");
+      }
+      NCCL_OK(api.GroupEnd(), "ncclGroupEnd");
+      for (int i = 0; i < n; i++) {
+        CUDA_OK(cudaSetDevice(ctxs[i]->device));
+        CUDA_OK(cudaStreamSynchronize(ctxs[i]->st_comp));
+      }
+    } catch (const std::exception& e) {
+      failed = true;
+      msg = e.what();
+    }
+    for (auto cm : comms)
+      if (cm) api.CommDestroy(cm);
+    if (failed) throw CudaError(msg);
     return CGC_OK;
   });
 }
@@ -1927,20 +2263,20 @@ int cgc_write_mtx(cgc_context* ctx, const char* path, int compat) {
     const int S = ctx->sys.n_sites, G = ctx->sys.num_tot;
     std::vector<float> m;
     if (!compat) {
-      // covariance -> float32 -> "%g" text, all on the device (K5); the host only writes the bytes.  A value the device
-      // formatter does not cover (|v| < 1e-16 and not 0, or non-finite) sends the whole matrix to the host formatter.
+      // covariance -> float32 -> "%g" text, all on the device (K5); the text leaves through the pinned sink buffers, a
+      // piece per D2H copy, while the writer thread puts the previous pieces into the file.  A value the device formatter
+      // does not cover (|v| < 1e-16 and not 0, or non-finite) sends the whole matrix to the host formatter.
       const int64_t n = (int64_t)S * G * G, rows = (int64_t)S * G, cap = format_time_capacity(rows, G);
       double *d_mean = nullptr, *d_covm = nullptr;
       float* d_m32 = nullptr;
       char* d_txt = nullptr;
       int64_t* d_off = nullptr;
-      std::vector<char> text;
       int64_t total = -1;
       int flag = 0;
+      bool wrote = true;
       cudaError_t err = cudaSuccess;
       auto ok = [&](cudaError_t e) { if (err == cudaSuccess) err = e; return e == cudaSuccess; };
       CUDA_OK(cudaDeviceSynchronize());
-      m.resize((size_t)n);
       if (ok(cudaMalloc(&d_mean, sizeof(double) * S * G)) && ok(cudaMalloc(&d_covm, sizeof(double) * n)) &&
           ok(cudaMalloc(&d_m32, sizeof(float) * n))) {
         launch_cov_finalize(ctx->d_cov, S, G, 0, d_mean, d_covm, ctx->st_comp);
@@ -1957,31 +2293,45 @@ int cgc_write_mtx(cgc_context* ctx, const char* path, int compat) {
             ok(cudaMemcpyAsync(&flag, ctx->d_fmt_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->st_comp));
             ok(cudaStreamSynchronize(ctx->st_comp));
             if (err == cudaSuccess && flag == 0 && total >= 0 && total <= cap) {
-              text.resize((size_t)total);
-              ok(cudaMemcpy(text.data(), d_txt, (size_t)total, cudaMemcpyDeviceToHost));
+              int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+              if (fd < 0) {
+                wrote = false;
+              } else {
+                try {
+                  ensure_sink_bufs(ctx, (int64_t)16 << 20);
+                  TextSink sink(fd, ctx);
+                  for (int64_t off = 0; off < total && err == cudaSuccess; off += ctx->sink_cap) {
+                    const int64_t nb = std::min<int64_t>(ctx->sink_cap, total - off);
+                    const int b = sink.acquire();
+                    ok(cudaMemcpyAsync(ctx->sink_buf[b], d_txt + off, (size_t)nb, cudaMemcpyDeviceToHost, ctx->st_out));
+                    ok(cudaEventRecord(ctx->sink_ev[b], ctx->st_out));
+                    sink.push_buffer(b, nb);
+                  }
+                  wrote = sink.finish();
+                } catch (...) {
+                  close(fd);
+                  cudaFree(d_mean); cudaFree(d_m32); cudaFree(d_txt); cudaFree(d_off);
+                  throw;
+                }
+                if (close(fd) != 0) wrote = false;
+              }
             } else {
               total = -1;
             }
           } else {
             cudaGetLastError();   // not enough device memory for the text: the host formatter takes over
           }
-          if (total < 0 && err == cudaSuccess) ok(cudaMemcpy(m.data(), d_m32, sizeof(float) * n, cudaMemcpyDeviceToHost));
+          if (total < 0 && err == cudaSuccess) {
+            m.resize((size_t)n);
+            ok(cudaMemcpy(m.data(), d_m32, sizeof(float) * n, cudaMemcpyDeviceToHost));
+          }
           if (flag) cudaMemset(ctx->d_fmt_flags, 0, sizeof(int));
         }
       }
       cudaFree(d_mean); cudaFree(d_covm); cudaFree(d_m32); cudaFree(d_txt); cudaFree(d_off);
       CUDA_OK(err);
       if (total >= 0) {
-        int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
-        if (fd < 0) throw ReadError(std::string("cannot write ") + path);
-        int64_t off = 0;
-        bool wrote = true;
-        while (off < total) {
-          ssize_t w = write(fd, text.data() + off, (size_t)(total - off));
-          if (w <= 0) { wrote = false; break; }
-          off += w;
-        }
-        if (close(fd) != 0 || !wrote) throw ReadError(std::string("cannot write ") + path);
+        if (!wrote) throw ReadError(std::string("cannot write ") + path);
         return CGC_OK;
       }
     } else {

@@ -22,11 +22,17 @@
 // has read the buffer).  There is no __syncthreads after start-up: the warps of a CTA run free.
 //
 // V_s(a) = sum_c dQ_c / r_ac is FP32 over <= P terms; everything after that is FP64: w = V * (33.2f * q_a), summed per
-// residue group.  Atoms of a group are consecutive in the file, so a thread's 8 atoms form a few runs at most:
+// residue group in a fixed order inside a thread / warp, and the per-thread / per-warp partials go into the bins as
+// FIXED-POINT 64-bit integers (units of 2^-40 kcal/mol, kCdcBinScale): integer addition is associative, so the bins —
+// and with them the float32 dE rows — are bit-identical from run to run and independent of how the launch was cut into
+// units, whatever order the atomics land in (SURVEY.md section 7 asks for a reproducible scheme; FP64 atomics are not).
+// One add is off by at most 2^-41 = 4.5e-13 kcal/mol, six orders of magnitude under the float32 rounding of the row.
+// A partial that is not finite or beyond +-4e6 kcal/mol (coincident atoms) raises kCdcRange in the error word instead
+// of wrapping around.  Atoms of a group are consecutive in the file, so a thread's 8 atoms form a few runs at most:
 //   * warp entirely inside one environment group (the solvent): each lane parks its FP64 partial in shared memory; the
 //     32 lane values of every site of the chunk are added after the chunk (4 lanes per site, 8 values each, two shuffle
 //     steps) — no shuffle tree and no dependent chain inside the site loop;
-//   * otherwise: in-thread runs, one fire-and-forget atomicAdd(double) per run (the own-site column is skipped here,
+//   * otherwise: in-thread runs, one fire-and-forget 64-bit integer reduction (RED.E.ADD.64) per run (the own-site column is skipped here,
 //     reference src/grom2atomFMO.cpp:674).  The 8 column indices are re-read from L1 here instead of living in
 //     registers across the pair loop: the loop sits at the 128-register cap, and freeing 8 was worth 0.7 % (freeing all
 //     24 epilogue registers is worth 3 %: the no-epilogue variant; re-reading 33.2f*q as well costs more than it frees).
@@ -45,6 +51,18 @@ constexpr int kCdcMinBlocks = 2;
 constexpr int kCdcMaxChunkSites = 8;   // site rows one warp reduces per chunk (4 lanes per row)
 constexpr int kCdcWarps = kTileThreads / 32;
 constexpr int kCdcRing = 4;            // site-block buffers in flight
+constexpr double kCdcBinScale = 1099511627776.0;          // 2^40: bins count units of 2^-40 kcal/mol
+constexpr double kCdcBinInvScale = 1.0 / 1099511627776.0;
+constexpr double kCdcBinLimit = 4.0e6;                    // |partial| must stay below this (2^63 / 2^40 = 8.4e6)
+
+// one partial sum -> its bin.  The conversion rounds to nearest; the range check also catches NaN.
+__device__ __forceinline__ void bin_add(long long* bin, double w, int* err_flags) {
+  if (!(fabs(w) < kCdcBinLimit)) {
+    atomicOr(err_flags, kCdcRange);
+    return;
+  }
+  atomicAdd(reinterpret_cast<unsigned long long*>(bin), (unsigned long long)__double2ll_rn(w * kCdcBinScale));
+}
 
 // sa = (-xc, -yc, -zc, dQ) of one site atom.  pack2(v, v) is folded by ptxas into the scalar-broadcast operand form of
 // the packed instruction (SASS "FADD2 R, R.F32x2.HI_LO, R.F32"), so the broadcast costs no instruction.
@@ -88,8 +106,8 @@ __host__ __device__ inline size_t cdc_smem_layout(int chunk_sites, int P, size_t
 template <int kMinBlocks, int kUnroll, int kFlags = 0>
 __global__ void __launch_bounds__(kTileThreads, kMinBlocks)
 cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, const double* __restrict__ kq_all,
-           const int32_t* __restrict__ col_all, double* __restrict__ acc, int n_pad, int tiles_per_frame,
-           long long n_units, int S, int P, int G, int chunk_sites, int chunks_per_item) {
+           const int32_t* __restrict__ col_all, long long* __restrict__ acc, int* __restrict__ err_flags, int n_pad,
+           int tiles_per_frame, long long n_units, int S, int P, int G, int chunk_sites, int chunks_per_item) {
   static_assert(kAtomsPerThread == 8, "the loads below are written for 8 atoms per thread");
   constexpr bool kBits = (kFlags & 2) != 0;
   extern __shared__ __align__(128) unsigned char sm_raw[];
@@ -143,7 +161,7 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
   unsigned run_mask = 0;              // bit e: atom e ends a run of equal, real columns; bit 8+e: atom e starts a run
   bool warp_uniform = false;
   int c_lane0 = -1;
-  double* acc_frame = acc;
+  long long* acc_frame = acc;
   long long cur_item = -1;
 
   uint32_t seq = 0;
@@ -200,12 +218,12 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
       float Vf[8];
 #pragma unroll
       for (int j = 0; j < 4; j++) unpack2(V[j], Vf[2 * j], Vf[2 * j + 1]);
-      double* acc_row = acc_frame + (size_t)s * G;
+      long long* acc_row = acc_frame + (size_t)s * G;
       if constexpr ((kFlags & 1) != 0) {
         float t = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; e++) t += Vf[e];
-        if (t == 123.456f) atomicAdd(acc_row, (double)t);
+        if (t == 123.456f) bin_add(acc_row, (double)t, err_flags);
       } else if (warp_uniform) {
         // two independent chains of four
         double t0 = f2d<kBits>(Vf[0]) * kq[0], t1 = f2d<kBits>(Vf[1]) * kq[1];
@@ -227,7 +245,7 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
           const double w = f2d<kBits>(Vf[e]) * kq[e];
           run = ((run_mask >> (8 + e)) & 1u) ? w : run + w;
           // own-site column: reference src/grom2atomFMO.cpp:674
-          if (((run_mask >> e) & 1u) && cols[e] != s) atomicAdd(acc_row + cols[e], run);
+          if (((run_mask >> e) & 1u) && cols[e] != s) bin_add(acc_row + cols[e], run, err_flags);
         }
       }
     };
@@ -303,7 +321,7 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
         }
         t += __shfl_xor_sync(0xffffffffu, t, 1);
         t += __shfl_xor_sync(0xffffffffu, t, 2);
-        if (qd == 0 && r < n_s && c_lane0 != s_begin + r) atomicAdd(acc_frame + (size_t)(s_begin + r) * G + c_lane0, t);
+        if (qd == 0 && r < n_s && c_lane0 != s_begin + r) bin_add(acc_frame + (size_t)(s_begin + r) * G + c_lane0, t, err_flags);
         __syncwarp();   // the rows are rewritten by the next chunk's epilogues
       }
     }

@@ -5,7 +5,7 @@
 //                         src/grom2atomFMO.cpp:396-455, and the per-site charge substitution of AtomDataLookup_v2, :574-609)
 //   K2  cdc_kernel        Coulomb sum dQ(site atoms) x q(all other atoms), binned per residue group
 //                         (replaces ComputeCDC_v1, reference src/grom2atomFMO.cpp:625-739)
-//   K2b finish_kernel     FP64 bins -> float32 dE rows (the reference's cdc_kcal vector)
+//   K2b finish_kernel     fixed-point bins -> float32 dE rows (the reference's cdc_kcal vector)
 //   K3  cov_* kernels     n, sum(x-c), sum (x-c)(x-c)^T per site on FP64 tensor cores (DMMA)
 //                         (replaces the Correlate block, reference src/FMOparse.cpp:168-178, 188-206)
 #include "kernels.cuh"
@@ -337,8 +337,8 @@ int cdc_pad_site_cap(int p) {
 }
 
 template <int kUnroll>
-static void launch_cdc_t(const DeviceSystem& sys, const float* xyz8, const float4* sites, double* acc, int n_frames,
-                         int sm_count, cudaStream_t st) {
+static void launch_cdc_t(const DeviceSystem& sys, const float* xyz8, const float4* sites, long long* acc, int* err_flags,
+                         int n_frames, int sm_count, cudaStream_t st) {
   const int tiles = sys.n_pad / kTileAtoms;
   auto kern = cdc_kernel<kCdcMinBlocks, kUnroll>;
   static size_t granted[16] = {};
@@ -354,31 +354,31 @@ static void launch_cdc_t(const DeviceSystem& sys, const float* xyz8, const float
   const long long n_units = (long long)tiles * n_frames * chunks_per_item;
   long long grid = (long long)sm_count * per_sm;
   if (grid > n_units) grid = n_units;
-  kern<<<(unsigned)grid, kTileThreads, smem, st>>>(xyz8, sites, sys.kq, sys.col, acc, sys.n_pad, tiles, n_units,
+  kern<<<(unsigned)grid, kTileThreads, smem, st>>>(xyz8, sites, sys.kq, sys.col, acc, err_flags, sys.n_pad, tiles, n_units,
                                                    sys.n_sites, sys.site_cap, sys.num_tot, chunk_sites, chunks_per_item);
 }
 
-void launch_cdc(const DeviceSystem& sys, const float* xyz8, const float4* sites, double* acc, int n_frames,
-                int sm_count, cudaStream_t st) {
+void launch_cdc(const DeviceSystem& sys, const float* xyz8, const float4* sites, long long* acc, int* err_flags,
+                int n_frames, int sm_count, cudaStream_t st) {
   if (sys.n_pad / kTileAtoms * n_frames == 0 || sys.n_sites == 0) return;
   // 42 site atoms per trip when that divides P - 2 (the 44 dQ atoms of a BCL), else 7 (cdc_pad_site_cap)
-  if ((sys.site_cap - 2) % 42 == 0) launch_cdc_t<42>(sys, xyz8, sites, acc, n_frames, sm_count, st);
-  else launch_cdc_t<7>(sys, xyz8, sites, acc, n_frames, sm_count, st);
+  if ((sys.site_cap - 2) % 42 == 0) launch_cdc_t<42>(sys, xyz8, sites, acc, err_flags, n_frames, sm_count, st);
+  else launch_cdc_t<7>(sys, xyz8, sites, acc, err_flags, n_frames, sm_count, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// K2b  finish: FP64 bins -> float32 dE (the reference's cdc_kcal), bins re-zeroed for the next batch
+// K2b  finish: fixed-point bins -> float32 dE (the reference's cdc_kcal), bins re-zeroed for the next batch
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void finish_kernel(double* __restrict__ acc, float* __restrict__ dE, int64_t n) {
+__global__ void finish_kernel(long long* __restrict__ acc, float* __restrict__ dE, int64_t n) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    dE[i] = (float)acc[i];
-    acc[i] = 0.0;
+    dE[i] = (float)((double)acc[i] * kCdcBinInvScale);   // exact below 2^53 units (8192 kcal/mol), then one rounding
+    acc[i] = 0;
   }
 }
 
-void launch_finish(double* acc, float* dE, int64_t n, cudaStream_t st) {
+void launch_finish(long long* acc, float* dE, int64_t n, cudaStream_t st) {
   if (n == 0) return;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;

@@ -24,9 +24,14 @@ def traj2dEcsv(traj, top, itp, out, num_frames, sites=0, mtx_compat=False, chunk
     local = int(os.environ.get("LOCAL_RANK", "0")) if device is None else device
     if not torch.cuda.is_available():
         raise RuntimeError("no CUDA device: the hot path is CUDA-only (no CPU fallback)")
+    if world > 1 and mtx_compat:
+        # the literal .mtx is built from float32 sums added frame by frame in order (reference src/FMOparse.cpp:173-175);
+        # partial sums of several ranks cannot reproduce that order, and a .mtx from one rank's sums would be wrong
+        raise capi.CgcError(capi.CGC_ERR_UNSUPPORTED, "--mtx-compat cannot be combined across ranks: run it on one GPU")
     torch.cuda.set_device(local)
     if world > 1:
         cdist.bind_to_gpu_numa(local)           # pinned staging buffers land on the GPU's own NUMA node
+        c_threads = max(2, min(16, (os.cpu_count() or 16) // world))
     if world > 1 and not tdist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         backend = os.environ.get("CGC_DIST_BACKEND", "nccl")    # "gloo" lets two test ranks share one GPU
@@ -38,6 +43,8 @@ def traj2dEcsv(traj, top, itp, out, num_frames, sites=0, mtx_compat=False, chunk
         c.open(traj)
         if sites:
             c.set_option("sites", sites)
+        if world > 1:
+            c.set_option("stage_threads", c_threads)            # the ranks share the host cores
         total = min(int(num_frames), c.frame_count())          # stops cleanly where the reference would overrun
         first, count = cdist.frame_range(rank, world, total)
         S, G = c.n_sites, c.num_tot
@@ -47,7 +54,7 @@ def traj2dEcsv(traj, top, itp, out, num_frames, sites=0, mtx_compat=False, chunk
             c.cov_bind(cov.data_ptr())
         part = out + (".time.part%d" % rank if world > 1 else ".time")
         capi.write_time(part, np.empty((0, G), np.float32), truncate=True)
-        step = chunk_frames or 16 * int(c.get_option("batch_frames"))
+        step = chunk_frames or max(1, count)                    # one call: one pipeline fill and drain
         done = 0
         while done < count:
             n = min(step, count - done)

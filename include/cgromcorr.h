@@ -30,6 +30,8 @@ typedef struct cgc_context cgc_context;
 #define CGC_OK                    0
 #define CGC_EOF                   1   /* fewer frames in the trajectory than requested; *frames_done tells how many.
                                          (The reference segfaults here, README.md:31.) */
+#define CGC_STOPPED               2   /* cgc_request_stop ended the call early; *frames_done tells how many frames were
+                                         delivered (the reference's SIGINT flag, src/FMOparse.cpp:24-29,62,68) */
 #define CGC_ERR_INPUT_MALFORMED  (-1) /* InputFileMalformed */
 #define CGC_ERR_INPUT_MINOR      (-2) /* InputFileMinorMalformed — only ever reported, never fatal (main() swallows it,
                                          src/FMOparse.cpp:358-366) */
@@ -101,6 +103,8 @@ int64_t cgc_frame_atoms_offset(cgc_context *ctx, int64_t frame);
  *                src/FMOparse.cpp:133)
  * "covariance"   0/1: accumulate n, sum(x-c), sum (x-c)(x-c)^T per site while running (default 1 when it fits)
  * "batch_frames" frames per device batch (default: sized from the frame text size)
+ * "stage_threads" host threads that copy trajectory text into the pinned staging ring (default min(16, cores); a process
+ *                that runs one context per GPU divides its cores between them)
  * "profile"      0/1: time every hot-path kernel with CUDA events (see cgc_kernel_times)
  * Must be set after cgc_open and before the first cgc_run. */
 int cgc_set_option(cgc_context *ctx, const char *key, double value);
@@ -108,10 +112,18 @@ double cgc_get_option(const cgc_context *ctx, const char *key);
 
 /* ---- the hot path -----------------------------------------------------------------------------------------------
  * cgc_run replaces the per-frame body of main_Cr (src/FMOparse.cpp:68-179): for frames [first, first+n) it streams the
- * text through pinned, ring-buffered (3 slots) H2D copies, decodes it (K1), evaluates ComputeCDC_v1 for every site (K2), and
- * accumulates the Correlate sums (K3).  dE_kcal (nullable) receives float32 [n][sites][numTot], caller-owned HOST memory.
- * Returns CGC_OK, or CGC_EOF with *frames_done < n when the trajectory ends early. */
+ * text through a ring of 4 pinned staging buffers (filled by background copier threads, two batches ahead) and H2D
+ * copies, decodes it (K1), evaluates ComputeCDC_v1 for every site (K2), and accumulates the Correlate sums (K3).
+ * dE_kcal (nullable) receives float32 [n][sites][numTot], caller-owned HOST memory.  The rows are bit-identical from run
+ * to run and for any batch size or frame range (K2 bins in fixed point).
+ * Returns CGC_OK, CGC_EOF with *frames_done < n when the trajectory ends early, or CGC_STOPPED after cgc_request_stop.
+ * On an error in the middle of the range (a malformed later frame) *frames_done, the rows delivered so far, the `.time`
+ * text and the Correlate sums all cover the same frames: the sound batches before the error. */
 int cgc_run(cgc_context *ctx, int64_t first_frame, int64_t n_frames, float *dE_kcal, int64_t *frames_done);
+/* Ask the cgc_run / cgc_run_write_time in progress on this context (or the next one) to stop after the batches already
+ * under way — the reference's SIGINT handling, "finish the current frame, then write .mtx" (src/FMOparse.cpp:24-29,62).
+ * One atomic store: callable from a signal handler or another thread. */
+void cgc_request_stop(cgc_context *ctx);
 /* cgc_run that also appends the `.time` rows of the frames it processed to `time_path` (truncate != 0 empties the file
  * first, src/FMOparse.cpp:48-50) — the text of src/FMOparse.cpp:151-165, byte for byte what cgc_write_time prints for the
  * same rows, but formatted ON THE DEVICE (K5, csrc/format_kernel.cu) and written by a background thread, so the host cores
@@ -126,7 +138,10 @@ int cgc_format_text_device(cgc_context *ctx, const float *values, int64_t rows, 
 
 /* Same computation on text that is already in DEVICE memory (d_text 16-byte aligned; atoms_offset[f] = byte offset of
  * the first atom line of frame f, HOST array).  d_dE_kcal: DEVICE float32 [n_frames][sites][numTot].  Work is enqueued
- * on `stream` (a cudaStream_t, NULL = default stream) and NOT synchronised.  n_frames must not exceed "batch_frames". */
+ * on `stream` (a cudaStream_t, NULL = default stream) and NOT synchronised.  Any n_frames >= 1 (the scratch buffers grow
+ * to the largest batch seen).  The decode kernel fetches whole 16-byte units: the allocation behind d_text must extend to
+ * the next multiple of 16 bytes after text_bytes.  cgc_run_device and cgc_decode_device share one set of scratch buffers
+ * per context: use ONE stream per context for them and do not interleave them with cgc_run. */
 int cgc_run_device(cgc_context *ctx, const void *d_text, int64_t text_bytes, const int64_t *atoms_offset,
                    int n_frames, float *d_dE_kcal, void *stream);
 
@@ -153,6 +168,15 @@ int64_t cgc_cov_size(const cgc_context *ctx);                       /* number of
 int cgc_cov_bind(cgc_context *ctx, double *d_buffer);               /* DEVICE pointer, cgc_cov_size doubles, zeroed here */
 int cgc_cov_reset(cgc_context *ctx);
 int cgc_cov_partials(cgc_context *ctx, double *host_out);           /* copy the flat buffer to HOST */
+/* The ONE collective of the hot path for a process that drives several GPUs itself (one context and one host thread per
+ * GPU, each run over its own frame range — what the reference's authors did with one process per trajectory chunk,
+ * scripts/2014-06-gro2dEcsv.sh:3-27): ncclCommInitAll over the contexts' devices and one grouped ncclAllReduce(sum,
+ * double) of n, sum(x-c) and sum (x-c)(x-c)^T; the shift block, identical everywhere, is left alone.  Afterwards every
+ * context holds the sums of all frames.  NCCL is bound at run time (libnccl.so.2): CGC_ERR_UNSUPPORTED when it cannot be
+ * loaded.  The float32 sums of the literal (compat) `.mtx` are per context and are NOT combined: their sequential order
+ * is the point of that mode.  (One process per GPU instead: all-reduce the cgc_cov_bind buffer with the caller's own
+ * communicator, cgromcorrfmo_b200/dist.py.) */
+int cgc_cov_allreduce(cgc_context **ctxs, int n);
 /* Checkpoint / resume of the Correlate state (the reference loses its accumulators when a run is killed; its `.time`
  * prefix survives because the file only grows, src/FMOparse.cpp:48-50,158-165 — SURVEY.md section 5).  The blob holds
  * the flat partial sums and the two float32 sums of the literal `.mtx`; loading it into a context opened on the same
