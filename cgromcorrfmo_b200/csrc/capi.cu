@@ -72,7 +72,7 @@ class CopyPool {
   // copied (MADV_DONTNEED on a shared file mapping keeps the page cache, it only unmaps), so that the cost of unmapping
   // gigabytes does not pile up at the end of the run.
   void submit(Job* job, char* dst, const char* src, int64_t n, bool drop_src_pages) {
-    const int64_t kChunk = 4 << 20;
+    const int64_t kChunk = 2 << 20;
     const int64_t chunks = std::max<int64_t>(1, (n + kChunk - 1) / kChunk);
     job->left.store(chunks);
     {
@@ -190,10 +190,13 @@ struct cgc_context {
   int batch_frames = 0;
 
   // pipeline
-  // batches in the ring: up to two staged ahead by the background copiers, up to two on the device (one in its H2D copy or
-  // queued, one computing) — the host thread only enqueues and drains
-  static constexpr int kSlots = 4;
-  static constexpr int kStageAhead = 2, kInFlight = 2;
+  // batches in the ring: up to three staged ahead by the background copiers, up to three on the device (H2D copy, queued,
+  // computing) — the host thread only enqueues and drains
+  static constexpr int kSlots = 6;
+  static constexpr int kStageAhead = 3, kInFlight = 3;
+  // the pinned staging buffers of slots 1.. are page-locked by a helper thread while the first batches already run
+  std::thread host_alloc_thread;
+  std::atomic<int> host_ready{0};   // slots whose h_text exists; -1: the allocation failed
   Slot slot[kSlots];
   bool dev_pipeline = false;
   int alloc_batch = 0;
@@ -247,6 +250,8 @@ void release_text(cgc_context* c) {
 }
 
 void free_pipeline(cgc_context* c) {
+  if (c->host_alloc_thread.joinable()) c->host_alloc_thread.join();
+  c->host_ready.store(0);
   if (c->device < 0) return;
   cudaSetDevice(c->device);
   for (auto& s : c->slot) {
@@ -488,10 +493,11 @@ void ensure_cov(cgc_context* c) {
 }
 
 int default_batch(const cgc_context* c) {
-  // about 192 MB of trajectory per batch: three slots of pinned staging this size cost ~0.2 s to page-lock and as much
-  // to release (512 MB slots: ~1 s, a third of a 4096-frame run), and the streaming rate no longer improves beyond it
+  // about 64 MB of trajectory per batch (C2: 14 frames = 2058 K2 work units over 296 CTAs, a 1.2 ms H2D copy): page-locking
+  // the staging ring costs time in proportion to its size (~0.3 s for 768 MB), and six slots of this size keep the copier
+  // threads, the copy engine and the kernels further apart than four large ones
   const int64_t frame_text = (int64_t)c->L.n_atoms * c->L.line_bytes + 256;
-  int64_t b = ((int64_t)192 << 20) / frame_text;
+  int64_t b = ((int64_t)64 << 20) / frame_text;
   // the FP64 bins of a batch should stay small next to the text
   const int64_t per_frame_out = (int64_t)c->sys.n_sites * c->sys.num_tot * 12;
   b = std::min<int64_t>(b, ((int64_t)2 << 30) / std::max<int64_t>(1, per_frame_out));
@@ -508,15 +514,17 @@ void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_ho
   }
   free_pipeline(c);
   const int64_t sg = (int64_t)sys.n_sites * sys.num_tot;
+  bool first = true;
   for (auto& s : c->slot) {
     CUDA_OK(cudaMalloc(&s.d_text, (size_t)text_bytes + 64));
-    if (need_host_text) CUDA_OK(cudaHostAlloc(&s.h_text, (size_t)text_bytes + 64, cudaHostAllocDefault));
+    if (need_host_text && first) CUDA_OK(cudaHostAlloc(&s.h_text, (size_t)text_bytes + 64, cudaHostAllocDefault));
+    first = false;
     CUDA_OK(cudaMalloc(&s.d_off, sizeof(int64_t) * batch));
     CUDA_OK(cudaHostAlloc(&s.h_off, sizeof(int64_t) * batch, cudaHostAllocDefault));
     CUDA_OK(cudaMalloc(&s.d_xyz8, sizeof(float) * 3 * (size_t)sys.n_pad * batch));
     CUDA_OK(cudaMalloc(&s.d_sites, (size_t)16 * sys.n_sites * sys.site_cap * batch));
     CUDA_OK(cudaMalloc(&s.d_acc, sizeof(long long) * sg * batch));
-    CUDA_OK(cudaMemset(s.d_acc, 0, sizeof(long long) * sg * batch));
+    CUDA_OK(cudaMemsetAsync(s.d_acc, 0, sizeof(long long) * sg * batch, c->st_comp));
     CUDA_OK(cudaMalloc(&s.d_dE, sizeof(float) * sg * batch));
     CUDA_OK(cudaHostAlloc(&s.h_dE, sizeof(float) * sg * batch, cudaHostAllocDefault));
     CUDA_OK(cudaEventCreateWithFlags(&s.ev_copied, cudaEventDisableTiming));
@@ -529,6 +537,24 @@ void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_ho
   c->dev_pipeline = true;
   c->alloc_batch = batch;
   c->alloc_text = text_bytes;
+  if (need_host_text) {
+    // the rest of the staging ring is page-locked while the first batches already stream (run_impl waits on host_ready)
+    c->host_ready.store(1);
+    const int dev = c->device;
+    c->host_alloc_thread = std::thread([c, dev, text_bytes] {
+      cudaSetDevice(dev);
+      for (int i = 1; i < cgc_context::kSlots; i++) {
+        if (cudaHostAlloc(&c->slot[i].h_text, (size_t)text_bytes + 64, cudaHostAllocDefault) != cudaSuccess) {
+          c->slot[i].h_text = nullptr;
+          c->host_ready.store(-1);
+          return;
+        }
+        c->host_ready.store(i + 1);
+      }
+    });
+  } else {
+    c->host_ready.store(cgc_context::kSlots);
+  }
 }
 
 CopyPool* copy_pool(cgc_context* c) {
@@ -768,13 +794,13 @@ double* centred_scratch(cgc_context* c, int n_frames) {
     if (c->d_centred) CUDA_OK(cudaFree(c->d_centred));  // synchronises: nothing in flight still reads it
     c->d_centred = nullptr;
     const int64_t want = std::max<int64_t>(n_frames, 64);
-    CUDA_OK(cudaMalloc(&c->d_centred, sizeof(double) * (size_t)want * c->sys.n_sites * c->sys.num_tot));
+    CUDA_OK(cudaMalloc(&c->d_centred, sizeof(double) * (size_t)cov_centred_doubles((int)want, c->sys.n_sites, c->sys.num_tot)));
     c->centred_frames = want;
   }
   return c->d_centred;
 }
 
-constexpr int64_t kCovGather = 128;
+constexpr int64_t kCovGather = 256;
 
 // run K3 on the gathered rows
 void flush_cov_rows(cgc_context* c, cudaStream_t st) {
@@ -783,7 +809,7 @@ void flush_cov_rows(cgc_context* c, cudaStream_t st) {
   const int n = (int)c->cov_rows_pending;
   {
     ScopedKernelTimer t(c, 3, st);
-    launch_cov_accumulate(c->d_cov_rows, n, c->d_cov, c->d_compat, centred_scratch(c, n), sys.n_sites, sys.num_tot, st);
+    CUDA_OK(launch_cov_accumulate(c->d_cov_rows, n, c->d_cov, c->d_compat, centred_scratch(c, n), sys.n_sites, sys.num_tot, st));
   }
   c->launches += 2;
   c->cov_rows_pending = 0;
@@ -795,7 +821,7 @@ void accumulate_rows(cgc_context* c, const float* d_dE, int n_frames, cudaStream
   const int64_t sg = (int64_t)sys.n_sites * sys.num_tot;
   if (n_frames >= kCovGather && c->cov_rows_pending == 0) {
     ScopedKernelTimer t(c, 3, st);
-    launch_cov_accumulate(d_dE, n_frames, c->d_cov, c->d_compat, centred_scratch(c, n_frames), sys.n_sites, sys.num_tot, st);
+    CUDA_OK(launch_cov_accumulate(d_dE, n_frames, c->d_cov, c->d_compat, centred_scratch(c, n_frames), sys.n_sites, sys.num_tot, st));
     c->launches += 2;
     return;
   }
@@ -1214,10 +1240,12 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       direct = cudaPointerGetAttributes(&at, ctx->text) == cudaSuccess && at.type == cudaMemoryTypeHost;
       cudaGetLastError();
     }
+    const double t_setup0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     ensure_pipeline(ctx, B, frame_text_max * B, !direct);
     ensure_cov(ctx);
     if (sink) ensure_time_text(ctx, B);
     CopyPool* pool = copy_pool(ctx);
+    const double t_setup = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_setup0;
     // a previous call that ended in an error may have left batches on the device: nothing of theirs is delivered
     for (auto& sl : ctx->slot) {
       if (sl.busy || sl.text_out_pending) {
@@ -1264,10 +1292,11 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
     int64_t planned = 0;                       // frames planned so far
     int64_t n_staged = 0, n_enq = 0, n_drained = 0;   // batches planned (+ staging started) / on the device / delivered
     bool eof = false, stopped = false;
+    std::exception_ptr plan_error;   // a malformed later frame: everything planned before it is still delivered
 
     // plan the next batch into its slot and start its staging copy; false when there is nothing left to plan
-    auto plan_and_stage = [&]() -> bool {
-      if (eof || stopped || planned >= n_frames) return false;
+    auto plan_and_stage_unguarded = [&]() -> bool {
+      if (eof || stopped || plan_error || planned >= n_frames) return false;
       if (ctx->stop_requested.load()) {
         stopped = true;
         return false;
@@ -1290,6 +1319,10 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
         if (want == 0) return false;
       }
       Slot& s = ctx->slot[n_staged % K];
+      if (!direct) {   // the slot's pinned staging buffer may still be on its way (first pass over the ring only)
+        while (ctx->host_ready.load() >= 0 && ctx->host_ready.load() <= (int)(n_staged % K)) std::this_thread::yield();
+        if (ctx->host_ready.load() < 0) throw CudaError("cudaHostAlloc of the pinned staging ring failed");
+      }
       const FrameSpan& fa = ctx->frames[(size_t)f_begin];
       const FrameSpan& fb = ctx->frames[(size_t)(f_begin + want - 1)];
       const int64_t b0 = fa.atoms & ~(int64_t)15;
@@ -1311,6 +1344,16 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       planned += want;
       n_staged++;
       return true;
+    };
+    auto plan_and_stage = [&]() -> bool {
+      try {
+        return plan_and_stage_unguarded();
+      } catch (const CudaError&) {
+        throw;
+      } catch (...) {
+        plan_error = std::current_exception();
+        return false;
+      }
     };
 
     auto enqueue = [&](Slot& s) {
@@ -1400,10 +1443,12 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
         n_drained++;
       }
       CUDA_OK(cudaStreamSynchronize(ctx->st_comp));
+      // A malformed frame met while planning: every batch before it has been delivered by now, so *frames_done, the
+      // caller's rows, the `.time` text and the Correlate sums all cover the same frames.
+      if (plan_error) std::rethrow_exception(plan_error);
     } catch (...) {
-      // An error while planning a later batch (malformed frame) leaves sound batches on the device whose rows are already
-      // in the Correlate sums: deliver them, so that *frames_done, the caller's rows, the `.time` text and the sums stay
-      // in step.  Whatever cannot be delivered (the device itself failed) is dropped by the next call's entry check.
+      // Deliver what is already on the device (its rows are in the Correlate sums).  Whatever cannot be delivered (the
+      // device itself failed) is dropped by the next call's entry check.
       for (int64_t b = n_enq; b < n_staged; b++) {
         Slot& s = ctx->slot[b % K];
         if (s.staged_here) pool->wait(&s.stage_job);   // no copier may still write into a slot the next call reuses
@@ -1420,17 +1465,17 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       throw;
     }
     if (trace) {
-      fprintf(stderr, "cgc trace: %lld frames in %.1f ms | host thread: wait for staging %.1f, enqueue %.1f, wait for GPU %.1f, "
-                      "rows to caller %.1f, text D2H + queue %.1f ms | %d copier threads\n", (long long)delivered,
-              (now() - t_call0) * 1e3, t_wait_stage * 1e3, t_enqueue * 1e3, t_wait_gpu * 1e3, t_rows * 1e3, t_text * 1e3,
-              pool->threads());
+      fprintf(stderr, "cgc trace: %lld frames in %.1f ms (+ %.1f ms buffer set-up) | host thread: wait for staging %.1f, enqueue %.1f, "
+                      "wait for GPU %.1f, rows to caller %.1f, text D2H + queue %.1f ms | %d frames per batch, %d copier threads\n",
+              (long long)delivered, (now() - t_call0) * 1e3, t_setup * 1e3, t_wait_stage * 1e3, t_enqueue * 1e3, t_wait_gpu * 1e3,
+              t_rows * 1e3, t_text * 1e3, B, pool->threads());
     }
     int flags = 0;
     CUDA_OK(cudaMemcpy(&flags, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
     if (flags) {
       CUDA_OK(cudaMemset(ctx->d_err, 0, sizeof(int)));
       if (flags & kCdcRange) {
-        throw InputFileMalformed("a pair sum is not finite or beyond +-4e6 kcal/mol: an environment atom coincides with a "
+        throw InputFileMalformed("a pair sum is not finite or beyond +-16384 kcal/mol: an environment atom coincides with a "
                                  "chromophore atom (the reference would print inf/nan here); the Correlate sums of this "
                                  "call are not usable");
       }
@@ -1625,8 +1670,8 @@ int cgc_cov_accumulate_device(cgc_context* ctx, const float* d_dE_kcal, int n_fr
     }
     {
       ScopedKernelTimer t(ctx, 3, st);
-      launch_cov_accumulate(d_dE_kcal, n_frames, ctx->d_cov, ctx->d_compat, centred_scratch(ctx, n_frames), ctx->sys.n_sites,
-                            ctx->sys.num_tot, st);
+      CUDA_OK(launch_cov_accumulate(d_dE_kcal, n_frames, ctx->d_cov, ctx->d_compat, centred_scratch(ctx, n_frames),
+                                    ctx->sys.n_sites, ctx->sys.num_tot, st));
     }
     ctx->launches += 2;
     CUDA_OK(cudaGetLastError());

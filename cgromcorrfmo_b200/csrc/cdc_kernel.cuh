@@ -23,12 +23,13 @@
 //
 // V_s(a) = sum_c dQ_c / r_ac is FP32 over <= P terms; everything after that is FP64: w = V * (33.2f * q_a), summed per
 // residue group in a fixed order inside a thread / warp, and the per-thread / per-warp partials go into the bins as
-// FIXED-POINT 64-bit integers (units of 2^-40 kcal/mol, kCdcBinScale): integer addition is associative, so the bins —
+// FIXED-POINT 64-bit integers (units of 2^-36 kcal/mol, kCdcBinScale): integer addition is associative, so the bins —
 // and with them the float32 dE rows — are bit-identical from run to run and independent of how the launch was cut into
 // units, whatever order the atomics land in (SURVEY.md section 7 asks for a reproducible scheme; FP64 atomics are not).
-// One add is off by at most 2^-41 = 4.5e-13 kcal/mol, six orders of magnitude under the float32 rounding of the row.
-// A partial that is not finite or beyond +-4e6 kcal/mol (coincident atoms) raises kCdcRange in the error word instead
-// of wrapping around.  Atoms of a group are consecutive in the file, so a thread's 8 atoms form a few runs at most:
+// One add is off by at most 2^-37 = 7.3e-12 kcal/mol (a bin takes a few hundred adds at most: < 1e-12 of its sum of
+// |terms|, five orders of magnitude under the float32 rounding of the row).  A partial that is not finite or beyond
+// +-16384 kcal/mol (coincident atoms; a thread's share is of order 10) raises kCdcRange in the error word instead of
+// wrapping around.  Atoms of a group are consecutive in the file, so a thread's 8 atoms form a few runs at most:
 //   * warp entirely inside one environment group (the solvent): each lane parks its FP64 partial in shared memory; the
 //     32 lane values of every site of the chunk are added after the chunk (4 lanes per site, 8 values each, two shuffle
 //     steps) — no shuffle tree and no dependent chain inside the site loop;
@@ -51,17 +52,22 @@ constexpr int kCdcMinBlocks = 2;
 constexpr int kCdcMaxChunkSites = 8;   // site rows one warp reduces per chunk (4 lanes per row)
 constexpr int kCdcWarps = kTileThreads / 32;
 constexpr int kCdcRing = 4;            // site-block buffers in flight
-constexpr double kCdcBinScale = 1099511627776.0;          // 2^40: bins count units of 2^-40 kcal/mol
-constexpr double kCdcBinInvScale = 1.0 / 1099511627776.0;
-constexpr double kCdcBinLimit = 4.0e6;                    // |partial| must stay below this (2^63 / 2^40 = 8.4e6)
+constexpr double kCdcBinScale = 68719476736.0;            // 2^36: bins count units of 2^-36 kcal/mol
+constexpr double kCdcBinInvScale = 1.0 / 68719476736.0;
+constexpr double kCdcBinLimit = 16384.0;                  // |partial| must stay below 2^51 / 2^36 = 32768 (kept at half)
 
-// one partial sum -> its bin.  The conversion rounds to nearest; the range check also catches NaN.
+// One partial sum -> its bin.  float64 -> fixed point WITHOUT a conversion instruction (F2I runs on the XU pipe, which the
+// pair loop saturates): w * 2^36 + 1.5 * 2^52 is one DFMA that leaves round-to-nearest-even(w * 2^36) in the low mantissa
+// bits, exact while |w * 2^36| < 2^51; subtracting the bit pattern of the constant recovers the integer.  The range
+// check also catches NaN and infinity.
 __device__ __forceinline__ void bin_add(long long* bin, double w, int* err_flags) {
   if (!(fabs(w) < kCdcBinLimit)) {
     atomicOr(err_flags, kCdcRange);
     return;
   }
-  atomicAdd(reinterpret_cast<unsigned long long*>(bin), (unsigned long long)__double2ll_rn(w * kCdcBinScale));
+  constexpr double kMagic = 6755399441055744.0;   // 1.5 * 2^52
+  const long long q = __double_as_longlong(fma(w, kCdcBinScale, kMagic)) - 0x4338000000000000ll;
+  atomicAdd(reinterpret_cast<unsigned long long*>(bin), (unsigned long long)q);
 }
 
 // sa = (-xc, -yc, -zc, dQ) of one site atom.  pack2(v, v) is folded by ptxas into the scalar-broadcast operand form of

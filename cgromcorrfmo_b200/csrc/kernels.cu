@@ -12,6 +12,8 @@
 #include "ptx_helpers.cuh"
 #include "cdc_kernel.cuh"
 
+#include <cuda.h>   // CUtensorMap and its enums; cuTensorMapEncodeTiled itself is bound through cudaGetDriverEntryPoint
+
 #include <algorithm>
 #include <cstdio>
 
@@ -373,7 +375,7 @@ __global__ void finish_kernel(long long* __restrict__ acc, float* __restrict__ d
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    dE[i] = (float)((double)acc[i] * kCdcBinInvScale);   // exact below 2^53 units (8192 kcal/mol), then one rounding
+    dE[i] = (float)((double)acc[i] * kCdcBinInvScale);   // exact below 2^53 units (131072 kcal/mol), then one rounding
     acc[i] = 0;
   }
 }
@@ -389,12 +391,34 @@ void launch_finish(long long* acc, float* dE, int64_t n, cudaStream_t st) {
 // K3  Correlate on FP64 tensor cores
 // ---------------------------------------------------------------------------------------------------------------------
 // buf = [ n | c (S*G) | sum (S*G) | sumsq (S*G*G) ], all double.  d_t = x_t - c.
-// sumsq_s += D_s^T D_s with D_s the (frames x G) matrix of one site: a SYRK.  The G x G result is cut into 64 x 64
-// blocks; only blocks with bi <= bj are computed (finalize mirrors them).  One CTA of 4 warps owns one block of one
-// site for the whole batch; each warp owns a 32 x 32 quarter = 4 x 4 DMMA m8n8k4 tiles (32 FP64 accumulators/thread).
-constexpr int kCovBlk = 64;
-constexpr int kCovChunk = 16;   // frames staged in shared memory per step (two stages in flight)
-constexpr int kCovLd = 68;      // row stride in doubles: 136 words == 8 (mod 32) -> conflict-free DMMA fragment loads
+// sumsq_s += D_s^T D_s with D_s the (frames x G) matrix of one site: a SYRK.  Only elements whose 64-block row is <= their
+// 64-block column are computed and stored (kCovBlk; finalize mirrors them).
+//
+// cov_sum_kernel writes the centred rows D = x - c in FP64 into a scratch matrix [frame][site][Gp], Gp = G rounded up to
+// 16 with zero pads.  cov_syrk_kernel is a persistent kernel, 2 CTAs of 4 warps per SM.  Work unit = one 128 x 64 tile of
+// one site's sumsq; a CTA takes tiles blockIdx, blockIdx + grid, ...  For every 16 frames the operands — 128 + 64 columns
+// of D — arrive in shared memory as twelve TMA tiled copies (cp.async.bulk.tensor.3d, SASS UTMALDG; box = 16 columns x 1
+// site x 16 frames = 2 KB) of a tensor map over D with 128-byte swizzle; frames beyond the batch and columns beyond Gp are
+// zero-filled by the TMA unit, so the loop has no bounds.  A ring of 4 stages with a full / empty mbarrier pair per stage
+// runs ahead across tile boundaries; one elected thread issues the copies, no CTA-wide barrier exists after start-up.
+// Each warp owns 32 x 64 of the tile = 4 x 8 DMMA m8n8k4 tiles (64 FP64 accumulators per thread): per k-step of 4 frames
+// 12 shared-memory loads feed 32 DMMAs.  The k-steps take frames {0,2,4,6}, {1,3,5,7}, {8,..}, {9,..} of the stage: with
+// the 128-byte swizzle (16-byte chunk index ^ (frame & 7)) the four rows of a fragment load then fall into four different
+// bank groups, so every LDS.64 is conflict-free.  Warps whose 32 rows lie under the diagonal 64-block, or beyond G, skip
+// the math.  The accumulators go back as fire-and-forget FP64 reductions (RED.E.ADD.F64): every element is touched by
+// exactly one thread per launch and launches are stream-ordered, so the result is deterministic.
+constexpr int kCovBlk = 64;        // granularity of the stored upper triangle
+constexpr int kSyrkBM = 128, kSyrkBN = 64;   // tile of sumsq per work unit
+constexpr int kSyrkK = 16;         // frames per stage
+constexpr int kSyrkStages = 4;
+constexpr int kSyrkBox = 16;       // columns per TMA box: 128 bytes, the swizzle span
+constexpr int kSyrkBoxBytes = kSyrkBox * kSyrkK * 8;                                   // 2048
+constexpr int kSyrkStageBytes = (kSyrkBM + kSyrkBN) / kSyrkBox * kSyrkBoxBytes;        // 24576
+constexpr int kSyrkThreads = 128;
+constexpr size_t kSyrkSmem = (size_t)kSyrkStages * kSyrkStageBytes + 1024;             // + room to align the ring to 1024 B
+
+int64_t cov_padded_cols(int G) { return ((int64_t)G + kSyrkBox - 1) / kSyrkBox * kSyrkBox; }
+int64_t cov_centred_doubles(int n_frames, int S, int G) { return (int64_t)n_frames * S * cov_padded_cols(G); }
 
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -412,124 +436,223 @@ void launch_cov_set_shift(const float* dE_row0, double* buf, int S, int G, cudaS
   cov_set_shift_kernel<<<(n + 255) / 256, 256, 0, st>>>(dE_row0, buf, n);
 }
 
-// cov_sum_kernel: n, sum(x-c), the centred rows D = x - c in FP64 (scratch, consumed by the SYRK), and the two float32
-// running sums the reference's literal .mtx arithmetic needs (src/FMOparse.cpp:173-175 with the zero stride of :193,202):
-// sum_t x_i and sum_t x_0 x_j, added frame by frame in order like the reference does.
-__global__ void cov_sum_kernel(const float* __restrict__ dE, int n_frames, double* __restrict__ buf, int SG, int G,
+// cov_sum_kernel: n, sum(x-c), the centred rows D = x - c in FP64 (scratch [frame][site][Gp], consumed by the SYRK; the pad
+// columns are written as zeros), and the two float32 running sums the reference's literal .mtx arithmetic needs
+// (src/FMOparse.cpp:173-175 with the zero stride of :193,202): sum_t x_i and sum_t x_0 x_j, added frame by frame in order
+// like the reference does.
+__global__ void cov_sum_kernel(const float* __restrict__ dE, int n_frames, double* __restrict__ buf, int S, int G, int Gp,
                                float* __restrict__ compat /* [2][SG] or null */, double* __restrict__ centred) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) buf[0] += (double)n_frames;
-  if (i >= SG) return;
+  const int ip = blockIdx.x * blockDim.x + threadIdx.x;   // index into the padded row
+  if (ip == 0) buf[0] += (double)n_frames;
+  const int SGp = S * Gp, SG = S * G;
+  if (ip >= SGp) return;
+  const int s = ip / Gp, g = ip - s * Gp;
+  if (g >= G) {
+    for (int t = 0; t < n_frames; t++) centred[(size_t)t * SGp + ip] = 0.0;
+    return;
+  }
+  const int i = s * G + g;
   const double c = buf[1 + i];
-  double s = 0.0;
-  const int i0 = (i / G) * G;  // column 0 of this site
+  double sum = 0.0;
+  const int i0 = s * G;  // column 0 of this site
   float m32 = compat ? compat[i] : 0.f, p32 = compat ? compat[SG + i] : 0.f;
   for (int t = 0; t < n_frames; t++) {
     const float x = dE[(size_t)t * SG + i];
     const double d = (double)x - c;
-    centred[(size_t)t * SG + i] = d;
-    s += d;
+    centred[(size_t)t * SGp + ip] = d;
+    sum += d;
     m32 += x;
     p32 += __fmul_rn(dE[(size_t)t * SG + i0], x);
   }
-  buf[1 + SG + i] += s;
+  buf[1 + SG + i] += sum;
   if (compat) { compat[i] = m32; compat[SG + i] = p32; }
 }
 
-__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc, bool valid) {
-  const int n = valid ? 8 : 0;   // src-size 0 -> the 8 bytes are zero-filled
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_addr(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+// one box of the tensor map -> shared memory; coordinates (column, site, frame)
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(smem_addr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(bar))
+               : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// sumsq_s += D_s^T D_s.  D (FP64, centred) is staged with cp.async (LDGSTS) into a double-buffered shared-memory tile:
-// the copy of chunk k+1 runs under the DMMAs of chunk k.
-__global__ void __launch_bounds__(128)
-cov_syrk_kernel(const double* __restrict__ D, int n_frames, double* __restrict__ buf, int S, int G, int nblk) {
-  __shared__ __align__(16) double Ai[2][kCovChunk][kCovLd];
-  __shared__ __align__(16) double Aj[2][kCovChunk][kCovLd];
-  // upper-triangular block index -> (bi, bj)
-  int b = blockIdx.x, bi = 0;
-  while (b >= nblk - bi) { b -= nblk - bi; bi++; }
-  const int bj = bi + b;
-  const int s = blockIdx.y;
-  const int SG = S * G;
-  double* sumsq = buf + 1 + 2 * (size_t)SG + (size_t)s * G * G;
+__global__ void __launch_bounds__(kSyrkThreads, 2)
+cov_syrk_kernel(const __grid_constant__ CUtensorMap dmap, int n_frames, double* __restrict__ buf, int S, int G,
+                int tiles_per_site, int n_tiles) {
+  extern __shared__ unsigned char syrk_smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kSyrkStages], empty_bar[kSyrkStages];
+  unsigned char* ring = syrk_smem_raw + ((1024u - (smem_addr(syrk_smem_raw) & 1023u)) & 1023u);   // the swizzle wants 1024 B
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wi = (warp >> 1) * 32, wj = (warp & 1) * 32;  // this warp's quarter of the block
   const int gid = lane >> 2, tig = lane & 3;
-  double acc[4][4][2];
+  if (threadIdx.x == 0) {
 #pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  auto stage = [&](int buf_i, int t0) {
-    for (int idx = threadIdx.x; idx < kCovChunk * kCovBlk; idx += 128) {
-      const int k = idx / kCovBlk, cidx = idx - k * kCovBlk;
-      const int t = t0 + k;
-      const int gi = bi * kCovBlk + cidx, gj = bj * kCovBlk + cidx;
-      const double* row = D + (size_t)(t < n_frames ? t : 0) * SG + (size_t)s * G;
-      cp_async_8(&Ai[buf_i][k][cidx], row + (gi < G ? gi : 0), t < n_frames && gi < G);
-      cp_async_8(&Aj[buf_i][k][cidx], row + (gj < G ? gj : 0), t < n_frames && gj < G);
+    for (int i = 0; i < kSyrkStages; i++) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], kSyrkThreads / 32);
     }
-    cp_async_commit();
-  };
-
-  const int n_chunks = (n_frames + kCovChunk - 1) / kCovChunk;
-  stage(0, 0);
-  for (int ch = 0; ch < n_chunks; ch++) {
-    const int cb = ch & 1;
-    if (ch + 1 < n_chunks) {
-      stage(cb ^ 1, (ch + 1) * kCovChunk);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k0 = 0; k0 < kCovChunk; k0 += 4) {
-      double a[4], bb[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) a[i] = Ai[cb][k0 + tig][wi + i * 8 + gid];
-#pragma unroll
-      for (int j = 0; j < 4; j++) bb[j] = Aj[cb][k0 + tig][wj + j * 8 + gid];
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
-    }
-    __syncthreads();  // the tile is free before the copy two chunks ahead overwrites it
+    mbar_fence_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&dmap) : "memory");
   }
-  // sumsq += acc as fire-and-forget reductions (RED.E.ADD.F64): the adds happen in L2 and the warp does not wait for
-  // them.  Every element is touched by exactly one thread per launch and launches are stream-ordered, so the result is
-  // deterministic.  The first version loaded, added and stored: ncu's source view showed 65 % of the kernel's stall
-  // samples on those dependent round trips, i.e. a CTA spent most of its life in this epilogue and the DMMA pipe was
-  // fed by fewer than two of the five resident CTAs (60 % pipe utilisation).
+  __syncthreads();
+
+  const int nb64 = (G + kCovBlk - 1) / kCovBlk;
+  const int k_stages = (n_frames + kSyrkK - 1) / kSyrkK;
+  const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const long long total = (long long)my_tiles * k_stages;   // stages this CTA consumes
+  if (total == 0) return;
+  auto decode_tile = [&](int tile, int& s, int& r0, int& c0) {   // tile -> site, first row, first column
+    s = tile / tiles_per_site;
+    int t = tile - s * tiles_per_site, bi = 0;
+    while (t >= nb64 - 2 * bi) { t -= nb64 - 2 * bi; bi++; }
+    r0 = bi * kSyrkBM;
+    c0 = (2 * bi + t) * kSyrkBN;
+  };
+  // producer (thread 0): stage n of this CTA's sequence
+  auto issue = [&](long long n) {
+    const int local_tile = (int)(n / k_stages);
+    const int ks = (int)(n - (long long)local_tile * k_stages);
+    int s, r0, c0;
+    decode_tile((int)blockIdx.x + local_tile * (int)gridDim.x, s, r0, c0);
+    const int st = (int)(n % kSyrkStages);
+    unsigned char* dst = ring + (size_t)st * kSyrkStageBytes;
+    mbar_expect_tx(&full_bar[st], kSyrkStageBytes);
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int r = bi * kCovBlk + wi + i * 8 + gid;
-    if (r >= G) continue;
-    double* row = sumsq + (size_t)r * G;
+    for (int j = 0; j < kSyrkBM / kSyrkBox; j++) tma_load_3d(dst + j * kSyrkBoxBytes, &dmap, r0 + j * kSyrkBox, s, ks * kSyrkK, &full_bar[st]);
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int c = bj * kCovBlk + wj + j * 8 + tig * 2;
-      if (c < G) atomicAdd(row + c, acc[i][j][0]);
-      if (c + 1 < G) atomicAdd(row + c + 1, acc[i][j][1]);
+    for (int j = 0; j < kSyrkBN / kSyrkBox; j++)
+      tma_load_3d(dst + (kSyrkBM / kSyrkBox + j) * kSyrkBoxBytes, &dmap, c0 + j * kSyrkBox, s, ks * kSyrkK, &full_bar[st]);
+  };
+  if (threadIdx.x == 0) {
+    for (long long n = 0; n < kSyrkStages - 1 && n < total; n++) issue(n);
+  }
+
+  // per-thread part of a fragment address inside a box: row (p + 2 tig) of the k-step with parity p, the swizzled 16-byte
+  // chunk of column 8 e + gid (e = low bit of the 8-column tile index), and the half of the chunk
+  uint32_t t_off[2][2];
+#pragma unroll
+  for (int p = 0; p < 2; p++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int row = p + 2 * tig;
+      const int chunk = (4 * e + (gid >> 1)) ^ (row & 7);
+      t_off[p][e] = (uint32_t)(row * 128 + chunk * 16 + (gid & 1) * 8);
+    }
+  const uint32_t ring_addr = smem_addr(ring);
+
+  double acc[4][8][2];
+  int s = 0, r0 = 0, c0 = 0;
+  bool active = false;
+  long long n = 0;
+  for (int lt = 0; lt < my_tiles; lt++) {
+    decode_tile((int)blockIdx.x + lt * (int)gridDim.x, s, r0, c0);
+    const int wr0 = r0 + 32 * warp;
+    // this warp's 32 rows: inside G, and not below the diagonal 64-block
+    active = wr0 < G && (wr0 / kCovBlk) <= (c0 / kCovBlk);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int ks = 0; ks < k_stages; ks++, n++) {
+      if (threadIdx.x == 0) {
+        const long long nxt = n + kSyrkStages - 1;
+        if (nxt < total) {
+          if (nxt >= kSyrkStages) mbar_wait(&empty_bar[nxt % kSyrkStages], (uint32_t)((nxt / kSyrkStages - 1) & 1));
+          issue(nxt);
+        }
+      }
+      __syncwarp();
+      const int st = (int)(n % kSyrkStages);
+      mbar_wait(&full_bar[st], (uint32_t)((n / kSyrkStages) & 1));
+      if (active) {
+        const uint32_t a_base = ring_addr + (uint32_t)st * kSyrkStageBytes + (uint32_t)warp * 2 * kSyrkBoxBytes;
+        const uint32_t b_base = ring_addr + (uint32_t)st * kSyrkStageBytes + (kSyrkBM / kSyrkBox) * kSyrkBoxBytes;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          double a[4], b[8];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const uint32_t ad = a_base + (i >> 1) * kSyrkBoxBytes + (q >> 1) * 1024 + t_off[q & 1][i & 1];
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[i]) : "r"(ad));
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const uint32_t ad = b_base + (j >> 1) * kSyrkBoxBytes + (q >> 1) * 1024 + t_off[q & 1][j & 1];
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b[j]) : "r"(ad));
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+      }
+      // every read of the stage is done (the values are in registers): hand it back to the producer
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[st]);
+    }
+    if (active) {
+      double* sumsq = buf + 1 + 2 * (size_t)S * G + (size_t)s * G * G;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int r = wr0 + i * 8 + gid;
+        if (r >= G) continue;
+        double* row = sumsq + (size_t)r * G;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int c = c0 + j * 8 + tig * 2;
+          if (c < G) atomicAdd(row + c, acc[i][j][0]);
+          if (c + 1 < G) atomicAdd(row + c + 1, acc[i][j][1]);
+        }
+      }
     }
   }
 }
 
-void launch_cov_accumulate(const float* dE, int n_frames, double* buf, float* compat, double* centred_scratch, int S,
-                           int G, cudaStream_t st) {
-  if (n_frames <= 0) return;
-  const int SG = S * G;
-  const int nblk = (G + kCovBlk - 1) / kCovBlk;
-  cov_sum_kernel<<<(SG + 255) / 256, 256, 0, st>>>(dE, n_frames, buf, SG, G, compat, centred_scratch);
-  dim3 grid(nblk * (nblk + 1) / 2, S);
-  cov_syrk_kernel<<<grid, 128, 0, st>>>(centred_scratch, n_frames, buf, S, G, nblk);
+// cuTensorMapEncodeTiled, bound through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess) {
+      p = nullptr;
+    }
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+cudaError_t launch_cov_accumulate(const float* dE, int n_frames, double* buf, float* compat, double* centred_scratch, int S,
+                                  int G, cudaStream_t st) {
+  if (n_frames <= 0) return cudaSuccess;
+  const int Gp = (int)cov_padded_cols(G);
+  cov_sum_kernel<<<(S * Gp + 255) / 256, 256, 0, st>>>(dE, n_frames, buf, S, G, Gp, compat, centred_scratch);
+  // tensor map over D [frame][site][Gp] (innermost first), box = 16 columns x 1 site x 16 frames, 128-byte swizzle,
+  // out-of-range elements read as zero
+  EncodeTiledFn encode = encode_tiled_fn();
+  if (!encode) return cudaErrorNotSupported;
+  CUtensorMap map;
+  const cuuint64_t dims[3] = {(cuuint64_t)Gp, (cuuint64_t)S, (cuuint64_t)n_frames};
+  const cuuint64_t strides[2] = {(cuuint64_t)Gp * 8, (cuuint64_t)S * Gp * 8};
+  const cuuint32_t box[3] = {(cuuint32_t)kSyrkBox, 1, (cuuint32_t)kSyrkK};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, centred_scratch, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+    return cudaErrorInvalidValue;
+  }
+  const int nb64 = (G + kCovBlk - 1) / kCovBlk, nb128 = (G + kSyrkBM - 1) / kSyrkBM;
+  int tiles_per_site = 0;
+  for (int bi = 0; bi < nb128; bi++) tiles_per_site += std::max(0, nb64 - 2 * bi);
+  const int n_tiles = tiles_per_site * S;
+  static size_t granted[16] = {};
+  ensure_dynamic_smem(cov_syrk_kernel, kSyrkSmem, granted);
+  int dev = 0, sm_count = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = std::min(n_tiles, 2 * sm_count);
+  cov_syrk_kernel<<<grid, kSyrkThreads, kSyrkSmem, st>>>(map, n_frames, buf, S, G, tiles_per_site, n_tiles);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -545,6 +668,14 @@ __global__ void centre_rows_kernel(const float* __restrict__ x, const double* __
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) d[i] = (double)x[i] - mean[i % SG];
 }
+
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc, bool valid) {
+  const int n = valid ? 8 : 0;   // src-size 0 -> the 8 bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_addr(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 constexpr int kPrjBlk = 64;    // tile edge (frames and modes)
 constexpr int kPrjK = 16;      // columns of G per stage

@@ -18,7 +18,7 @@ enum : int {
   kDecBadChar = 1,      // a coordinate field holds something other than [ -.0-9]
   kDecBadPoint = 2,     // the decimal point is not where the frame-0 layout says
   kDecBadNewline = 4,   // an atom line does not end where the frame-0 layout says
-  kCdcRange = 8,        // K2: a partial pair sum was not finite or beyond +-4e6 kcal/mol (coincident atoms)
+  kCdcRange = 8,        // K2: a partial pair sum was not finite or beyond +-16384 kcal/mol (coincident atoms)
 };
 
 struct DeviceSystem {
@@ -46,9 +46,9 @@ void launch_unblock(const DeviceSystem& sys, const float* xyz8, float* xyz, int 
 // fill every slot of the per-frame site blocks with the neutral padding entry
 void launch_init_sites(const DeviceSystem& sys, float4* sites, int n_frames, cudaStream_t st);
 
-// K2: CDC pair sums.  acc: fixed-point bins, int64 [n_frames][n_sites][num_tot] in units of 2^-40 kcal/mol, zero on entry
+// K2: CDC pair sums.  acc: fixed-point bins, int64 [n_frames][n_sites][num_tot] in units of 2^-36 kcal/mol, zero on entry
 // (integer adds: bit-reproducible whatever the order of the atomics).  err_flags |= kCdcRange when a partial sum does not
-// fit (non-finite, or beyond +-4e6 kcal/mol).
+// fit (non-finite, or beyond +-16384 kcal/mol).
 void launch_cdc(const DeviceSystem& sys, const float* xyz8, const float4* sites, long long* acc, int* err_flags,
                 int n_frames, int sm_count, cudaStream_t st);
 size_t cdc_smem_bytes(const DeviceSystem& sys);
@@ -59,9 +59,12 @@ void launch_finish(long long* acc, float* dE, int64_t n, cudaStream_t st);
 
 // K3: per-site shifted sums.  buf = [ n | c (S*G) | sum (S*G) | sumsq (S*G*G) ]
 void launch_cov_set_shift(const float* dE_row0, double* buf, int S, int G, cudaStream_t st);
-// centred_scratch: n_frames * S * G doubles (the centred rows the SYRK consumes)
-void launch_cov_accumulate(const float* dE, int n_frames, double* buf, float* compat /* float32 [2][S*G] or null */,
-                           double* centred_scratch, int S, int G, cudaStream_t st);
+// centred_scratch: cov_centred_doubles(n_frames, S, G) doubles (the centred rows the SYRK consumes, columns padded to 16).
+// Returns an error when the TMA tensor map cannot be built (driver entry point missing).
+int64_t cov_padded_cols(int G);
+int64_t cov_centred_doubles(int n_frames, int S, int G);
+cudaError_t launch_cov_accumulate(const float* dE, int n_frames, double* buf, float* compat /* float32 [2][S*G] or null */,
+                                  double* centred_scratch, int S, int G, cudaStream_t st);
 // K4: out[t][s][m] = sum_g (x[t][s][g] - mean[s][g]) * modes[s][m][g]  (all DEVICE; centred: n_frames*S*G doubles scratch)
 void launch_project(const float* x, int n_frames, const double* mean, const double* modes, int n_modes, double* centred,
                     double* out, int S, int G, cudaStream_t st);
