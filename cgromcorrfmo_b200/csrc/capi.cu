@@ -136,7 +136,7 @@ struct Slot {
   int64_t* h_off = nullptr;  // pinned
   float* d_xyz8 = nullptr;
   float4* d_sites = nullptr;
-  long long* d_acc = nullptr;   // K2's fixed-point bins
+  double* d_acc = nullptr;   // K2's bins
   float* d_dE = nullptr;
   float* h_dE = nullptr;     // pinned
   // `.time` text of the batch, formatted on the device (cgc_run_write_time); allocated on first use
@@ -493,11 +493,11 @@ void ensure_cov(cgc_context* c) {
 }
 
 int default_batch(const cgc_context* c) {
-  // about 64 MB of trajectory per batch (C2: 14 frames = 2058 K2 work units over 296 CTAs, a 1.2 ms H2D copy): page-locking
-  // the staging ring costs time in proportion to its size (~0.3 s for 768 MB), and six slots of this size keep the copier
-  // threads, the copy engine and the kernels further apart than four large ones
+  // about 128 MB of trajectory per batch (C2: 29 frames = 4263 K2 work units over 296 CTAs, a 2.4 ms H2D copy).  Measured
+  // on the B200 box (2048 C2 frames from a file in the page cache): 192 MB x 4 slots 234 ms, 64 MB x 6 slots 324 ms — each
+  // batch costs the host thread a fixed ~0.3 ms of enqueueing and two synchronisations
   const int64_t frame_text = (int64_t)c->L.n_atoms * c->L.line_bytes + 256;
-  int64_t b = ((int64_t)64 << 20) / frame_text;
+  int64_t b = ((int64_t)128 << 20) / frame_text;
   // the FP64 bins of a batch should stay small next to the text
   const int64_t per_frame_out = (int64_t)c->sys.n_sites * c->sys.num_tot * 12;
   b = std::min<int64_t>(b, ((int64_t)2 << 30) / std::max<int64_t>(1, per_frame_out));
@@ -523,8 +523,8 @@ void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_ho
     CUDA_OK(cudaHostAlloc(&s.h_off, sizeof(int64_t) * batch, cudaHostAllocDefault));
     CUDA_OK(cudaMalloc(&s.d_xyz8, sizeof(float) * 3 * (size_t)sys.n_pad * batch));
     CUDA_OK(cudaMalloc(&s.d_sites, (size_t)16 * sys.n_sites * sys.site_cap * batch));
-    CUDA_OK(cudaMalloc(&s.d_acc, sizeof(long long) * sg * batch));
-    CUDA_OK(cudaMemsetAsync(s.d_acc, 0, sizeof(long long) * sg * batch, c->st_comp));
+    CUDA_OK(cudaMalloc(&s.d_acc, sizeof(double) * sg * batch));
+    CUDA_OK(cudaMemsetAsync(s.d_acc, 0, sizeof(double) * sg * batch, c->st_comp));
     CUDA_OK(cudaMalloc(&s.d_dE, sizeof(float) * sg * batch));
     CUDA_OK(cudaHostAlloc(&s.h_dE, sizeof(float) * sg * batch, cudaHostAllocDefault));
     CUDA_OK(cudaEventCreateWithFlags(&s.ev_copied, cudaEventDisableTiming));
@@ -563,7 +563,7 @@ CopyPool* copy_pool(cgc_context* c) {
     // (profiles/r01_host_staging_paths.log); with several contexts in one process (one per GPU) the caller divides the
     // cores with the "stage_threads" option
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const int n = c->stage_threads > 0 ? c->stage_threads : (int)std::min(16u, hw);
+    const int n = c->stage_threads > 0 ? c->stage_threads : (int)std::max(1u, std::min(16u, hw > 4 ? hw - 2 : hw));   // two cores stay free for this thread and the writer
     c->pool = new CopyPool(n);
   }
   return c->pool;
@@ -843,7 +843,7 @@ void accumulate_rows(cgc_context* c, const float* d_dE, int n_frames, cudaStream
 
 // K1 -> K2 -> finish (-> K3) for one batch whose text is already in d_text; everything on `st`
 void enqueue_compute(cgc_context* c, const char* d_text, int64_t text_bytes, const int64_t* d_off, int n_frames,
-                     float* d_xyz8, float4* d_sites, long long* d_acc, float* d_dE, bool accumulate, cudaStream_t st) {
+                     float* d_xyz8, float4* d_sites, double* d_acc, float* d_dE, bool accumulate, cudaStream_t st) {
   const DeviceSystem& sys = c->sys;
   {
     ScopedKernelTimer t(c, 0, st);
@@ -851,7 +851,7 @@ void enqueue_compute(cgc_context* c, const char* d_text, int64_t text_bytes, con
   }
   {
     ScopedKernelTimer t(c, 1, st);
-    launch_cdc(sys, d_xyz8, d_sites, d_acc, c->d_err, n_frames, c->sm_count, st);
+    launch_cdc(sys, d_xyz8, d_sites, d_acc, n_frames, c->sm_count, st);
   }
   {
     ScopedKernelTimer t(c, 2, st);
@@ -1474,11 +1474,6 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
     CUDA_OK(cudaMemcpy(&flags, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
     if (flags) {
       CUDA_OK(cudaMemset(ctx->d_err, 0, sizeof(int)));
-      if (flags & kCdcRange) {
-        throw InputFileMalformed("a pair sum is not finite or beyond +-16384 kcal/mol: an environment atom coincides with a "
-                                 "chromophore atom (the reference would print inf/nan here); the Correlate sums of this "
-                                 "call are not usable");
-      }
       std::string m = "device decode found malformed coordinate text:";
       if (flags & kDecBadChar) m += " unexpected character in a coordinate field;";
       if (flags & kDecBadPoint) m += " decimal point not at the column found in frame 0;";

@@ -22,18 +22,14 @@
 // has read the buffer).  There is no __syncthreads after start-up: the warps of a CTA run free.
 //
 // V_s(a) = sum_c dQ_c / r_ac is FP32 over <= P terms; everything after that is FP64: w = V * (33.2f * q_a), summed per
-// residue group in a fixed order inside a thread / warp, and the per-thread / per-warp partials go into the bins as
-// FIXED-POINT 64-bit integers (units of 2^-36 kcal/mol, kCdcBinScale): integer addition is associative, so the bins —
-// and with them the float32 dE rows — are bit-identical from run to run and independent of how the launch was cut into
-// units, whatever order the atomics land in (SURVEY.md section 7 asks for a reproducible scheme; FP64 atomics are not).
-// One add is off by at most 2^-37 = 7.3e-12 kcal/mol (a bin takes a few hundred adds at most: < 1e-12 of its sum of
-// |terms|, five orders of magnitude under the float32 rounding of the row).  A partial that is not finite or beyond
-// +-16384 kcal/mol (coincident atoms; a thread's share is of order 10) raises kCdcRange in the error word instead of
-// wrapping around.  Atoms of a group are consecutive in the file, so a thread's 8 atoms form a few runs at most:
+// residue group in a fixed order inside a thread / warp; the per-thread / per-warp partials are rounded to a fixed grid of
+// 2^-36 kcal/mol before they are added to the FP64 bins, which makes those adds exact and therefore order-independent
+// (bin_add below): the rows are bit-reproducible although the bins are filled by atomics (SURVEY.md section 7 asks for a
+// reproducible scheme).  Atoms of a group are consecutive in the file, so a thread's 8 atoms form a few runs at most:
 //   * warp entirely inside one environment group (the solvent): each lane parks its FP64 partial in shared memory; the
 //     32 lane values of every site of the chunk are added after the chunk (4 lanes per site, 8 values each, two shuffle
 //     steps) — no shuffle tree and no dependent chain inside the site loop;
-//   * otherwise: in-thread runs, one fire-and-forget 64-bit integer reduction (RED.E.ADD.64) per run (the own-site column is skipped here,
+//   * otherwise: in-thread runs, one fire-and-forget grid-rounded FP64 reduction (RED.E.ADD.F64) per run (the own-site column is skipped here,
 //     reference src/grom2atomFMO.cpp:674).  The 8 column indices are re-read from L1 here instead of living in
 //     registers across the pair loop: the loop sits at the 128-register cap, and freeing 8 was worth 0.7 % (freeing all
 //     24 epilogue registers is worth 3 %: the no-epilogue variant; re-reading 33.2f*q as well costs more than it frees).
@@ -52,22 +48,19 @@ constexpr int kCdcMinBlocks = 2;
 constexpr int kCdcMaxChunkSites = 8;   // site rows one warp reduces per chunk (4 lanes per row)
 constexpr int kCdcWarps = kTileThreads / 32;
 constexpr int kCdcRing = 4;            // site-block buffers in flight
-constexpr double kCdcBinScale = 68719476736.0;            // 2^36: bins count units of 2^-36 kcal/mol
-constexpr double kCdcBinInvScale = 1.0 / 68719476736.0;
-constexpr double kCdcBinLimit = 16384.0;                  // |partial| must stay below 2^51 / 2^36 = 32768 (kept at half)
+constexpr double kCdcBinGridShift = 98304.0;   // 1.5 * 2^16: adding it puts the unit in the last place at 2^-36
 
-// One partial sum -> its bin.  float64 -> fixed point WITHOUT a conversion instruction (F2I runs on the XU pipe, which the
-// pair loop saturates): w * 2^36 + 1.5 * 2^52 is one DFMA that leaves round-to-nearest-even(w * 2^36) in the low mantissa
-// bits, exact while |w * 2^36| < 2^51; subtracting the bit pattern of the constant recovers the integer.  The range
-// check also catches NaN and infinity.
-__device__ __forceinline__ void bin_add(long long* bin, double w, int* err_flags) {
-  if (!(fabs(w) < kCdcBinLimit)) {
-    atomicOr(err_flags, kCdcRange);
-    return;
-  }
-  constexpr double kMagic = 6755399441055744.0;   // 1.5 * 2^52
-  const long long q = __double_as_longlong(fma(w, kCdcBinScale, kMagic)) - 0x4338000000000000ll;
-  atomicAdd(reinterpret_cast<unsigned long long*>(bin), (unsigned long long)q);
+// One partial sum -> its bin, reproducibly.  The partial is first rounded to a multiple of 2^-36 kcal/mol — (w + C) - C with
+// C = 1.5 * 2^16, two FP64 adds, no branch, no conversion instruction (F2I would run on the XU pipe the pair loop saturates) —
+// and then added with a fire-and-forget FP64 reduction (RED.E.ADD.F64, the add happens in L2).  Every addend and every
+// partial sum of a bin is a multiple of 2^-36, so while |bin| < 2^17 = 131072 kcal/mol each add is EXACT and the bin does
+// not depend on the order in which the reductions land: the bins, and the float32 rows made from them, are bit-identical
+// from run to run and for any cut of the frames into launches.  (Beyond 2^17 the adds round again: nothing breaks, only the
+// guarantee lapses.  Infinity and NaN from coincident atoms propagate as they do in the reference.)  One add is off by at
+// most 2^-37 = 7.3e-12 kcal/mol; a bin takes a few hundred adds: < 1e-12 of its sum of |terms|, five orders of magnitude
+// under the float32 rounding of the row.
+__device__ __forceinline__ void bin_add(double* bin, double w) {
+  atomicAdd(bin, __dadd_rn(__dadd_rn(w, kCdcBinGridShift), -kCdcBinGridShift));
 }
 
 // sa = (-xc, -yc, -zc, dQ) of one site atom.  pack2(v, v) is folded by ptxas into the scalar-broadcast operand form of
@@ -112,8 +105,8 @@ __host__ __device__ inline size_t cdc_smem_layout(int chunk_sites, int P, size_t
 template <int kMinBlocks, int kUnroll, int kFlags = 0>
 __global__ void __launch_bounds__(kTileThreads, kMinBlocks)
 cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, const double* __restrict__ kq_all,
-           const int32_t* __restrict__ col_all, long long* __restrict__ acc, int* __restrict__ err_flags, int n_pad,
-           int tiles_per_frame, long long n_units, int S, int P, int G, int chunk_sites, int chunks_per_item) {
+           const int32_t* __restrict__ col_all, double* __restrict__ acc, int n_pad, int tiles_per_frame,
+           long long n_units, int S, int P, int G, int chunk_sites, int chunks_per_item) {
   static_assert(kAtomsPerThread == 8, "the loads below are written for 8 atoms per thread");
   constexpr bool kBits = (kFlags & 2) != 0;
   extern __shared__ __align__(128) unsigned char sm_raw[];
@@ -167,7 +160,7 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
   unsigned run_mask = 0;              // bit e: atom e ends a run of equal, real columns; bit 8+e: atom e starts a run
   bool warp_uniform = false;
   int c_lane0 = -1;
-  long long* acc_frame = acc;
+  double* acc_frame = acc;
   long long cur_item = -1;
 
   uint32_t seq = 0;
@@ -224,12 +217,12 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
       float Vf[8];
 #pragma unroll
       for (int j = 0; j < 4; j++) unpack2(V[j], Vf[2 * j], Vf[2 * j + 1]);
-      long long* acc_row = acc_frame + (size_t)s * G;
+      double* acc_row = acc_frame + (size_t)s * G;
       if constexpr ((kFlags & 1) != 0) {
         float t = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; e++) t += Vf[e];
-        if (t == 123.456f) bin_add(acc_row, (double)t, err_flags);
+        if (t == 123.456f) bin_add(acc_row, (double)t);
       } else if (warp_uniform) {
         // two independent chains of four
         double t0 = f2d<kBits>(Vf[0]) * kq[0], t1 = f2d<kBits>(Vf[1]) * kq[1];
@@ -251,7 +244,7 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
           const double w = f2d<kBits>(Vf[e]) * kq[e];
           run = ((run_mask >> (8 + e)) & 1u) ? w : run + w;
           // own-site column: reference src/grom2atomFMO.cpp:674
-          if (((run_mask >> e) & 1u) && cols[e] != s) bin_add(acc_row + cols[e], run, err_flags);
+          if (((run_mask >> e) & 1u) && cols[e] != s) bin_add(acc_row + cols[e], run);
         }
       }
     };
@@ -327,7 +320,7 @@ cdc_kernel(const float* __restrict__ xyz8, const float4* __restrict__ sites, con
         }
         t += __shfl_xor_sync(0xffffffffu, t, 1);
         t += __shfl_xor_sync(0xffffffffu, t, 2);
-        if (qd == 0 && r < n_s && c_lane0 != s_begin + r) bin_add(acc_frame + (size_t)(s_begin + r) * G + c_lane0, t, err_flags);
+        if (qd == 0 && r < n_s && c_lane0 != s_begin + r) bin_add(acc_frame + (size_t)(s_begin + r) * G + c_lane0, t);
         __syncwarp();   // the rows are rewritten by the next chunk's epilogues
       }
     }

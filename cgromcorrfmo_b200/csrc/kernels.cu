@@ -5,7 +5,7 @@
 //                         src/grom2atomFMO.cpp:396-455, and the per-site charge substitution of AtomDataLookup_v2, :574-609)
 //   K2  cdc_kernel        Coulomb sum dQ(site atoms) x q(all other atoms), binned per residue group
 //                         (replaces ComputeCDC_v1, reference src/grom2atomFMO.cpp:625-739)
-//   K2b finish_kernel     fixed-point bins -> float32 dE rows (the reference's cdc_kcal vector)
+//   K2b finish_kernel     FP64 bins -> float32 dE rows (the reference's cdc_kcal vector)
 //   K3  cov_* kernels     n, sum(x-c), sum (x-c)(x-c)^T per site on FP64 tensor cores (DMMA)
 //                         (replaces the Correlate block, reference src/FMOparse.cpp:168-178, 188-206)
 #include "kernels.cuh"
@@ -16,6 +16,8 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <mutex>
+#include <vector>
 
 namespace cgc {
 
@@ -29,6 +31,42 @@ static void ensure_dynamic_smem(K kernel, size_t bytes, size_t* granted /* [16] 
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     granted[dev] = bytes;
   }
+}
+
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor and the device attributes cost tens of microseconds per query: the
+// streaming loop launches every kernel once per batch, so the answers are remembered per (device, kernel, shared memory).
+static int device_index() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev & 15;
+}
+static int cached_sm_count() {
+  static int count[16] = {};
+  const int dev = device_index();
+  if (count[dev] == 0) {
+    int v = 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    count[dev] = v;
+  }
+  return count[dev];
+}
+template <typename K>
+static int cached_occupancy(K kernel, int threads, size_t smem, int* slots /* [16][8][2] */) {
+  int* mine = slots + device_index() * 16;
+  for (int i = 0; i < 8; i++) {
+    if (mine[2 * i + 1] != 0 && mine[2 * i] == (int)smem) return mine[2 * i + 1];
+  }
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+  if (per_sm < 1) per_sm = 1;
+  for (int i = 0; i < 8; i++) {
+    if (mine[2 * i + 1] == 0) {
+      mine[2 * i] = (int)smem;
+      mine[2 * i + 1] = per_sm;
+      break;
+    }
+  }
+  return per_sm;
 }
 
 // The neutral padding entry of a site block: dQ = 0 at a far-away point (stored negated), so it adds exactly 0.
@@ -294,11 +332,9 @@ void launch_decode(const DeviceSystem& sys, const char* text, int64_t text_bytes
               : mode == kDecText83 ? decode_kernel<kDecText83> : decode_kernel<kDecText>;
   static size_t granted[4][16] = {};
   ensure_dynamic_smem(kern, smem, granted[mode]);
-  int dev = 0, sm_count = 148, per_sm = 1;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDecodeThreads, smem);
-  if (per_sm < 1) per_sm = 1;
+  static int occ[4][16 * 16] = {};
+  const int sm_count = cached_sm_count();
+  const int per_sm = cached_occupancy(kern, kDecodeThreads, smem, occ[mode]);
   const long long grid = std::min<long long>(n_chunks, (long long)sm_count * per_sm);
   kern<<<(unsigned)grid, kDecodeThreads, smem, st>>>(text, text_bytes, atoms_off, sys.n_atoms, sys.n_pad, sys.line_bytes,
                                                      sys.x_col, sys.field_w, sys.ndec, sys.slot, sys.slot_dq,
@@ -339,48 +375,46 @@ int cdc_pad_site_cap(int p) {
 }
 
 template <int kUnroll>
-static void launch_cdc_t(const DeviceSystem& sys, const float* xyz8, const float4* sites, long long* acc, int* err_flags,
-                         int n_frames, int sm_count, cudaStream_t st) {
+static void launch_cdc_t(const DeviceSystem& sys, const float* xyz8, const float4* sites, double* acc, int n_frames,
+                         int sm_count, cudaStream_t st) {
   const int tiles = sys.n_pad / kTileAtoms;
   auto kern = cdc_kernel<kCdcMinBlocks, kUnroll>;
   static size_t granted[16] = {};
   ensure_dynamic_smem(kern, 200 * 1024, granted);
-  int per_sm = kCdcMinBlocks;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, cdc_smem_bytes(sys));
-  if (per_sm < 1) per_sm = 1;
+  static int occ[16 * 16] = {};
+  int per_sm = cached_occupancy(kern, kTileThreads, cdc_smem_bytes(sys), occ);
   const int chunk_sites = cdc_chunk_sites(sys, n_frames, sm_count * per_sm);
   const int chunks_per_item = (sys.n_sites + chunk_sites - 1) / chunk_sites;
   const size_t smem = cdc_smem_layout(chunk_sites, sys.site_cap, nullptr);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem);
-  if (per_sm < 1) per_sm = 1;
+  per_sm = cached_occupancy(kern, kTileThreads, smem, occ);
   const long long n_units = (long long)tiles * n_frames * chunks_per_item;
   long long grid = (long long)sm_count * per_sm;
   if (grid > n_units) grid = n_units;
-  kern<<<(unsigned)grid, kTileThreads, smem, st>>>(xyz8, sites, sys.kq, sys.col, acc, err_flags, sys.n_pad, tiles, n_units,
+  kern<<<(unsigned)grid, kTileThreads, smem, st>>>(xyz8, sites, sys.kq, sys.col, acc, sys.n_pad, tiles, n_units,
                                                    sys.n_sites, sys.site_cap, sys.num_tot, chunk_sites, chunks_per_item);
 }
 
-void launch_cdc(const DeviceSystem& sys, const float* xyz8, const float4* sites, long long* acc, int* err_flags,
-                int n_frames, int sm_count, cudaStream_t st) {
+void launch_cdc(const DeviceSystem& sys, const float* xyz8, const float4* sites, double* acc, int n_frames,
+                int sm_count, cudaStream_t st) {
   if (sys.n_pad / kTileAtoms * n_frames == 0 || sys.n_sites == 0) return;
   // 42 site atoms per trip when that divides P - 2 (the 44 dQ atoms of a BCL), else 7 (cdc_pad_site_cap)
-  if ((sys.site_cap - 2) % 42 == 0) launch_cdc_t<42>(sys, xyz8, sites, acc, err_flags, n_frames, sm_count, st);
-  else launch_cdc_t<7>(sys, xyz8, sites, acc, err_flags, n_frames, sm_count, st);
+  if ((sys.site_cap - 2) % 42 == 0) launch_cdc_t<42>(sys, xyz8, sites, acc, n_frames, sm_count, st);
+  else launch_cdc_t<7>(sys, xyz8, sites, acc, n_frames, sm_count, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// K2b  finish: fixed-point bins -> float32 dE (the reference's cdc_kcal), bins re-zeroed for the next batch
+// K2b  finish: FP64 bins -> float32 dE (the reference's cdc_kcal), bins re-zeroed for the next batch
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void finish_kernel(long long* __restrict__ acc, float* __restrict__ dE, int64_t n) {
+__global__ void finish_kernel(double* __restrict__ acc, float* __restrict__ dE, int64_t n) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    dE[i] = (float)((double)acc[i] * kCdcBinInvScale);   // exact below 2^53 units (131072 kcal/mol), then one rounding
-    acc[i] = 0;
+    dE[i] = (float)acc[i];
+    acc[i] = 0.0;
   }
 }
 
-void launch_finish(long long* acc, float* dE, int64_t n, cudaStream_t st) {
+void launch_finish(double* acc, float* dE, int64_t n, cudaStream_t st) {
   if (n == 0) return;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -394,28 +428,35 @@ void launch_finish(long long* acc, float* dE, int64_t n, cudaStream_t st) {
 // sumsq_s += D_s^T D_s with D_s the (frames x G) matrix of one site: a SYRK.  Only elements whose 64-block row is <= their
 // 64-block column are computed and stored (kCovBlk; finalize mirrors them).
 //
-// cov_sum_kernel writes the centred rows D = x - c in FP64 into a scratch matrix [frame][site][Gp], Gp = G rounded up to
-// 16 with zero pads.  cov_syrk_kernel is a persistent kernel, 2 CTAs of 4 warps per SM.  Work unit = one 128 x 64 tile of
-// one site's sumsq; a CTA takes tiles blockIdx, blockIdx + grid, ...  For every 16 frames the operands — 128 + 64 columns
-// of D — arrive in shared memory as twelve TMA tiled copies (cp.async.bulk.tensor.3d, SASS UTMALDG; box = 16 columns x 1
-// site x 16 frames = 2 KB) of a tensor map over D with 128-byte swizzle; frames beyond the batch and columns beyond Gp are
-// zero-filled by the TMA unit, so the loop has no bounds.  A ring of 4 stages with a full / empty mbarrier pair per stage
-// runs ahead across tile boundaries; one elected thread issues the copies, no CTA-wide barrier exists after start-up.
-// Each warp owns 32 x 64 of the tile = 4 x 8 DMMA m8n8k4 tiles (64 FP64 accumulators per thread): per k-step of 4 frames
-// 12 shared-memory loads feed 32 DMMAs.  The k-steps take frames {0,2,4,6}, {1,3,5,7}, {8,..}, {9,..} of the stage: with
-// the 128-byte swizzle (16-byte chunk index ^ (frame & 7)) the four rows of a fragment load then fall into four different
-// bank groups, so every LDS.64 is conflict-free.  Warps whose 32 rows lie under the diagonal 64-block, or beyond G, skip
-// the math.  The accumulators go back as fire-and-forget FP64 reductions (RED.E.ADD.F64): every element is touched by
-// exactly one thread per launch and launches are stream-ordered, so the result is deterministic.
+// cov_centre_kernel writes the centred rows D = x - c in FP64 into a scratch matrix [frame][site][Gp], Gp = G rounded up to
+// 16 with zero pads; cov_sum_kernel adds n, sum(x-c) and the reference's two float32 running sums.
+// cov_syrk_kernel is a persistent kernel, ONE CTA of 8 warps per SM.  Work unit = one 128 x 128 tile of one site's sumsq
+// (16 FLOP per byte of operand read from L2; the 64 x 64 tiles of the first version and the 128 x 64 tiles of the second,
+// 8 and 10.7 FLOP/B, both stopped at 20 TFLOP/s with the L2 -> SM path saturated).  The host deals the tiles out
+// longest-first (LPT) into one list per CTA, so the tail is as short as the tile costs allow.  For every 16 frames the
+// operands — 128 + 128 columns of D (128 on a diagonal tile) — arrive in shared memory as TMA tiled copies
+// (cp.async.bulk.tensor.3d, SASS UTMALDG; box = 16 columns x 1 site x 16 frames = 2 KB) of a tensor map over D with 128-byte
+// swizzle; frames beyond the batch and columns beyond Gp are zero-filled by the TMA unit, so the loop has no bounds.  A ring
+// of 5 stages with a full / empty mbarrier pair per stage runs ahead across tile boundaries; one elected thread issues the
+// copies, no CTA-wide barrier exists after start-up.  Warp w owns rows 32 (w & 3) .. +32 and columns 64 (w >> 2) .. +64 of
+// the tile = 4 x 8 DMMA m8n8k4 tiles (64 FP64 accumulators per thread): per k-step of 4 frames 12 shared-memory loads feed
+// 32 DMMAs.  The k-steps take frames {0,2,4,6}, {1,3,5,7}, {8,..}, {9,..} of the stage: with the 128-byte swizzle (16-byte
+// chunk index ^ (frame & 7)) the four rows of a fragment load then fall into four different bank groups, so every LDS.64 is
+// conflict-free.  Warps whose 32 x 64 piece lies under the diagonal 64-block or beyond G skip the math, and a warp whose
+// columns end early (the last column block) runs the narrow instantiation of the k-step (2 or 4 of the 8 column tiles); the
+// two warps of a sub-partition are the two column halves of one row strip, so such savings shorten the tile.  The
+// accumulators go back as fire-and-forget FP64 reductions (RED.E.ADD.F64): every element is touched by exactly one thread
+// per launch and launches are stream-ordered, so the result is deterministic.
 constexpr int kCovBlk = 64;        // granularity of the stored upper triangle
-constexpr int kSyrkBM = 128, kSyrkBN = 64;   // tile of sumsq per work unit
+constexpr int kSyrkTile = 128;     // tile edge
 constexpr int kSyrkK = 16;         // frames per stage
-constexpr int kSyrkStages = 4;
+constexpr int kSyrkStages = 5;
 constexpr int kSyrkBox = 16;       // columns per TMA box: 128 bytes, the swizzle span
-constexpr int kSyrkBoxBytes = kSyrkBox * kSyrkK * 8;                                   // 2048
-constexpr int kSyrkStageBytes = (kSyrkBM + kSyrkBN) / kSyrkBox * kSyrkBoxBytes;        // 24576
-constexpr int kSyrkThreads = 128;
-constexpr size_t kSyrkSmem = (size_t)kSyrkStages * kSyrkStageBytes + 1024;             // + room to align the ring to 1024 B
+constexpr int kSyrkBoxBytes = kSyrkBox * kSyrkK * 8;                              // 2048
+constexpr int kSyrkOperandBytes = kSyrkTile / kSyrkBox * kSyrkBoxBytes;           // 16384: 128 columns x 16 frames
+constexpr int kSyrkStageBytes = 2 * kSyrkOperandBytes;                            // 32768
+constexpr int kSyrkThreads = 256;
+constexpr size_t kSyrkSmem = (size_t)kSyrkStages * kSyrkStageBytes + 1024;        // + room to align the ring to 1024 B
 
 int64_t cov_padded_cols(int G) { return ((int64_t)G + kSyrkBox - 1) / kSyrkBox * kSyrkBox; }
 int64_t cov_centred_doubles(int n_frames, int S, int G) { return (int64_t)n_frames * S * cov_padded_cols(G); }
@@ -436,31 +477,51 @@ void launch_cov_set_shift(const float* dE_row0, double* buf, int S, int G, cudaS
   cov_set_shift_kernel<<<(n + 255) / 256, 256, 0, st>>>(dE_row0, buf, n);
 }
 
-// cov_sum_kernel: n, sum(x-c), the centred rows D = x - c in FP64 (scratch [frame][site][Gp], consumed by the SYRK; the pad
-// columns are written as zeros), and the two float32 running sums the reference's literal .mtx arithmetic needs
-// (src/FMOparse.cpp:173-175 with the zero stride of :193,202): sum_t x_i and sum_t x_0 x_j, added frame by frame in order
-// like the reference does.
-__global__ void cov_sum_kernel(const float* __restrict__ dE, int n_frames, double* __restrict__ buf, int S, int G, int Gp,
-                               float* __restrict__ compat /* [2][SG] or null */, double* __restrict__ centred) {
+// D = x - c in FP64, [frame][site][Gp] with zero pads: one thread per element of the padded matrix
+__global__ void cov_centre_kernel(const float* __restrict__ dE, int n_frames, const double* __restrict__ buf, int S, int G,
+                                  int Gp, double* __restrict__ centred) {
   const int ip = blockIdx.x * blockDim.x + threadIdx.x;   // index into the padded row
-  if (ip == 0) buf[0] += (double)n_frames;
   const int SGp = S * Gp, SG = S * G;
   if (ip >= SGp) return;
   const int s = ip / Gp, g = ip - s * Gp;
-  if (g >= G) {
-    for (int t = 0; t < n_frames; t++) centred[(size_t)t * SGp + ip] = 0.0;
-    return;
+  const bool real = g < G;
+  const int i = s * G + (real ? g : 0);
+  const double c = real ? buf[1 + i] : 0.0;
+  for (int t = blockIdx.y; t < n_frames; t += gridDim.y) {
+    centred[(size_t)t * SGp + ip] = real ? (double)dE[(size_t)t * SG + i] - c : 0.0;
   }
-  const int i = s * G + g;
+}
+
+// cov_sum_kernel: n, sum(x-c), and the two float32 running sums the reference's literal .mtx arithmetic needs
+// (src/FMOparse.cpp:173-175 with the zero stride of :193,202): sum_t x_i and sum_t x_0 x_j, added frame by frame in order
+// like the reference does (the loads of 8 frames are issued together; the adds keep their order).
+__global__ void cov_sum_kernel(const float* __restrict__ dE, int n_frames, double* __restrict__ buf, int SG, int G,
+                               float* __restrict__ compat /* [2][SG] or null */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) buf[0] += (double)n_frames;
+  if (i >= SG) return;
   const double c = buf[1 + i];
   double sum = 0.0;
-  const int i0 = s * G;  // column 0 of this site
+  const int i0 = (i / G) * G;  // column 0 of this site
   float m32 = compat ? compat[i] : 0.f, p32 = compat ? compat[SG + i] : 0.f;
-  for (int t = 0; t < n_frames; t++) {
+  int t = 0;
+  for (; t + 8 <= n_frames; t += 8) {
+    float x[8], x0[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      x[u] = dE[(size_t)(t + u) * SG + i];
+      x0[u] = dE[(size_t)(t + u) * SG + i0];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      sum += (double)x[u] - c;
+      m32 += x[u];
+      p32 += __fmul_rn(x0[u], x[u]);
+    }
+  }
+  for (; t < n_frames; t++) {
     const float x = dE[(size_t)t * SG + i];
-    const double d = (double)x - c;
-    centred[(size_t)t * SGp + ip] = d;
-    sum += d;
+    sum += (double)x - c;
     m32 += x;
     p32 += __fmul_rn(dE[(size_t)t * SG + i0], x);
   }
@@ -475,14 +536,36 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
                : "memory");
 }
 
-__global__ void __launch_bounds__(kSyrkThreads, 2)
+// one k-step (4 frames) of a warp: 4 row tiles x kNJ column tiles
+template <int kNJ>
+__device__ __forceinline__ void syrk_kstep(double (&acc)[4][8][2], uint32_t a_base, uint32_t b_base, int q, const uint32_t (&t_off)[2][2]) {
+  double a[4], b[kNJ];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint32_t ad = a_base + (i >> 1) * kSyrkBoxBytes + (q >> 1) * 1024 + t_off[q & 1][i & 1];
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[i]) : "r"(ad));
+  }
+#pragma unroll
+  for (int j = 0; j < kNJ; j++) {
+    const uint32_t ad = b_base + (j >> 1) * kSyrkBoxBytes + (q >> 1) * 1024 + t_off[q & 1][j & 1];
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b[j]) : "r"(ad));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < kNJ; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+}
+
+// tile = s * 65536 + bi * 256 + bj  (128-blocks; bi <= bj)
+__global__ void __launch_bounds__(kSyrkThreads, 1)
 cov_syrk_kernel(const __grid_constant__ CUtensorMap dmap, int n_frames, double* __restrict__ buf, int S, int G,
-                int tiles_per_site, int n_tiles) {
+                const int* __restrict__ sched_off, const int* __restrict__ sched_tile) {
   extern __shared__ unsigned char syrk_smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kSyrkStages], empty_bar[kSyrkStages];
   unsigned char* ring = syrk_smem_raw + ((1024u - (smem_addr(syrk_smem_raw) & 1023u)) & 1023u);   // the swizzle wants 1024 B
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
+  const int strip = warp & 3, half = warp >> 2;
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < kSyrkStages; i++) {
@@ -494,32 +577,26 @@ cov_syrk_kernel(const __grid_constant__ CUtensorMap dmap, int n_frames, double* 
   }
   __syncthreads();
 
-  const int nb64 = (G + kCovBlk - 1) / kCovBlk;
+  const int t_begin = sched_off[blockIdx.x], my_tiles = sched_off[blockIdx.x + 1] - t_begin;
   const int k_stages = (n_frames + kSyrkK - 1) / kSyrkK;
-  const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const long long total = (long long)my_tiles * k_stages;   // stages this CTA consumes
   if (total == 0) return;
-  auto decode_tile = [&](int tile, int& s, int& r0, int& c0) {   // tile -> site, first row, first column
-    s = tile / tiles_per_site;
-    int t = tile - s * tiles_per_site, bi = 0;
-    while (t >= nb64 - 2 * bi) { t -= nb64 - 2 * bi; bi++; }
-    r0 = bi * kSyrkBM;
-    c0 = (2 * bi + t) * kSyrkBN;
-  };
   // producer (thread 0): stage n of this CTA's sequence
   auto issue = [&](long long n) {
     const int local_tile = (int)(n / k_stages);
     const int ks = (int)(n - (long long)local_tile * k_stages);
-    int s, r0, c0;
-    decode_tile((int)blockIdx.x + local_tile * (int)gridDim.x, s, r0, c0);
+    const int tile = sched_tile[t_begin + local_tile];
+    const int s = tile >> 16, bi = (tile >> 8) & 255, bj = tile & 255;
     const int st = (int)(n % kSyrkStages);
     unsigned char* dst = ring + (size_t)st * kSyrkStageBytes;
-    mbar_expect_tx(&full_bar[st], kSyrkStageBytes);
+    mbar_expect_tx(&full_bar[st], bi == bj ? kSyrkOperandBytes : kSyrkStageBytes);
 #pragma unroll
-    for (int j = 0; j < kSyrkBM / kSyrkBox; j++) tma_load_3d(dst + j * kSyrkBoxBytes, &dmap, r0 + j * kSyrkBox, s, ks * kSyrkK, &full_bar[st]);
+    for (int j = 0; j < kSyrkTile / kSyrkBox; j++) tma_load_3d(dst + j * kSyrkBoxBytes, &dmap, bi * kSyrkTile + j * kSyrkBox, s, ks * kSyrkK, &full_bar[st]);
+    if (bi != bj) {
 #pragma unroll
-    for (int j = 0; j < kSyrkBN / kSyrkBox; j++)
-      tma_load_3d(dst + (kSyrkBM / kSyrkBox + j) * kSyrkBoxBytes, &dmap, c0 + j * kSyrkBox, s, ks * kSyrkK, &full_bar[st]);
+      for (int j = 0; j < kSyrkTile / kSyrkBox; j++)
+        tma_load_3d(dst + kSyrkOperandBytes + j * kSyrkBoxBytes, &dmap, bj * kSyrkTile + j * kSyrkBox, s, ks * kSyrkK, &full_bar[st]);
+    }
   };
   if (threadIdx.x == 0) {
     for (long long n = 0; n < kSyrkStages - 1 && n < total; n++) issue(n);
@@ -539,14 +616,15 @@ cov_syrk_kernel(const __grid_constant__ CUtensorMap dmap, int n_frames, double* 
   const uint32_t ring_addr = smem_addr(ring);
 
   double acc[4][8][2];
-  int s = 0, r0 = 0, c0 = 0;
-  bool active = false;
   long long n = 0;
   for (int lt = 0; lt < my_tiles; lt++) {
-    decode_tile((int)blockIdx.x + lt * (int)gridDim.x, s, r0, c0);
-    const int wr0 = r0 + 32 * warp;
-    // this warp's 32 rows: inside G, and not below the diagonal 64-block
-    active = wr0 < G && (wr0 / kCovBlk) <= (c0 / kCovBlk);
+    const int tile = sched_tile[t_begin + lt];
+    const int s = tile >> 16, bi = (tile >> 8) & 255, bj = tile & 255;
+    const int wr0 = bi * kSyrkTile + 32 * strip, wc0 = bj * kSyrkTile + 64 * half;
+    // this warp's 32 x 64 piece: inside G, and not below the diagonal 64-block; column tiles of 8 that hold real columns
+    const bool active = wr0 < G && wc0 < G && (wr0 / kCovBlk) <= (wc0 / kCovBlk);
+    const int nj = active ? min(8, (G - wc0 + 7) / 8) : 0;
+    const uint32_t b_operand = bi == bj ? 0u : (uint32_t)kSyrkOperandBytes;   // diagonal tile: B is the A operand
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -562,27 +640,17 @@ cov_syrk_kernel(const __grid_constant__ CUtensorMap dmap, int n_frames, double* 
       __syncwarp();
       const int st = (int)(n % kSyrkStages);
       mbar_wait(&full_bar[st], (uint32_t)((n / kSyrkStages) & 1));
-      if (active) {
-        const uint32_t a_base = ring_addr + (uint32_t)st * kSyrkStageBytes + (uint32_t)warp * 2 * kSyrkBoxBytes;
-        const uint32_t b_base = ring_addr + (uint32_t)st * kSyrkStageBytes + (kSyrkBM / kSyrkBox) * kSyrkBoxBytes;
+      const uint32_t a_base = ring_addr + (uint32_t)st * kSyrkStageBytes + (uint32_t)strip * 2 * kSyrkBoxBytes;
+      const uint32_t b_base = ring_addr + (uint32_t)st * kSyrkStageBytes + b_operand + (uint32_t)half * 4 * kSyrkBoxBytes;
+      if (nj > 4) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          double a[4], b[8];
+        for (int q = 0; q < 4; q++) syrk_kstep<8>(acc, a_base, b_base, q, t_off);
+      } else if (nj > 2) {
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const uint32_t ad = a_base + (i >> 1) * kSyrkBoxBytes + (q >> 1) * 1024 + t_off[q & 1][i & 1];
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[i]) : "r"(ad));
-          }
+        for (int q = 0; q < 4; q++) syrk_kstep<4>(acc, a_base, b_base, q, t_off);
+      } else if (nj > 0) {
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const uint32_t ad = b_base + (j >> 1) * kSyrkBoxBytes + (q >> 1) * 1024 + t_off[q & 1][j & 1];
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b[j]) : "r"(ad));
-          }
-#pragma unroll
-          for (int i = 0; i < 4; i++)
-#pragma unroll
-            for (int j = 0; j < 8; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-        }
+        for (int q = 0; q < 4; q++) syrk_kstep<2>(acc, a_base, b_base, q, t_off);
       }
       // every read of the stage is done (the values are in registers): hand it back to the producer
       __syncwarp();
@@ -597,7 +665,7 @@ cov_syrk_kernel(const __grid_constant__ CUtensorMap dmap, int n_frames, double* 
         double* row = sumsq + (size_t)r * G;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          const int c = c0 + j * 8 + tig * 2;
+          const int c = wc0 + j * 8 + tig * 2;
           if (c < G) atomicAdd(row + c, acc[i][j][0]);
           if (c + 1 < G) atomicAdd(row + c + 1, acc[i][j][1]);
         }
@@ -623,11 +691,76 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+// The tiles of all sites dealt out to `ctas` lists, longest first (LPT): cost = the busiest sub-partition's DMMA count.
+// One schedule per (device, S, G), built on first use and kept on the device.
+struct SyrkSchedule {
+  int S = 0, G = 0, ctas = 0;
+  int* d_off = nullptr;    // [ctas + 1]
+  int* d_tile = nullptr;   // [n_tiles]
+};
+static const SyrkSchedule* syrk_schedule(int S, int G, int ctas) {
+  static std::mutex mu;
+  static std::vector<SyrkSchedule> cache[16];
+  std::lock_guard<std::mutex> lock(mu);
+  auto& mine = cache[device_index()];
+  for (auto& e : mine)
+    if (e.S == S && e.G == G && e.ctas == ctas) return &e;
+  const int nb = (G + kSyrkTile - 1) / kSyrkTile;
+  struct T { int id; int cost; };
+  std::vector<T> tiles;
+  for (int s = 0; s < S; s++)
+    for (int bi = 0; bi < nb; bi++)
+      for (int bj = bi; bj < nb; bj++) {
+        int cost = 0;   // max over the 4 row strips (= sub-partitions) of the column tiles its two warps compute
+        for (int strip = 0; strip < 4; strip++) {
+          int c = 0;
+          for (int half = 0; half < 2; half++) {
+            const int wr0 = bi * kSyrkTile + 32 * strip, wc0 = bj * kSyrkTile + 64 * half;
+            if (wr0 < G && wc0 < G && wr0 / kCovBlk <= wc0 / kCovBlk) {
+              const int nj = std::min(8, (G - wc0 + 7) / 8);
+              c += nj > 4 ? 8 : nj > 2 ? 4 : 2;
+            }
+          }
+          cost = std::max(cost, c);
+        }
+        tiles.push_back({(s << 16) | (bi << 8) | bj, cost + 1});   // + 1: the fixed cost of walking the stages
+      }
+  std::stable_sort(tiles.begin(), tiles.end(), [](const T& a, const T& b) { return a.cost > b.cost; });
+  std::vector<std::vector<int>> lists((size_t)ctas);
+  std::vector<long long> load((size_t)ctas, 0);
+  for (const T& t : tiles) {
+    int best = 0;
+    for (int c = 1; c < ctas; c++)
+      if (load[(size_t)c] < load[(size_t)best]) best = c;
+    lists[(size_t)best].push_back(t.id);
+    load[(size_t)best] += t.cost;
+  }
+  std::vector<int> off((size_t)ctas + 1, 0), flat;
+  for (int c = 0; c < ctas; c++) {
+    off[(size_t)c + 1] = off[(size_t)c] + (int)lists[(size_t)c].size();
+    flat.insert(flat.end(), lists[(size_t)c].begin(), lists[(size_t)c].end());
+  }
+  SyrkSchedule e;
+  e.S = S; e.G = G; e.ctas = ctas;
+  if (cudaMalloc(&e.d_off, sizeof(int) * off.size()) != cudaSuccess || cudaMalloc(&e.d_tile, sizeof(int) * std::max<size_t>(1, flat.size())) != cudaSuccess ||
+      cudaMemcpy(e.d_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(e.d_tile, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    return nullptr;
+  }
+  mine.push_back(e);
+  return &mine.back();
+}
+
 cudaError_t launch_cov_accumulate(const float* dE, int n_frames, double* buf, float* compat, double* centred_scratch, int S,
                                   int G, cudaStream_t st) {
   if (n_frames <= 0) return cudaSuccess;
+  if (S >= 32768 || (G + kSyrkTile - 1) / kSyrkTile > 255) return cudaErrorInvalidValue;
   const int Gp = (int)cov_padded_cols(G);
-  cov_sum_kernel<<<(S * Gp + 255) / 256, 256, 0, st>>>(dE, n_frames, buf, S, G, Gp, compat, centred_scratch);
+  const int SG = S * G;
+  const int sm_count = cached_sm_count();
+  dim3 cgrid((S * Gp + 255) / 256, std::max(1, std::min(n_frames, 8 * sm_count / std::max(1, (S * Gp + 255) / 256))));
+  cov_centre_kernel<<<cgrid, 256, 0, st>>>(dE, n_frames, buf, S, G, Gp, centred_scratch);
+  cov_sum_kernel<<<(SG + 127) / 128, 128, 0, st>>>(dE, n_frames, buf, SG, G, compat);
   // tensor map over D [frame][site][Gp] (innermost first), box = 16 columns x 1 site x 16 frames, 128-byte swizzle,
   // out-of-range elements read as zero
   EncodeTiledFn encode = encode_tiled_fn();
@@ -641,17 +774,14 @@ cudaError_t launch_cov_accumulate(const float* dE, int n_frames, double* buf, fl
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
     return cudaErrorInvalidValue;
   }
-  const int nb64 = (G + kCovBlk - 1) / kCovBlk, nb128 = (G + kSyrkBM - 1) / kSyrkBM;
-  int tiles_per_site = 0;
-  for (int bi = 0; bi < nb128; bi++) tiles_per_site += std::max(0, nb64 - 2 * bi);
-  const int n_tiles = tiles_per_site * S;
+  const int nb = (G + kSyrkTile - 1) / kSyrkTile;
+  const int n_tiles = S * nb * (nb + 1) / 2;
+  const int grid = std::min(n_tiles, sm_count);
+  const SyrkSchedule* sched = syrk_schedule(S, G, grid);
+  if (!sched) return cudaErrorMemoryAllocation;
   static size_t granted[16] = {};
   ensure_dynamic_smem(cov_syrk_kernel, kSyrkSmem, granted);
-  int dev = 0, sm_count = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = std::min(n_tiles, 2 * sm_count);
-  cov_syrk_kernel<<<grid, kSyrkThreads, kSyrkSmem, st>>>(map, n_frames, buf, S, G, tiles_per_site, n_tiles);
+  cov_syrk_kernel<<<grid, kSyrkThreads, kSyrkSmem, st>>>(map, n_frames, buf, S, G, sched->d_off, sched->d_tile);
   return cudaGetLastError();
 }
 

@@ -18,7 +18,6 @@ enum : int {
   kDecBadChar = 1,      // a coordinate field holds something other than [ -.0-9]
   kDecBadPoint = 2,     // the decimal point is not where the frame-0 layout says
   kDecBadNewline = 4,   // an atom line does not end where the frame-0 layout says
-  kCdcRange = 8,        // K2: a partial pair sum was not finite or beyond +-16384 kcal/mol (coincident atoms)
 };
 
 struct DeviceSystem {
@@ -46,16 +45,15 @@ void launch_unblock(const DeviceSystem& sys, const float* xyz8, float* xyz, int 
 // fill every slot of the per-frame site blocks with the neutral padding entry
 void launch_init_sites(const DeviceSystem& sys, float4* sites, int n_frames, cudaStream_t st);
 
-// K2: CDC pair sums.  acc: fixed-point bins, int64 [n_frames][n_sites][num_tot] in units of 2^-36 kcal/mol, zero on entry
-// (integer adds: bit-reproducible whatever the order of the atomics).  err_flags |= kCdcRange when a partial sum does not
-// fit (non-finite, or beyond +-16384 kcal/mol).
-void launch_cdc(const DeviceSystem& sys, const float* xyz8, const float4* sites, long long* acc, int* err_flags,
-                int n_frames, int sm_count, cudaStream_t st);
+// K2: CDC pair sums.  acc: double [n_frames][n_sites][num_tot], must be zero on entry.  The partials are rounded to a grid
+// of 2^-36 kcal/mol before they are added, so the adds are exact and the bins do not depend on the order of the atomics.
+void launch_cdc(const DeviceSystem& sys, const float* xyz8, const float4* sites, double* acc, int n_frames,
+                int sm_count, cudaStream_t st);
 size_t cdc_smem_bytes(const DeviceSystem& sys);
 int cdc_pad_site_cap(int p);  // dQ atoms per site, padded to what the kernel's loop structure wants
 
-// acc (fixed-point bins) -> dE (float32), and re-zero acc for the next batch.
-void launch_finish(long long* acc, float* dE, int64_t n, cudaStream_t st);
+// acc (double) -> dE (float32), and re-zero acc for the next batch.
+void launch_finish(double* acc, float* dE, int64_t n, cudaStream_t st);
 
 // K3: per-site shifted sums.  buf = [ n | c (S*G) | sum (S*G) | sumsq (S*G*G) ]
 void launch_cov_set_shift(const float* dE_row0, double* buf, int S, int G, cudaStream_t st);

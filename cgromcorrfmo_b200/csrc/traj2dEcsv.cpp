@@ -22,7 +22,7 @@
 //     cut into N contiguous ranges — what the authors did by hand with one process per trajectory chunk file in a bash
 //     loop (reference scripts/2014-06-gro2dEcsv.sh:3-27) — every GPU writes csv_out.time.part<r>, the Correlate sums are
 //     combined by ONE ncclAllReduce(double) (cgc_cov_allreduce), then the parts are joined in rank order into
-//     csv_out.time and device 0 writes csv_out.mtx.  The rows are bit-identical to a one-GPU run (K2 bins in fixed point).
+//     csv_out.time and device 0 writes csv_out.mtx.  The rows are bit-identical to a one-GPU run (K2 adds grid-rounded partial sums: exact, order-independent).
 // Extra flags come AFTER the five positionals.
 #include <fcntl.h>
 #include <sys/stat.h>

@@ -115,7 +115,7 @@ double cgc_get_option(const cgc_context *ctx, const char *key);
  * text through a ring of 4 pinned staging buffers (filled by background copier threads, two batches ahead) and H2D
  * copies, decodes it (K1), evaluates ComputeCDC_v1 for every site (K2), and accumulates the Correlate sums (K3).
  * dE_kcal (nullable) receives float32 [n][sites][numTot], caller-owned HOST memory.  The rows are bit-identical from run
- * to run and for any batch size or frame range (K2 bins in fixed point).
+ * to run and for any batch size or frame range (K2 rounds its partial sums to a fixed grid, so the bin adds are exact).
  * Returns CGC_OK, CGC_EOF with *frames_done < n when the trajectory ends early, or CGC_STOPPED after cgc_request_stop.
  * On an error in the middle of the range (a malformed later frame) *frames_done, the rows delivered so far, the `.time`
  * text and the Correlate sums all cover the same frames: the sound batches before the error. */

@@ -1,5 +1,5 @@
 """GPU tests of the streaming engine behind cgc_run / cgc_run_write_time (csrc/capi.cu run_impl) and of the multi-GPU
-paths: reproducibility of the rows (K2 bins in fixed point), recovery after an error in the middle of a trajectory,
+paths: reproducibility of the rows (K2 adds grid-rounded partial sums: exact, order-independent), recovery after an error in the middle of a trajectory,
 the stop request, single-process multi-GPU (traj2dEcsv --gpus N, cgc_cov_allreduce over NCCL).
 
 The frame loop these replace: reference src/FMOparse.cpp:68-184; its SIGINT flag :24-29,62; the authors' one process per
@@ -37,7 +37,7 @@ def _repeat(traj, reps, path):
 
 @pytest.mark.parametrize("tag", ["tiny", "permol"])
 def test_rows_bit_identical_across_runs_batch_sizes_and_ranges(tag, small_inputs, capi_mod, tmp_path):
-    """Fixed-point bins: the float32 rows do not depend on the order in which the device's atomics land, nor on how the
+    """Exact bin adds (partials rounded to a 2^-36 grid): the float32 rows do not depend on the order in which the device's atomics land, nor on how the
     frames were cut into batches, launches or frame ranges (a reproducible scheme)."""
     capi = capi_mod
     traj, top, itp, frames = small_inputs(tag)

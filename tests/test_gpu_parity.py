@@ -407,7 +407,7 @@ def test_zero_frames_and_reopen(small_inputs, capi_mod):
         a, _, _ = c.run(0, frames)
         c.open(traj)                                          # re-opening resets the Correlate sums and options
         b, _, _ = c.run(0, frames)
-        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))   # fixed-point bins: bit-identical from run to run
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))   # grid-rounded partial sums: bit-identical from run to run
         assert c.cov_partials()[0] == frames
     with capi.Context(top2, itp2, 0) as c:
         c.open(traj2)
