@@ -201,6 +201,7 @@ struct cgc_context {
   bool dev_pipeline = false;
   int alloc_batch = 0;
   int64_t alloc_text = 0;
+  int alloc_slots = 0;          // slots that have their buffers (1 for the device-resident entry points, kSlots for the ring)
   cudaStream_t st_copy = nullptr, st_comp = nullptr, st_out = nullptr;
   int* d_err = nullptr;
   int* d_fmt_flags = nullptr;   // K5 flag word of the one-shot formatter calls (cgc_write_mtx); the ring has one per slot
@@ -286,6 +287,7 @@ void free_pipeline(cgc_context* c) {
   c->dev_pipeline = false;
   c->alloc_batch = 0;
   c->alloc_text = 0;
+  c->alloc_slots = 0;
 }
 
 void free_static(cgc_context* c) {
@@ -504,29 +506,33 @@ int default_batch(const cgc_context* c) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(256, b));
 }
 
-void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_host_text) {
+// n_slots: kSlots for the streaming ring (run_impl), 1 for the entry points that work on text already on the device (they
+// use slot 0's scratch only — no pinned buffers, no text buffer of their own)
+void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_host_text, int n_slots = cgc_context::kSlots) {
   need_device(c);
   if (!c->dev_static) throw std::runtime_error("internal: static data missing");
   const DeviceSystem& sys = c->sys;
-  if (c->dev_pipeline && c->alloc_batch >= batch && c->alloc_text >= text_bytes &&
+  if (c->dev_pipeline && c->alloc_batch >= batch && c->alloc_text >= text_bytes && c->alloc_slots >= n_slots &&
       (!need_host_text || c->slot[0].h_text)) {
     return;
   }
   free_pipeline(c);
   const int64_t sg = (int64_t)sys.n_sites * sys.num_tot;
-  bool first = true;
-  for (auto& s : c->slot) {
-    CUDA_OK(cudaMalloc(&s.d_text, (size_t)text_bytes + 64));
-    if (need_host_text && first) CUDA_OK(cudaHostAlloc(&s.h_text, (size_t)text_bytes + 64, cudaHostAllocDefault));
-    first = false;
+  const bool ring = n_slots > 1;
+  for (int si = 0; si < n_slots; si++) {
+    Slot& s = c->slot[si];
+    if (ring) CUDA_OK(cudaMalloc(&s.d_text, (size_t)text_bytes + 64));
+    if (need_host_text && si == 0) CUDA_OK(cudaHostAlloc(&s.h_text, (size_t)text_bytes + 64, cudaHostAllocDefault));
     CUDA_OK(cudaMalloc(&s.d_off, sizeof(int64_t) * batch));
     CUDA_OK(cudaHostAlloc(&s.h_off, sizeof(int64_t) * batch, cudaHostAllocDefault));
     CUDA_OK(cudaMalloc(&s.d_xyz8, sizeof(float) * 3 * (size_t)sys.n_pad * batch));
     CUDA_OK(cudaMalloc(&s.d_sites, (size_t)16 * sys.n_sites * sys.site_cap * batch));
     CUDA_OK(cudaMalloc(&s.d_acc, sizeof(double) * sg * batch));
     CUDA_OK(cudaMemsetAsync(s.d_acc, 0, sizeof(double) * sg * batch, c->st_comp));
-    CUDA_OK(cudaMalloc(&s.d_dE, sizeof(float) * sg * batch));
-    CUDA_OK(cudaHostAlloc(&s.h_dE, sizeof(float) * sg * batch, cudaHostAllocDefault));
+    if (ring) {
+      CUDA_OK(cudaMalloc(&s.d_dE, sizeof(float) * sg * batch));
+      CUDA_OK(cudaHostAlloc(&s.h_dE, sizeof(float) * sg * batch, cudaHostAllocDefault));
+    }
     CUDA_OK(cudaEventCreateWithFlags(&s.ev_copied, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&s.ev_text_out, cudaEventDisableTiming));
@@ -537,6 +543,7 @@ void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_ho
   c->dev_pipeline = true;
   c->alloc_batch = batch;
   c->alloc_text = text_bytes;
+  c->alloc_slots = n_slots;
   if (need_host_text) {
     // the rest of the staging ring is page-locked while the first batches already stream (run_impl waits on host_ready)
     c->host_ready.store(1);
@@ -811,8 +818,26 @@ void flush_cov_rows(cgc_context* c, cudaStream_t st) {
     ScopedKernelTimer t(c, 3, st);
     CUDA_OK(launch_cov_accumulate(c->d_cov_rows, n, c->d_cov, c->d_compat, centred_scratch(c, n), sys.n_sites, sys.num_tot, st));
   }
-  c->launches += 2;
+  c->launches += 3;
   c->cov_rows_pending = 0;
+}
+
+// Room for the gather buffer and the centred scratch of K3, sized once for the largest launch the streaming loop can
+// produce (kCovGather - 1 gathered frames + one more batch): growing either in the middle of a run would mean a cudaFree,
+// i.e. a device-wide synchronisation with everything the loop has queued.
+void ensure_cov_buffers(cgc_context* c, int batch) {
+  if (!c->d_cov) return;
+  const DeviceSystem& sys = c->sys;
+  const int64_t sg = (int64_t)sys.n_sites * sys.num_tot;
+  const int64_t cap = kCovGather + batch;
+  if (c->cov_rows_cap < cap) {
+    if (c->d_cov_rows) CUDA_OK(cudaFree(c->d_cov_rows));
+    c->d_cov_rows = nullptr;
+    c->cov_rows_cap = 0;
+    CUDA_OK(cudaMalloc(&c->d_cov_rows, sizeof(float) * (size_t)(cap * sg)));
+    c->cov_rows_cap = cap;
+  }
+  centred_scratch(c, (int)cap);
 }
 
 // hand the rows of one batch to K3: directly when the batch is large, through the gather buffer otherwise
@@ -822,19 +847,14 @@ void accumulate_rows(cgc_context* c, const float* d_dE, int n_frames, cudaStream
   if (n_frames >= kCovGather && c->cov_rows_pending == 0) {
     ScopedKernelTimer t(c, 3, st);
     CUDA_OK(launch_cov_accumulate(d_dE, n_frames, c->d_cov, c->d_compat, centred_scratch(c, n_frames), sys.n_sites, sys.num_tot, st));
-    c->launches += 2;
+    c->launches += 3;
     return;
   }
-  const int64_t cap = std::max<int64_t>(kCovGather, n_frames);
-  if (c->cov_rows_cap < cap) {
+  if (c->cov_rows_cap < c->cov_rows_pending + n_frames) {   // not sized by ensure_cov_buffers (a caller outside the loop)
     flush_cov_rows(c, st);
     CUDA_OK(cudaStreamSynchronize(st));
-    if (c->d_cov_rows) CUDA_OK(cudaFree(c->d_cov_rows));
-    c->d_cov_rows = nullptr;
-    CUDA_OK(cudaMalloc(&c->d_cov_rows, sizeof(float) * (size_t)(cap * sg)));
-    c->cov_rows_cap = cap;
+    ensure_cov_buffers(c, n_frames);
   }
-  if (c->cov_rows_pending + n_frames > c->cov_rows_cap) flush_cov_rows(c, st);
   CUDA_OK(cudaMemcpyAsync(c->d_cov_rows + c->cov_rows_pending * sg, d_dE, sizeof(float) * (size_t)(n_frames * sg),
                           cudaMemcpyDeviceToDevice, st));
   c->cov_rows_pending += n_frames;
@@ -1241,11 +1261,15 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       cudaGetLastError();
     }
     const double t_setup0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    auto wall = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     ensure_pipeline(ctx, B, frame_text_max * B, !direct);
+    const double t_setup1 = wall();
     ensure_cov(ctx);
+    ensure_cov_buffers(ctx, B);
+    const double t_setup2 = wall();
     if (sink) ensure_time_text(ctx, B);
     CopyPool* pool = copy_pool(ctx);
-    const double t_setup = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t_setup0;
+    const double t_setup = wall() - t_setup0;
     // a previous call that ended in an error may have left batches on the device: nothing of theirs is delivered
     for (auto& sl : ctx->slot) {
       if (sl.busy || sl.text_out_pending) {
@@ -1465,9 +1489,10 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       throw;
     }
     if (trace) {
-      fprintf(stderr, "cgc trace: %lld frames in %.1f ms (+ %.1f ms buffer set-up) | host thread: wait for staging %.1f, enqueue %.1f, "
+      fprintf(stderr, "cgc trace: %lld frames in %.1f ms (+ %.1f ms buffer set-up: ring %.1f, Correlate %.1f, text %.1f) | host thread: wait for staging %.1f, enqueue %.1f, "
                       "wait for GPU %.1f, rows to caller %.1f, text D2H + queue %.1f ms | %d frames per batch, %d copier threads\n",
-              (long long)delivered, (now() - t_call0) * 1e3, t_setup * 1e3, t_wait_stage * 1e3, t_enqueue * 1e3, t_wait_gpu * 1e3,
+              (long long)delivered, (now() - t_call0) * 1e3, t_setup * 1e3, (t_setup1 - t_setup0) * 1e3, (t_setup2 - t_setup1) * 1e3,
+              (t_setup - (t_setup2 - t_setup0)) * 1e3, t_wait_stage * 1e3, t_enqueue * 1e3, t_wait_gpu * 1e3,
               t_rows * 1e3, t_text * 1e3, B, pool->threads());
     }
     int flags = 0;
@@ -1564,7 +1589,7 @@ int cgc_run_device(cgc_context* ctx, const void* d_text, int64_t text_bytes, con
   return guarded(ctx, [&]() {
     need_device(ctx);
     const int B = std::max(n_frames, ctx->batch_frames > 0 ? ctx->batch_frames : default_batch(ctx));
-    ensure_pipeline(ctx, B, std::max<int64_t>(ctx->alloc_text, 64), false);
+    ensure_pipeline(ctx, B, std::max<int64_t>(ctx->alloc_text, 64), false, std::max(1, ctx->alloc_slots));
     Slot& s = ctx->slot[0];
     cudaStream_t st = (cudaStream_t)stream;
     // pageable source: the runtime stages it before returning, so the caller's array may be reused at once
@@ -1584,7 +1609,7 @@ int cgc_decode_device(cgc_context* ctx, const void* d_text, int64_t text_bytes, 
   return guarded(ctx, [&]() {
     need_device(ctx);
     const int B = std::max(n_frames, ctx->batch_frames > 0 ? ctx->batch_frames : default_batch(ctx));
-    ensure_pipeline(ctx, B, std::max<int64_t>(ctx->alloc_text, 64), false);
+    ensure_pipeline(ctx, B, std::max<int64_t>(ctx->alloc_text, 64), false, std::max(1, ctx->alloc_slots));
     Slot& s = ctx->slot[0];
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_OK(cudaMemcpyAsync(s.d_off, atoms_offset, sizeof(int64_t) * n_frames, cudaMemcpyHostToDevice, st));
@@ -1668,7 +1693,7 @@ int cgc_cov_accumulate_device(cgc_context* ctx, const float* d_dE_kcal, int n_fr
       CUDA_OK(launch_cov_accumulate(d_dE_kcal, n_frames, ctx->d_cov, ctx->d_compat, centred_scratch(ctx, n_frames),
                                     ctx->sys.n_sites, ctx->sys.num_tot, st));
     }
-    ctx->launches += 2;
+    ctx->launches += 3;
     CUDA_OK(cudaGetLastError());
     return CGC_OK;
   });

@@ -430,35 +430,37 @@ void launch_finish(double* acc, float* dE, int64_t n, cudaStream_t st) {
 //
 // cov_centre_kernel writes the centred rows D = x - c in FP64 into a scratch matrix [frame][site][Gp], Gp = G rounded up to
 // 16 with zero pads; cov_sum_kernel adds n, sum(x-c) and the reference's two float32 running sums.
-// cov_syrk_kernel is a persistent kernel, ONE CTA of 8 warps per SM.  Work unit = one 128 x 128 tile of one site's sumsq
-// (16 FLOP per byte of operand read from L2; the 64 x 64 tiles of the first version and the 128 x 64 tiles of the second,
-// 8 and 10.7 FLOP/B, both stopped at 20 TFLOP/s with the L2 -> SM path saturated).  The host deals the tiles out
-// longest-first (LPT) into one list per CTA, so the tail is as short as the tile costs allow.  For every 16 frames the
-// operands — 128 + 128 columns of D (128 on a diagonal tile) — arrive in shared memory as TMA tiled copies
-// (cp.async.bulk.tensor.3d, SASS UTMALDG; box = 16 columns x 1 site x 16 frames = 2 KB) of a tensor map over D with 128-byte
-// swizzle; frames beyond the batch and columns beyond Gp are zero-filled by the TMA unit, so the loop has no bounds.  A ring
-// of 5 stages with a full / empty mbarrier pair per stage runs ahead across tile boundaries; one elected thread issues the
-// copies, no CTA-wide barrier exists after start-up.  Warp w owns rows 32 (w & 3) .. +32 and columns 64 (w >> 2) .. +64 of
-// the tile = 4 x 8 DMMA m8n8k4 tiles (64 FP64 accumulators per thread): per k-step of 4 frames 12 shared-memory loads feed
-// 32 DMMAs.  The k-steps take frames {0,2,4,6}, {1,3,5,7}, {8,..}, {9,..} of the stage: with the 128-byte swizzle (16-byte
-// chunk index ^ (frame & 7)) the four rows of a fragment load then fall into four different bank groups, so every LDS.64 is
-// conflict-free.  Warps whose 32 x 64 piece lies under the diagonal 64-block or beyond G skip the math, and a warp whose
-// columns end early (the last column block) runs the narrow instantiation of the k-step (2 or 4 of the 8 column tiles); the
-// two warps of a sub-partition are the two column halves of one row strip, so such savings shorten the tile.  The
-// accumulators go back as fire-and-forget FP64 reductions (RED.E.ADD.F64): every element is touched by exactly one thread
-// per launch and launches are stream-ordered, so the result is deterministic.
+// cov_syrk_kernel is a persistent kernel, ONE CTA of 8 warps per SM.  Work unit = one 128 x 128 tile of one site's sumsq, or
+// one 128 x 64 half of it; the host deals the units out longest-first (LPT) into one list per CTA, the cheapest tiles cut in
+// halves so that the tail is short.  For every 16 frames the two operands — 128 (+4) columns of D each — arrive in shared
+// memory as TWO TMA tiled copies (cp.async.bulk.tensor.3d, SASS UTMALDG; box = 132 columns x 1 site x 16 frames: rows of
+// 1056 contiguous bytes) of a tensor map over D; frames beyond the batch and columns beyond Gp are zero-filled by the TMA
+// unit, so the loop has no bounds.  The 132-column box makes the shared-memory row pitch 1056 B = 264 words == 8 (mod 32),
+// which puts the four frames of a DMMA fragment load into four different bank groups: every LDS.64 is conflict-free without
+// any swizzle.  (History, all at 19-21 TFLOP/s: 64 x 64 tiles staged by cp.async; 128 x 64 and 128 x 128 tiles fed by
+// sixteen 16-column boxes with 128-byte swizzle per stage — ncu put 26 % of the stall samples on the full-barrier wait with
+// L2 at 6 %: 256 row requests of 128 B per stage is more than the TMA unit turns around.)  A ring of 5 stages with a full /
+// empty mbarrier pair per stage runs ahead across tile boundaries; one elected thread issues the copies, no CTA-wide
+// barrier exists after start-up.  Warp w owns rows 32 (w & 3) .. +32 and columns 64 (w >> 2) .. +64 of the tile = 4 x 8
+// DMMA m8n8k4 tiles (64 FP64 accumulators per thread): per k-step of 4 frames 12 shared-memory loads feed 32 DMMAs.  Warps
+// whose 32 x 64 piece lies under the diagonal 64-block, beyond G, or in the half the unit does not cover skip the math, and
+// a warp whose columns end early (the last column block) runs the narrow instantiation of the k-step (2 or 4 of the 8
+// column tiles); the two warps of a sub-partition are the two column halves of one row strip, so such savings shorten the
+// unit.  The accumulators go back as fire-and-forget FP64 reductions (RED.E.ADD.F64): every element is touched by exactly one
+// thread per launch and launches are stream-ordered, so the result is deterministic.
 constexpr int kCovBlk = 64;        // granularity of the stored upper triangle
 constexpr int kSyrkTile = 128;     // tile edge
 constexpr int kSyrkK = 16;         // frames per stage
 constexpr int kSyrkStages = 5;
-constexpr int kSyrkBox = 16;       // columns per TMA box: 128 bytes, the swizzle span
-constexpr int kSyrkBoxBytes = kSyrkBox * kSyrkK * 8;                              // 2048
-constexpr int kSyrkOperandBytes = kSyrkTile / kSyrkBox * kSyrkBoxBytes;           // 16384: 128 columns x 16 frames
-constexpr int kSyrkStageBytes = 2 * kSyrkOperandBytes;                            // 32768
+constexpr int kSyrkBoxCols = 132;  // columns per TMA box: the tile's 128 + 4, for a bank-conflict-free row pitch
+constexpr int kSyrkPitch = kSyrkBoxCols * 8;                                      // 1056 B
+constexpr int kSyrkOperandBytes = kSyrkPitch * kSyrkK;                            // 16896
+constexpr int kSyrkStageBytes = 2 * kSyrkOperandBytes;                            // 33792
 constexpr int kSyrkThreads = 256;
-constexpr size_t kSyrkSmem = (size_t)kSyrkStages * kSyrkStageBytes + 1024;        // + room to align the ring to 1024 B
+constexpr size_t kSyrkSmem = (size_t)kSyrkStages * kSyrkStageBytes + 128;         // + room to align the ring to 128 B
+constexpr int kSyrkColPad = 16;    // D's columns are padded to a multiple of this (16-byte aligned rows for the tensor map)
 
-int64_t cov_padded_cols(int G) { return ((int64_t)G + kSyrkBox - 1) / kSyrkBox * kSyrkBox; }
+int64_t cov_padded_cols(int G) { return ((int64_t)G + kSyrkColPad - 1) / kSyrkColPad * kSyrkColPad; }
 int64_t cov_centred_doubles(int n_frames, int S, int G) { return (int64_t)n_frames * S * cov_padded_cols(G); }
 
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
@@ -536,33 +538,28 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
                : "memory");
 }
 
-// one k-step (4 frames) of a warp: 4 row tiles x kNJ column tiles
+// one k-step (4 frames) of a warp: 4 row tiles x kNJ column tiles.  a_addr / b_addr: this thread's element (frame tig of the
+// k-step, column gid) of the warp's first row / column tile
 template <int kNJ>
-__device__ __forceinline__ void syrk_kstep(double (&acc)[4][8][2], uint32_t a_base, uint32_t b_base, int q, const uint32_t (&t_off)[2][2]) {
+__device__ __forceinline__ void syrk_kstep(double (&acc)[4][8][2], uint32_t a_addr, uint32_t b_addr) {
   double a[4], b[kNJ];
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const uint32_t ad = a_base + (i >> 1) * kSyrkBoxBytes + (q >> 1) * 1024 + t_off[q & 1][i & 1];
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[i]) : "r"(ad));
-  }
+  for (int i = 0; i < 4; i++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[i]) : "r"(a_addr + i * 64));
 #pragma unroll
-  for (int j = 0; j < kNJ; j++) {
-    const uint32_t ad = b_base + (j >> 1) * kSyrkBoxBytes + (q >> 1) * 1024 + t_off[q & 1][j & 1];
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b[j]) : "r"(ad));
-  }
+  for (int j = 0; j < kNJ; j++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b[j]) : "r"(b_addr + j * 64));
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < kNJ; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
 }
 
-// tile = s * 65536 + bi * 256 + bj  (128-blocks; bi <= bj)
+// unit = halves << 28 | s << 16 | bi << 8 | bj  (128-blocks, bi <= bj; halves: bit 0 = columns 0..63, bit 1 = columns 64..127)
 __global__ void __launch_bounds__(kSyrkThreads, 1)
 cov_syrk_kernel(const __grid_constant__ CUtensorMap dmap, int n_frames, double* __restrict__ buf, int S, int G,
-                const int* __restrict__ sched_off, const int* __restrict__ sched_tile) {
+                const int* __restrict__ sched_off, const int* __restrict__ sched_unit) {
   extern __shared__ unsigned char syrk_smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kSyrkStages], empty_bar[kSyrkStages];
-  unsigned char* ring = syrk_smem_raw + ((1024u - (smem_addr(syrk_smem_raw) & 1023u)) & 1023u);   // the swizzle wants 1024 B
+  unsigned char* ring = syrk_smem_raw + ((128u - (smem_addr(syrk_smem_raw) & 127u)) & 127u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const int strip = warp & 3, half = warp >> 2;
@@ -577,54 +574,42 @@ cov_syrk_kernel(const __grid_constant__ CUtensorMap dmap, int n_frames, double* 
   }
   __syncthreads();
 
-  const int t_begin = sched_off[blockIdx.x], my_tiles = sched_off[blockIdx.x + 1] - t_begin;
+  const int u_begin = sched_off[blockIdx.x], my_units = sched_off[blockIdx.x + 1] - u_begin;
   const int k_stages = (n_frames + kSyrkK - 1) / kSyrkK;
-  const long long total = (long long)my_tiles * k_stages;   // stages this CTA consumes
+  const long long total = (long long)my_units * k_stages;   // stages this CTA consumes
   if (total == 0) return;
   // producer (thread 0): stage n of this CTA's sequence
   auto issue = [&](long long n) {
-    const int local_tile = (int)(n / k_stages);
-    const int ks = (int)(n - (long long)local_tile * k_stages);
-    const int tile = sched_tile[t_begin + local_tile];
-    const int s = tile >> 16, bi = (tile >> 8) & 255, bj = tile & 255;
+    const int local = (int)(n / k_stages);
+    const int ks = (int)(n - (long long)local * k_stages);
+    const int unit = sched_unit[u_begin + local];
+    const int halves = (unit >> 28) & 3, s = (unit >> 16) & 0xfff, bi = (unit >> 8) & 255, bj = unit & 255;
     const int st = (int)(n % kSyrkStages);
     unsigned char* dst = ring + (size_t)st * kSyrkStageBytes;
-    mbar_expect_tx(&full_bar[st], bi == bj ? kSyrkOperandBytes : kSyrkStageBytes);
-#pragma unroll
-    for (int j = 0; j < kSyrkTile / kSyrkBox; j++) tma_load_3d(dst + j * kSyrkBoxBytes, &dmap, bi * kSyrkTile + j * kSyrkBox, s, ks * kSyrkK, &full_bar[st]);
-    if (bi != bj) {
-#pragma unroll
-      for (int j = 0; j < kSyrkTile / kSyrkBox; j++)
-        tma_load_3d(dst + kSyrkOperandBytes + j * kSyrkBoxBytes, &dmap, bj * kSyrkTile + j * kSyrkBox, s, ks * kSyrkK, &full_bar[st]);
-    }
+    const bool diag = bi == bj;   // B's columns are inside A's
+    mbar_expect_tx(&full_bar[st], diag ? kSyrkOperandBytes : kSyrkStageBytes);
+    tma_load_3d(dst, &dmap, bi * kSyrkTile, s, ks * kSyrkK, &full_bar[st]);
+    if (!diag) tma_load_3d(dst + kSyrkOperandBytes, &dmap, bj * kSyrkTile + (halves == 2 ? 64 : 0), s, ks * kSyrkK, &full_bar[st]);
   };
   if (threadIdx.x == 0) {
     for (long long n = 0; n < kSyrkStages - 1 && n < total; n++) issue(n);
   }
 
-  // per-thread part of a fragment address inside a box: row (p + 2 tig) of the k-step with parity p, the swizzled 16-byte
-  // chunk of column 8 e + gid (e = low bit of the 8-column tile index), and the half of the chunk
-  uint32_t t_off[2][2];
-#pragma unroll
-  for (int p = 0; p < 2; p++)
-#pragma unroll
-    for (int e = 0; e < 2; e++) {
-      const int row = p + 2 * tig;
-      const int chunk = (4 * e + (gid >> 1)) ^ (row & 7);
-      t_off[p][e] = (uint32_t)(row * 128 + chunk * 16 + (gid & 1) * 8);
-    }
   const uint32_t ring_addr = smem_addr(ring);
+  const uint32_t t_off = (uint32_t)(tig * kSyrkPitch + gid * 8);   // this thread's element of a fragment: frame tig, column gid
 
   double acc[4][8][2];
   long long n = 0;
-  for (int lt = 0; lt < my_tiles; lt++) {
-    const int tile = sched_tile[t_begin + lt];
-    const int s = tile >> 16, bi = (tile >> 8) & 255, bj = tile & 255;
+  for (int lu = 0; lu < my_units; lu++) {
+    const int unit = sched_unit[u_begin + lu];
+    const int halves = (unit >> 28) & 3, s = (unit >> 16) & 0xfff, bi = (unit >> 8) & 255, bj = unit & 255;
     const int wr0 = bi * kSyrkTile + 32 * strip, wc0 = bj * kSyrkTile + 64 * half;
-    // this warp's 32 x 64 piece: inside G, and not below the diagonal 64-block; column tiles of 8 that hold real columns
-    const bool active = wr0 < G && wc0 < G && (wr0 / kCovBlk) <= (wc0 / kCovBlk);
-    const int nj = active ? min(8, (G - wc0 + 7) / 8) : 0;
-    const uint32_t b_operand = bi == bj ? 0u : (uint32_t)kSyrkOperandBytes;   // diagonal tile: B is the A operand
+    // this warp's 32 x 64 piece: in a half the unit covers, inside G, and not below the diagonal 64-block
+    const bool active = ((halves >> half) & 1) && wr0 < G && wc0 < G && (wr0 / kCovBlk) <= (wc0 / kCovBlk);
+    const int nj = active ? min(8, (G - wc0 + 7) / 8) : 0;   // column tiles of 8 that hold real columns
+    // where this warp's B columns sit in the stage: inside the A operand on a diagonal tile, else in the B operand, whose
+    // first column is the tile's column 64 when the unit covers only the second half
+    const uint32_t b_off = bi == bj ? (uint32_t)(64 * half * 8) : (uint32_t)(kSyrkOperandBytes + (halves == 2 ? 0 : 64 * half * 8));
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -640,17 +625,17 @@ cov_syrk_kernel(const __grid_constant__ CUtensorMap dmap, int n_frames, double* 
       __syncwarp();
       const int st = (int)(n % kSyrkStages);
       mbar_wait(&full_bar[st], (uint32_t)((n / kSyrkStages) & 1));
-      const uint32_t a_base = ring_addr + (uint32_t)st * kSyrkStageBytes + (uint32_t)strip * 2 * kSyrkBoxBytes;
-      const uint32_t b_base = ring_addr + (uint32_t)st * kSyrkStageBytes + b_operand + (uint32_t)half * 4 * kSyrkBoxBytes;
+      const uint32_t a_addr = ring_addr + (uint32_t)st * kSyrkStageBytes + (uint32_t)(32 * strip * 8) + t_off;
+      const uint32_t b_addr = ring_addr + (uint32_t)st * kSyrkStageBytes + b_off + t_off;
       if (nj > 4) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) syrk_kstep<8>(acc, a_base, b_base, q, t_off);
+        for (int q = 0; q < 4; q++) syrk_kstep<8>(acc, a_addr + q * 4 * kSyrkPitch, b_addr + q * 4 * kSyrkPitch);
       } else if (nj > 2) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) syrk_kstep<4>(acc, a_base, b_base, q, t_off);
+        for (int q = 0; q < 4; q++) syrk_kstep<4>(acc, a_addr + q * 4 * kSyrkPitch, b_addr + q * 4 * kSyrkPitch);
       } else if (nj > 0) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) syrk_kstep<2>(acc, a_base, b_base, q, t_off);
+        for (int q = 0; q < 4; q++) syrk_kstep<2>(acc, a_addr + q * 4 * kSyrkPitch, b_addr + q * 4 * kSyrkPitch);
       }
       // every read of the stage is done (the values are in registers): hand it back to the producer
       __syncwarp();
@@ -691,13 +676,30 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// The tiles of all sites dealt out to `ctas` lists, longest first (LPT): cost = the busiest sub-partition's DMMA count.
+// The units of all sites dealt out to `ctas` lists, longest first (LPT): cost = the busiest sub-partition's DMMA count per
+// k-step (in column tiles) + a fixed cost for walking the stages.  The cheapest tiles — about two rounds' worth — are cut
+// into their two column halves, so the lists can be evened out to within half a tile.
 // One schedule per (device, S, G), built on first use and kept on the device.
 struct SyrkSchedule {
   int S = 0, G = 0, ctas = 0;
   int* d_off = nullptr;    // [ctas + 1]
-  int* d_tile = nullptr;   // [n_tiles]
+  int* d_unit = nullptr;   // [n_units]
 };
+static int syrk_unit_cost(int G, int bi, int bj, int halves) {
+  int cost = 0;   // max over the 4 row strips (= sub-partitions) of the column tiles its two warps compute
+  for (int strip = 0; strip < 4; strip++) {
+    int c = 0;
+    for (int half = 0; half < 2; half++) {
+      const int wr0 = bi * kSyrkTile + 32 * strip, wc0 = bj * kSyrkTile + 64 * half;
+      if (((halves >> half) & 1) && wr0 < G && wc0 < G && wr0 / kCovBlk <= wc0 / kCovBlk) {
+        const int nj = std::min(8, (G - wc0 + 7) / 8);
+        c += nj > 4 ? 8 : nj > 2 ? 4 : 2;
+      }
+    }
+    cost = std::max(cost, c);
+  }
+  return cost;
+}
 static const SyrkSchedule* syrk_schedule(int S, int G, int ctas) {
   static std::mutex mu;
   static std::vector<SyrkSchedule> cache[16];
@@ -706,34 +708,35 @@ static const SyrkSchedule* syrk_schedule(int S, int G, int ctas) {
   for (auto& e : mine)
     if (e.S == S && e.G == G && e.ctas == ctas) return &e;
   const int nb = (G + kSyrkTile - 1) / kSyrkTile;
-  struct T { int id; int cost; };
-  std::vector<T> tiles;
+  struct U { int id; int cost; };
+  std::vector<U> units;
   for (int s = 0; s < S; s++)
     for (int bi = 0; bi < nb; bi++)
       for (int bj = bi; bj < nb; bj++) {
-        int cost = 0;   // max over the 4 row strips (= sub-partitions) of the column tiles its two warps compute
-        for (int strip = 0; strip < 4; strip++) {
-          int c = 0;
-          for (int half = 0; half < 2; half++) {
-            const int wr0 = bi * kSyrkTile + 32 * strip, wc0 = bj * kSyrkTile + 64 * half;
-            if (wr0 < G && wc0 < G && wr0 / kCovBlk <= wc0 / kCovBlk) {
-              const int nj = std::min(8, (G - wc0 + 7) / 8);
-              c += nj > 4 ? 8 : nj > 2 ? 4 : 2;
-            }
-          }
-          cost = std::max(cost, c);
-        }
-        tiles.push_back({(s << 16) | (bi << 8) | bj, cost + 1});   // + 1: the fixed cost of walking the stages
+        const int c = syrk_unit_cost(G, bi, bj, 3);
+        if (c > 0) units.push_back({(3 << 28) | (s << 16) | (bi << 8) | bj, c + 1});
       }
-  std::stable_sort(tiles.begin(), tiles.end(), [](const T& a, const T& b) { return a.cost > b.cost; });
+  std::stable_sort(units.begin(), units.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
+  // cut the cheapest tiles in halves
+  const size_t n_split = std::min(units.size(), (size_t)2 * ctas);
+  std::vector<U> tail(units.end() - (long)n_split, units.end());
+  units.resize(units.size() - n_split);
+  for (const U& t : tail) {
+    const int bi = (t.id >> 8) & 255, bj = t.id & 255;
+    for (int h = 1; h <= 2; h++) {
+      const int c = syrk_unit_cost(G, bi, bj, h);
+      if (c > 0) units.push_back({(t.id & 0x0fffffff) | (h << 28), c + 1});
+    }
+  }
+  std::stable_sort(units.begin(), units.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
   std::vector<std::vector<int>> lists((size_t)ctas);
   std::vector<long long> load((size_t)ctas, 0);
-  for (const T& t : tiles) {
+  for (const U& u : units) {
     int best = 0;
     for (int c = 1; c < ctas; c++)
       if (load[(size_t)c] < load[(size_t)best]) best = c;
-    lists[(size_t)best].push_back(t.id);
-    load[(size_t)best] += t.cost;
+    lists[(size_t)best].push_back(u.id);
+    load[(size_t)best] += u.cost;
   }
   std::vector<int> off((size_t)ctas + 1, 0), flat;
   for (int c = 0; c < ctas; c++) {
@@ -742,9 +745,9 @@ static const SyrkSchedule* syrk_schedule(int S, int G, int ctas) {
   }
   SyrkSchedule e;
   e.S = S; e.G = G; e.ctas = ctas;
-  if (cudaMalloc(&e.d_off, sizeof(int) * off.size()) != cudaSuccess || cudaMalloc(&e.d_tile, sizeof(int) * std::max<size_t>(1, flat.size())) != cudaSuccess ||
+  if (cudaMalloc(&e.d_off, sizeof(int) * off.size()) != cudaSuccess || cudaMalloc(&e.d_unit, sizeof(int) * std::max<size_t>(1, flat.size())) != cudaSuccess ||
       cudaMemcpy(e.d_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(e.d_tile, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaMemcpy(e.d_unit, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
     return nullptr;
   }
   mine.push_back(e);
@@ -754,24 +757,24 @@ static const SyrkSchedule* syrk_schedule(int S, int G, int ctas) {
 cudaError_t launch_cov_accumulate(const float* dE, int n_frames, double* buf, float* compat, double* centred_scratch, int S,
                                   int G, cudaStream_t st) {
   if (n_frames <= 0) return cudaSuccess;
-  if (S >= 32768 || (G + kSyrkTile - 1) / kSyrkTile > 255) return cudaErrorInvalidValue;
+  if (S >= 4096 || (G + kSyrkTile - 1) / kSyrkTile > 255) return cudaErrorInvalidValue;
   const int Gp = (int)cov_padded_cols(G);
   const int SG = S * G;
   const int sm_count = cached_sm_count();
   dim3 cgrid((S * Gp + 255) / 256, std::max(1, std::min(n_frames, 8 * sm_count / std::max(1, (S * Gp + 255) / 256))));
   cov_centre_kernel<<<cgrid, 256, 0, st>>>(dE, n_frames, buf, S, G, Gp, centred_scratch);
   cov_sum_kernel<<<(SG + 127) / 128, 128, 0, st>>>(dE, n_frames, buf, SG, G, compat);
-  // tensor map over D [frame][site][Gp] (innermost first), box = 16 columns x 1 site x 16 frames, 128-byte swizzle,
+  // tensor map over D [frame][site][Gp] (innermost first), box = 132 columns x 1 site x 16 frames, no swizzle,
   // out-of-range elements read as zero
   EncodeTiledFn encode = encode_tiled_fn();
   if (!encode) return cudaErrorNotSupported;
   CUtensorMap map;
   const cuuint64_t dims[3] = {(cuuint64_t)Gp, (cuuint64_t)S, (cuuint64_t)n_frames};
   const cuuint64_t strides[2] = {(cuuint64_t)Gp * 8, (cuuint64_t)S * Gp * 8};
-  const cuuint32_t box[3] = {(cuuint32_t)kSyrkBox, 1, (cuuint32_t)kSyrkK};
+  const cuuint32_t box[3] = {(cuuint32_t)kSyrkBoxCols, 1, (cuuint32_t)kSyrkK};
   const cuuint32_t estr[3] = {1, 1, 1};
   if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, centred_scratch, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
     return cudaErrorInvalidValue;
   }
   const int nb = (G + kSyrkTile - 1) / kSyrkTile;
@@ -781,7 +784,7 @@ cudaError_t launch_cov_accumulate(const float* dE, int n_frames, double* buf, fl
   if (!sched) return cudaErrorMemoryAllocation;
   static size_t granted[16] = {};
   ensure_dynamic_smem(cov_syrk_kernel, kSyrkSmem, granted);
-  cov_syrk_kernel<<<grid, kSyrkThreads, kSyrkSmem, st>>>(map, n_frames, buf, S, G, sched->d_off, sched->d_tile);
+  cov_syrk_kernel<<<grid, kSyrkThreads, kSyrkSmem, st>>>(map, n_frames, buf, S, G, sched->d_off, sched->d_unit);
   return cudaGetLastError();
 }
 
