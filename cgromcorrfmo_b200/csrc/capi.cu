@@ -229,6 +229,7 @@ struct cgc_context {
   bool cov_bound = false;
   bool shift_set = false;
   float* d_compat = nullptr;  // float32 [2][S*G]
+  bool compat_on = false;     // option "mtx_compat": keep the reference's literal float32 sums while running
   double* d_centred = nullptr;  // scratch: centred FP64 rows of the batch being accumulated
   int64_t centred_frames = 0;
   // rows waiting for K3: the streaming loop gathers the float32 rows of small batches here and runs the Correlate kernels
@@ -816,7 +817,7 @@ void flush_cov_rows(cgc_context* c, cudaStream_t st) {
   const int n = (int)c->cov_rows_pending;
   {
     ScopedKernelTimer t(c, 3, st);
-    CUDA_OK(launch_cov_accumulate(c->d_cov_rows, n, c->d_cov, c->d_compat, centred_scratch(c, n), sys.n_sites, sys.num_tot, st));
+    CUDA_OK(launch_cov_accumulate(c->d_cov_rows, n, c->d_cov, c->compat_on ? c->d_compat : nullptr, centred_scratch(c, n), sys.n_sites, sys.num_tot, st));
   }
   c->launches += 3;
   c->cov_rows_pending = 0;
@@ -846,7 +847,7 @@ void accumulate_rows(cgc_context* c, const float* d_dE, int n_frames, cudaStream
   const int64_t sg = (int64_t)sys.n_sites * sys.num_tot;
   if (n_frames >= kCovGather && c->cov_rows_pending == 0) {
     ScopedKernelTimer t(c, 3, st);
-    CUDA_OK(launch_cov_accumulate(d_dE, n_frames, c->d_cov, c->d_compat, centred_scratch(c, n_frames), sys.n_sites, sys.num_tot, st));
+    CUDA_OK(launch_cov_accumulate(d_dE, n_frames, c->d_cov, c->compat_on ? c->d_compat : nullptr, centred_scratch(c, n_frames), sys.n_sites, sys.num_tot, st));
     c->launches += 3;
     return;
   }
@@ -946,6 +947,7 @@ void open_common(cgc_context* c, const char* structure_gro = nullptr) {
   }
   resolve_atoms(c);
   c->n_sites = c->L.n_chromo;
+  c->compat_on = false;
   c->cov_opt = -1;
   c->batch_frames = 0;
   if (c->L.n_chromo < 1) throw InputFileMalformed("no BCL/BCX residue in the trajectory: nothing to excite");
@@ -1171,6 +1173,8 @@ int cgc_set_option(cgc_context* ctx, const char* key, double value) {
       ctx->cov_opt = value != 0.0 ? 1 : 0;
     } else if (k == "profile") {
       ctx->profile = value != 0.0;
+    } else if (k == "mtx_compat") {
+      ctx->compat_on = value != 0.0;
     } else if (k == "batch_frames") {
       if (value < 1 || value > 65535) throw std::invalid_argument("batch_frames must be within 1..65535");
       ctx->batch_frames = (int)value;
@@ -1192,6 +1196,7 @@ double cgc_get_option(const cgc_context* ctx, const char* key) {
   if (!ctx || !key || !ctx->opened) return NAN;
   std::string k(key);
   if (k == "sites") return ctx->n_sites;
+  if (k == "mtx_compat") return ctx->compat_on ? 1 : 0;
   if (k == "covariance") return ctx->device >= 0 && ctx->dev_static ? (cov_enabled(ctx) ? 1 : 0) : ctx->cov_opt;
   if (k == "batch_frames") return ctx->batch_frames > 0 ? ctx->batch_frames : default_batch(ctx);
   if (k == "stage_threads") return ctx->pool ? ctx->pool->threads() : ctx->stage_threads;
@@ -1690,7 +1695,7 @@ int cgc_cov_accumulate_device(cgc_context* ctx, const float* d_dE_kcal, int n_fr
     }
     {
       ScopedKernelTimer t(ctx, 3, st);
-      CUDA_OK(launch_cov_accumulate(d_dE_kcal, n_frames, ctx->d_cov, ctx->d_compat, centred_scratch(ctx, n_frames),
+      CUDA_OK(launch_cov_accumulate(d_dE_kcal, n_frames, ctx->d_cov, ctx->compat_on ? ctx->d_compat : nullptr, centred_scratch(ctx, n_frames),
                                     ctx->sys.n_sites, ctx->sys.num_tot, st));
     }
     ctx->launches += 3;
@@ -2400,6 +2405,10 @@ int cgc_write_mtx(cgc_context* ctx, const char* path, int compat) {
         return CGC_OK;
       }
     } else {
+      if (!ctx->compat_on) {
+        throw std::invalid_argument("the literal .mtx needs the float32 sums of every frame: set the option \"mtx_compat\" "
+                                    "(traj2dEcsv --mtx-compat) before the first cgc_run");
+      }
       m.resize((size_t)S * G * G);
       // the reference's literal arithmetic (src/FMOparse.cpp:189-206 with dEsize == 0), float32 throughout
       CUDA_OK(cudaDeviceSynchronize());

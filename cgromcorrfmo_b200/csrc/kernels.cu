@@ -429,7 +429,8 @@ void launch_finish(double* acc, float* dE, int64_t n, cudaStream_t st) {
 // 64-block column are computed and stored (kCovBlk; finalize mirrors them).
 //
 // cov_centre_kernel writes the centred rows D = x - c in FP64 into a scratch matrix [frame][site][Gp], Gp = G rounded up to
-// 16 with zero pads; cov_sum_kernel adds n, sum(x-c) and the reference's two float32 running sums.
+// 16 with zero pads, and partial column sums that cov_sum_finish_kernel adds (with n) in a fixed order; cov_compat_kernel
+// keeps the reference's two float32 running sums when the literal .mtx is wanted.
 // cov_syrk_kernel is a persistent kernel, ONE CTA of 8 warps per SM.  Work unit = one 128 x 128 tile of one site's sumsq, or
 // one 128 x 64 half of it; the host deals the units out longest-first (LPT) into one list per CTA, the cheapest tiles cut in
 // halves so that the tail is short.  For every 16 frames the two operands — 128 (+4) columns of D each — arrive in shared
@@ -441,12 +442,13 @@ void launch_finish(double* acc, float* dE, int64_t n, cudaStream_t st) {
 // sixteen 16-column boxes with 128-byte swizzle per stage — ncu put 26 % of the stall samples on the full-barrier wait with
 // L2 at 6 %: 256 row requests of 128 B per stage is more than the TMA unit turns around.)  A ring of 5 stages with a full /
 // empty mbarrier pair per stage runs ahead across tile boundaries; one elected thread issues the copies, no CTA-wide
-// barrier exists after start-up.  Warp w owns rows 32 (w & 3) .. +32 and columns 64 (w >> 2) .. +64 of the tile = 4 x 8
-// DMMA m8n8k4 tiles (64 FP64 accumulators per thread): per k-step of 4 frames 12 shared-memory loads feed 32 DMMAs.  Warps
-// whose 32 x 64 piece lies under the diagonal 64-block, beyond G, or in the half the unit does not cover skip the math, and
-// a warp whose columns end early (the last column block) runs the narrow instantiation of the k-step (2 or 4 of the 8
-// column tiles); the two warps of a sub-partition are the two column halves of one row strip, so such savings shorten the
-// unit.  The accumulators go back as fire-and-forget FP64 reductions (RED.E.ADD.F64): every element is touched by exactly one
+// barrier exists after start-up.  16 warps: warp w owns rows 32 (w & 3) .. +32 and columns 32 (w >> 2) .. +32 of the tile = 4 x 4
+// DMMA m8n8k4 tiles (32 FP64 accumulators per thread): per k-step of 4 frames 8 shared-memory loads feed 16 DMMAs, and
+// every sub-partition holds four warps to hide them behind (with 8 warps of 32 x 64 ncu showed the DMMA pipe 78 % busy: one
+// or two warps per sub-partition do not cover their own LDS latency).  Warps whose piece lies under the diagonal 64-block,
+// beyond G, or in the half the unit does not cover skip the math, and a warp whose columns end early (the last column
+// block) runs a narrow instantiation of the k-step (1 or 2 of the 4 column tiles); the four warps of a sub-partition are
+// the four column quarters of one row strip, so such savings shorten the unit.  The accumulators go back as fire-and-forget FP64 reductions (RED.E.ADD.F64): every element is touched by exactly one
 // thread per launch and launches are stream-ordered, so the result is deterministic.
 constexpr int kCovBlk = 64;        // granularity of the stored upper triangle
 constexpr int kSyrkTile = 128;     // tile edge
@@ -456,12 +458,15 @@ constexpr int kSyrkBoxCols = 132;  // columns per TMA box: the tile's 128 + 4, f
 constexpr int kSyrkPitch = kSyrkBoxCols * 8;                                      // 1056 B
 constexpr int kSyrkOperandBytes = kSyrkPitch * kSyrkK;                            // 16896
 constexpr int kSyrkStageBytes = 2 * kSyrkOperandBytes;                            // 33792
-constexpr int kSyrkThreads = 256;
+constexpr int kSyrkThreads = 512;   // 16 warps: 4 row strips x 4 column quarters of 32 x 32
 constexpr size_t kSyrkSmem = (size_t)kSyrkStages * kSyrkStageBytes + 128;         // + room to align the ring to 128 B
 constexpr int kSyrkColPad = 16;    // D's columns are padded to a multiple of this (16-byte aligned rows for the tensor map)
 
 int64_t cov_padded_cols(int G) { return ((int64_t)G + kSyrkColPad - 1) / kSyrkColPad * kSyrkColPad; }
-int64_t cov_centred_doubles(int n_frames, int S, int G) { return (int64_t)n_frames * S * cov_padded_cols(G); }
+constexpr int kCentreChunksMax = 16;
+int64_t cov_centred_doubles(int n_frames, int S, int G) {   // D, then the partial column sums of cov_centre_kernel
+  return (int64_t)n_frames * S * cov_padded_cols(G) + (int64_t)kCentreChunksMax * S * G;
+}
 
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -479,33 +484,46 @@ void launch_cov_set_shift(const float* dE_row0, double* buf, int S, int G, cudaS
   cov_set_shift_kernel<<<(n + 255) / 256, 256, 0, st>>>(dE_row0, buf, n);
 }
 
-// D = x - c in FP64, [frame][site][Gp] with zero pads: one thread per element of the padded matrix
+// D = x - c in FP64, [frame][site][Gp] with zero pads, and the column sums of D: thread (ip, y) walks the frames y, y + Y, ...
+// of column ip and leaves its partial sum in part[y][column]; cov_sum_finish_kernel adds the Y partials in order.
 __global__ void cov_centre_kernel(const float* __restrict__ dE, int n_frames, const double* __restrict__ buf, int S, int G,
-                                  int Gp, double* __restrict__ centred) {
+                                  int Gp, double* __restrict__ centred, double* __restrict__ part) {
   const int ip = blockIdx.x * blockDim.x + threadIdx.x;   // index into the padded row
   const int SGp = S * Gp, SG = S * G;
   if (ip >= SGp) return;
   const int s = ip / Gp, g = ip - s * Gp;
-  const bool real = g < G;
-  const int i = s * G + (real ? g : 0);
-  const double c = real ? buf[1 + i] : 0.0;
-  for (int t = blockIdx.y; t < n_frames; t += gridDim.y) {
-    centred[(size_t)t * SGp + ip] = real ? (double)dE[(size_t)t * SG + i] - c : 0.0;
+  if (g >= G) {
+    for (int t = blockIdx.y; t < n_frames; t += gridDim.y) centred[(size_t)t * SGp + ip] = 0.0;
+    return;
   }
+  const int i = s * G + g;
+  const double c = buf[1 + i];
+  double sum = 0.0;
+  for (int t = blockIdx.y; t < n_frames; t += gridDim.y) {
+    const double d = (double)dE[(size_t)t * SG + i] - c;
+    centred[(size_t)t * SGp + ip] = d;
+    sum += d;
+  }
+  part[(size_t)blockIdx.y * SG + i] = sum;
 }
 
-// cov_sum_kernel: n, sum(x-c), and the two float32 running sums the reference's literal .mtx arithmetic needs
-// (src/FMOparse.cpp:173-175 with the zero stride of :193,202): sum_t x_i and sum_t x_0 x_j, added frame by frame in order
-// like the reference does (the loads of 8 frames are issued together; the adds keep their order).
-__global__ void cov_sum_kernel(const float* __restrict__ dE, int n_frames, double* __restrict__ buf, int SG, int G,
-                               float* __restrict__ compat /* [2][SG] or null */) {
+__global__ void cov_sum_finish_kernel(const double* __restrict__ part, int n_part, int n_frames, double* __restrict__ buf, int SG) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) buf[0] += (double)n_frames;
   if (i >= SG) return;
-  const double c = buf[1 + i];
   double sum = 0.0;
+  for (int y = 0; y < n_part; y++) sum += part[(size_t)y * SG + i];
+  buf[1 + SG + i] += sum;
+}
+
+// The two float32 running sums the reference's literal .mtx arithmetic needs (src/FMOparse.cpp:173-175 with the zero stride
+// of :193,202): sum_t x_i and sum_t x_0 x_j, added frame by frame in order like the reference does (the loads of 8 frames
+// are issued together; the adds keep their order).  Only launched when the "mtx_compat" option is on.
+__global__ void cov_compat_kernel(const float* __restrict__ dE, int n_frames, int SG, int G, float* __restrict__ compat /* [2][SG] */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= SG) return;
   const int i0 = (i / G) * G;  // column 0 of this site
-  float m32 = compat ? compat[i] : 0.f, p32 = compat ? compat[SG + i] : 0.f;
+  float m32 = compat[i], p32 = compat[SG + i];
   int t = 0;
   for (; t + 8 <= n_frames; t += 8) {
     float x[8], x0[8];
@@ -516,19 +534,17 @@ __global__ void cov_sum_kernel(const float* __restrict__ dE, int n_frames, doubl
     }
 #pragma unroll
     for (int u = 0; u < 8; u++) {
-      sum += (double)x[u] - c;
       m32 += x[u];
       p32 += __fmul_rn(x0[u], x[u]);
     }
   }
   for (; t < n_frames; t++) {
     const float x = dE[(size_t)t * SG + i];
-    sum += (double)x - c;
     m32 += x;
     p32 += __fmul_rn(dE[(size_t)t * SG + i0], x);
   }
-  buf[1 + SG + i] += sum;
-  if (compat) { compat[i] = m32; compat[SG + i] = p32; }
+  compat[i] = m32;
+  compat[SG + i] = p32;
 }
 
 // one box of the tensor map -> shared memory; coordinates (column, site, frame)
@@ -541,7 +557,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 // one k-step (4 frames) of a warp: 4 row tiles x kNJ column tiles.  a_addr / b_addr: this thread's element (frame tig of the
 // k-step, column gid) of the warp's first row / column tile
 template <int kNJ>
-__device__ __forceinline__ void syrk_kstep(double (&acc)[4][8][2], uint32_t a_addr, uint32_t b_addr) {
+__device__ __forceinline__ void syrk_kstep(double (&acc)[4][4][2], uint32_t a_addr, uint32_t b_addr) {
   double a[4], b[kNJ];
 #pragma unroll
   for (int i = 0; i < 4; i++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[i]) : "r"(a_addr + i * 64));
@@ -562,7 +578,7 @@ cov_syrk_kernel(const __grid_constant__ CUtensorMap dmap, int n_frames, double* 
   unsigned char* ring = syrk_smem_raw + ((128u - (smem_addr(syrk_smem_raw) & 127u)) & 127u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
-  const int strip = warp & 3, half = warp >> 2;
+  const int strip = warp & 3, quarter = warp >> 2, half = quarter >> 1;   // the 4 warps of a sub-partition share a row strip
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < kSyrkStages; i++) {
@@ -598,22 +614,23 @@ cov_syrk_kernel(const __grid_constant__ CUtensorMap dmap, int n_frames, double* 
   const uint32_t ring_addr = smem_addr(ring);
   const uint32_t t_off = (uint32_t)(tig * kSyrkPitch + gid * 8);   // this thread's element of a fragment: frame tig, column gid
 
-  double acc[4][8][2];
+  double acc[4][4][2];
   long long n = 0;
   for (int lu = 0; lu < my_units; lu++) {
     const int unit = sched_unit[u_begin + lu];
     const int halves = (unit >> 28) & 3, s = (unit >> 16) & 0xfff, bi = (unit >> 8) & 255, bj = unit & 255;
-    const int wr0 = bi * kSyrkTile + 32 * strip, wc0 = bj * kSyrkTile + 64 * half;
-    // this warp's 32 x 64 piece: in a half the unit covers, inside G, and not below the diagonal 64-block
+    const int wr0 = bi * kSyrkTile + 32 * strip, wc0 = bj * kSyrkTile + 32 * quarter;
+    // this warp's 32 x 32 piece: in a half the unit covers, inside G, and not below the diagonal 64-block
     const bool active = ((halves >> half) & 1) && wr0 < G && wc0 < G && (wr0 / kCovBlk) <= (wc0 / kCovBlk);
-    const int nj = active ? min(8, (G - wc0 + 7) / 8) : 0;   // column tiles of 8 that hold real columns
+    const int nj = active ? min(4, (G - wc0 + 7) / 8) : 0;   // column tiles of 8 that hold real columns
     // where this warp's B columns sit in the stage: inside the A operand on a diagonal tile, else in the B operand, whose
     // first column is the tile's column 64 when the unit covers only the second half
-    const uint32_t b_off = bi == bj ? (uint32_t)(64 * half * 8) : (uint32_t)(kSyrkOperandBytes + (halves == 2 ? 0 : 64 * half * 8));
+    const uint32_t b_off = bi == bj ? (uint32_t)(32 * quarter * 8)
+                                    : (uint32_t)(kSyrkOperandBytes + (32 * quarter - (halves == 2 ? 64 : 0)) * 8);
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-      for (int j = 0; j < 8; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
     for (int ks = 0; ks < k_stages; ks++, n++) {
       if (threadIdx.x == 0) {
         const long long nxt = n + kSyrkStages - 1;
@@ -627,15 +644,15 @@ cov_syrk_kernel(const __grid_constant__ CUtensorMap dmap, int n_frames, double* 
       mbar_wait(&full_bar[st], (uint32_t)((n / kSyrkStages) & 1));
       const uint32_t a_addr = ring_addr + (uint32_t)st * kSyrkStageBytes + (uint32_t)(32 * strip * 8) + t_off;
       const uint32_t b_addr = ring_addr + (uint32_t)st * kSyrkStageBytes + b_off + t_off;
-      if (nj > 4) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) syrk_kstep<8>(acc, a_addr + q * 4 * kSyrkPitch, b_addr + q * 4 * kSyrkPitch);
-      } else if (nj > 2) {
+      if (nj > 2) {
 #pragma unroll
         for (int q = 0; q < 4; q++) syrk_kstep<4>(acc, a_addr + q * 4 * kSyrkPitch, b_addr + q * 4 * kSyrkPitch);
-      } else if (nj > 0) {
+      } else if (nj > 1) {
 #pragma unroll
         for (int q = 0; q < 4; q++) syrk_kstep<2>(acc, a_addr + q * 4 * kSyrkPitch, b_addr + q * 4 * kSyrkPitch);
+      } else if (nj > 0) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) syrk_kstep<1>(acc, a_addr + q * 4 * kSyrkPitch, b_addr + q * 4 * kSyrkPitch);
       }
       // every read of the stage is done (the values are in registers): hand it back to the producer
       __syncwarp();
@@ -649,7 +666,7 @@ cov_syrk_kernel(const __grid_constant__ CUtensorMap dmap, int n_frames, double* 
         if (r >= G) continue;
         double* row = sumsq + (size_t)r * G;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < 4; j++) {
           const int c = wc0 + j * 8 + tig * 2;
           if (c < G) atomicAdd(row + c, acc[i][j][0]);
           if (c + 1 < G) atomicAdd(row + c + 1, acc[i][j][1]);
@@ -686,14 +703,14 @@ struct SyrkSchedule {
   int* d_unit = nullptr;   // [n_units]
 };
 static int syrk_unit_cost(int G, int bi, int bj, int halves) {
-  int cost = 0;   // max over the 4 row strips (= sub-partitions) of the column tiles its two warps compute
+  int cost = 0;   // max over the 4 row strips (= sub-partitions) of the column tiles its four warps compute
   for (int strip = 0; strip < 4; strip++) {
     int c = 0;
-    for (int half = 0; half < 2; half++) {
-      const int wr0 = bi * kSyrkTile + 32 * strip, wc0 = bj * kSyrkTile + 64 * half;
-      if (((halves >> half) & 1) && wr0 < G && wc0 < G && wr0 / kCovBlk <= wc0 / kCovBlk) {
-        const int nj = std::min(8, (G - wc0 + 7) / 8);
-        c += nj > 4 ? 8 : nj > 2 ? 4 : 2;
+    for (int quarter = 0; quarter < 4; quarter++) {
+      const int wr0 = bi * kSyrkTile + 32 * strip, wc0 = bj * kSyrkTile + 32 * quarter;
+      if (((halves >> (quarter >> 1)) & 1) && wr0 < G && wc0 < G && wr0 / kCovBlk <= wc0 / kCovBlk) {
+        const int nj = std::min(4, (G - wc0 + 7) / 8);
+        c += nj > 2 ? 4 : nj > 1 ? 2 : 1;
       }
     }
     cost = std::max(cost, c);
@@ -761,9 +778,11 @@ cudaError_t launch_cov_accumulate(const float* dE, int n_frames, double* buf, fl
   const int Gp = (int)cov_padded_cols(G);
   const int SG = S * G;
   const int sm_count = cached_sm_count();
-  dim3 cgrid((S * Gp + 255) / 256, std::max(1, std::min(n_frames, 8 * sm_count / std::max(1, (S * Gp + 255) / 256))));
-  cov_centre_kernel<<<cgrid, 256, 0, st>>>(dE, n_frames, buf, S, G, Gp, centred_scratch);
-  cov_sum_kernel<<<(SG + 127) / 128, 128, 0, st>>>(dE, n_frames, buf, SG, G, compat);
+  dim3 cgrid((S * Gp + 255) / 256, std::max(1, std::min(std::min(n_frames, kCentreChunksMax), 8 * sm_count / std::max(1, (S * Gp + 255) / 256))));
+  double* part = centred_scratch + (size_t)n_frames * S * Gp;
+  cov_centre_kernel<<<cgrid, 256, 0, st>>>(dE, n_frames, buf, S, G, Gp, centred_scratch, part);
+  cov_sum_finish_kernel<<<(SG + 255) / 256, 256, 0, st>>>(part, (int)cgrid.y, n_frames, buf, SG);
+  if (compat) cov_compat_kernel<<<(SG + 127) / 128, 128, 0, st>>>(dE, n_frames, SG, G, compat);
   // tensor map over D [frame][site][Gp] (innermost first), box = 132 columns x 1 site x 16 frames, no swizzle,
   // out-of-range elements read as zero
   EncodeTiledFn encode = encode_tiled_fn();

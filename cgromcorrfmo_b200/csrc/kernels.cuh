@@ -57,7 +57,8 @@ void launch_finish(double* acc, float* dE, int64_t n, cudaStream_t st);
 
 // K3: per-site shifted sums.  buf = [ n | c (S*G) | sum (S*G) | sumsq (S*G*G) ]
 void launch_cov_set_shift(const float* dE_row0, double* buf, int S, int G, cudaStream_t st);
-// centred_scratch: cov_centred_doubles(n_frames, S, G) doubles (the centred rows the SYRK consumes, columns padded to 16).
+// centred_scratch: cov_centred_doubles(n_frames, S, G) doubles (the centred rows the SYRK consumes, columns padded to 16,
+// and partial column sums).  compat == null: the reference's literal float32 sums are not kept.
 // Returns an error when the TMA tensor map cannot be built (driver entry point missing).
 int64_t cov_padded_cols(int G);
 int64_t cov_centred_doubles(int n_frames, int S, int G);

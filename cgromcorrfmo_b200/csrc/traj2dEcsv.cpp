@@ -161,6 +161,10 @@ static cgc_context* open_context(const Options& o, int device, bool announce, in
     *status = die(ctx, rc, "setting --sites");
     return nullptr;
   }
+  if (o.compat && (rc = cgc_set_option(ctx, "mtx_compat", 1)) != CGC_OK) {
+    *status = die(ctx, rc, "setting --mtx-compat");
+    return nullptr;
+  }
   if (o.no_mtx && (rc = cgc_set_option(ctx, "covariance", 0)) != CGC_OK) {
     *status = die(ctx, rc, "setting --no-mtx");
     return nullptr;

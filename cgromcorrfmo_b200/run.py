@@ -43,6 +43,8 @@ def traj2dEcsv(traj, top, itp, out, num_frames, sites=0, mtx_compat=False, chunk
         c.open(traj)
         if sites:
             c.set_option("sites", sites)
+        if mtx_compat:
+            c.set_option("mtx_compat", 1)
         if world > 1:
             c.set_option("stage_threads", c_threads)            # the ranks share the host cores
         total = min(int(num_frames), c.frame_count())          # stops cleanly where the reference would overrun

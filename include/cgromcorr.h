@@ -106,6 +106,8 @@ int64_t cgc_frame_atoms_offset(cgc_context *ctx, int64_t frame);
  * "stage_threads" host threads that copy trajectory text into the pinned staging ring (default min(16, cores); a process
  *                that runs one context per GPU divides its cores between them)
  * "profile"      0/1: time every hot-path kernel with CUDA events (see cgc_kernel_times)
+ * "mtx_compat"   0/1: also keep, frame by frame in order, the two float32 sums the reference's LITERAL `.mtx` arithmetic
+ *                uses (cgc_write_mtx with compat != 0 needs them); default 0
  * Must be set after cgc_open and before the first cgc_run. */
 int cgc_set_option(cgc_context *ctx, const char *key, double value);
 double cgc_get_option(const cgc_context *ctx, const char *key);
@@ -240,7 +242,8 @@ int cgc_parse_text(cgc_context *ctx, const char *text, int64_t nbytes, int *num_
 int cgc_write_time(const char *path, int truncate, const float *dE_kcal, int64_t rows, int num_tot);
 /* cgc_write_mtx writes sites*numTot lines of numTot values (src/FMOparse.cpp:208-221).  compat == 0: population
  * covariance in (kcal/mol)^2; compat != 0: the reference's literal arithmetic including its zero stride
- * (src/FMOparse.cpp:42,193,202), i.e. sum_t x_0 x_j / T^numTot - <x_i><x_j> in float32. */
+ * (src/FMOparse.cpp:42,193,202), i.e. sum_t x_0 x_j / T^numTot - <x_i><x_j> in float32 — needs the option "mtx_compat" set
+ * before the frames were run (CGC_ERR_ARG otherwise) and a single context (the float32 sums are sequential by nature). */
 int cgc_write_mtx(cgc_context *ctx, const char *path, int compat);
 
 #ifdef __cplusplus

@@ -273,6 +273,13 @@ def test_writers_match_reference_format(small_inputs, oracle_mod, capi_mod, tmp_
     with capi.Context(top, itp, 0) as c:
         c.open(traj)
         dE, done, _ = c.run(0, frames)
+        with pytest.raises(capi.CgcError):                    # the literal .mtx needs its float32 sums kept while running
+            c.write_mtx(str(tmp_path / "o_compat.mtx"), compat=True)
+    with capi.Context(top, itp, 0) as c:
+        c.open(traj)
+        c.set_option("mtx_compat", 1)
+        c.set_option("batch_frames", 2)                       # the sums carry across launches, in frame order
+        dE, done, _ = c.run(0, frames)
         capi.write_time(str(tmp_path / "o.time"), dE)
         assert open(tmp_path / "o.time").read() == O.format_time_rows(dE.reshape(-1, dE.shape[-1]))
         c.write_mtx(str(tmp_path / "o_compat.mtx"), compat=True)
