@@ -128,9 +128,64 @@ class CopyPool {
   std::vector<std::thread> th_;
 };
 
+// Page-locked host memory for the large buffers (staging ring, rows, sink): an anonymous mapping advised to use transparent
+// huge pages, touched by several threads, then registered with CUDA.  On the B200 box 128 MB cost 5 ms this way against
+// 50 ms for cudaHostAlloc (which pins 4 KiB page by page and holds a driver-wide lock while it does: a helper thread that
+// allocated the ring in the background stalled the streaming thread's launches for as long), at the same H2D rate
+// (profiles/r02_pinned_alloc.txt).  Falls back to cudaHostAlloc when the mapping cannot be registered.
+struct PinnedBlock {
+  char* p = nullptr;
+  void* map = nullptr;      // the mapping p lies in; null: cudaHostAlloc
+  size_t map_bytes = 0;
+};
+PinnedBlock pinned_alloc(size_t bytes) {
+  PinnedBlock b;
+  const size_t kHuge = (size_t)2 << 20;
+  if (bytes >= ((size_t)4 << 20)) {
+    const size_t len = ((bytes + kHuge - 1) / kHuge) * kHuge;
+    void* m = mmap(nullptr, len + kHuge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (m != MAP_FAILED) {
+      char* a = (char*)(((uintptr_t)m + kHuge - 1) & ~(uintptr_t)(kHuge - 1));
+      madvise(a, len, MADV_HUGEPAGE);
+      const int nt = (int)std::max<size_t>(1, std::min<size_t>(8, len / ((size_t)16 << 20)));
+      std::vector<std::thread> th;
+      for (int t = 0; t < nt; t++) {
+        const size_t lo = len / kHuge * t / nt * kHuge, hi = len / kHuge * (t + 1) / nt * kHuge;
+        th.emplace_back([a, lo, hi] { memset(a + lo, 0, hi - lo); });
+      }
+      for (auto& t : th) t.join();
+      if (cudaHostRegister(a, len, cudaHostRegisterPortable) == cudaSuccess) {
+        b.p = a;
+        b.map = m;
+        b.map_bytes = len + kHuge;
+        return b;
+      }
+      cudaGetLastError();
+      munmap(m, len + kHuge);
+    }
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    throw CudaError(std::string("cudaHostAlloc of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(cudaGetLastError()));
+  }
+  b.p = (char*)p;
+  return b;
+}
+void pinned_free(PinnedBlock& b) {
+  if (!b.p) return;
+  if (b.map) {
+    cudaHostUnregister(b.p);
+    munmap(b.map, b.map_bytes);
+  } else {
+    cudaFreeHost(b.p);
+  }
+  b = PinnedBlock();
+}
+
 // One slot of the streaming ring (cgc_context::kSlots of them): text in, dE out.
 struct Slot {
   char* h_text = nullptr;   // pinned staging (file path only)
+  PinnedBlock h_text_block, h_dE_block;
   char* d_text = nullptr;
   int64_t* d_off = nullptr;
   int64_t* h_off = nullptr;  // pinned
@@ -194,9 +249,6 @@ struct cgc_context {
   // computing) — the host thread only enqueues and drains
   static constexpr int kSlots = 6;
   static constexpr int kStageAhead = 3, kInFlight = 3;
-  // the pinned staging buffers of slots 1.. are page-locked by a helper thread while the first batches already run
-  std::thread host_alloc_thread;
-  std::atomic<int> host_ready{0};   // slots whose h_text exists; -1: the allocation failed
   Slot slot[kSlots];
   bool dev_pipeline = false;
   int alloc_batch = 0;
@@ -213,6 +265,7 @@ struct cgc_context {
   // hands it back once the bytes are in the file), kept across calls
   static constexpr int kSinkBufs = 6;
   char* sink_buf[kSinkBufs] = {};
+  PinnedBlock sink_block[kSinkBufs];
   cudaEvent_t sink_ev[kSinkBufs] = {};
   int64_t sink_cap = 0;
 
@@ -236,6 +289,7 @@ struct cgc_context {
   // once per kCovGather frames (their write-back touches all S*G*G sums, whatever the batch size)
   float* d_cov_rows = nullptr;
   int64_t cov_rows_cap = 0, cov_rows_pending = 0;
+  double host_cov_gather_s = 0, host_cov_flush_s = 0;   // host time spent enqueueing K3 work (CGC_TRACE)
 
   ~cgc_context();
 };
@@ -252,12 +306,10 @@ void release_text(cgc_context* c) {
 }
 
 void free_pipeline(cgc_context* c) {
-  if (c->host_alloc_thread.joinable()) c->host_alloc_thread.join();
-  c->host_ready.store(0);
   if (c->device < 0) return;
   cudaSetDevice(c->device);
   for (auto& s : c->slot) {
-    if (s.h_text) cudaFreeHost(s.h_text);
+    pinned_free(s.h_text_block);
     if (s.d_text) cudaFree(s.d_text);
     if (s.d_off) cudaFree(s.d_off);
     if (s.h_off) cudaFreeHost(s.h_off);
@@ -265,7 +317,7 @@ void free_pipeline(cgc_context* c) {
     if (s.d_sites) cudaFree(s.d_sites);
     if (s.d_acc) cudaFree(s.d_acc);
     if (s.d_dE) cudaFree(s.d_dE);
-    if (s.h_dE) cudaFreeHost(s.h_dE);
+    pinned_free(s.h_dE_block);
     if (s.d_ttext) cudaFree(s.d_ttext);
     if (s.d_rowoff) cudaFree(s.d_rowoff);
     if (s.h_tinfo) cudaFreeHost(s.h_tinfo);
@@ -279,7 +331,7 @@ void free_pipeline(cgc_context* c) {
     s.text_out_pending = false; s.staged_here = false; s.src = nullptr; s.nb = 0; s.frames = 0; s.out_frame = 0; s.busy = false;
   }
   for (int i = 0; i < cgc_context::kSinkBufs; i++) {
-    if (c->sink_buf[i]) cudaFreeHost(c->sink_buf[i]);
+    pinned_free(c->sink_block[i]);
     if (c->sink_ev[i]) cudaEventDestroy(c->sink_ev[i]);
     c->sink_buf[i] = nullptr;
     c->sink_ev[i] = nullptr;
@@ -523,7 +575,10 @@ void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_ho
   for (int si = 0; si < n_slots; si++) {
     Slot& s = c->slot[si];
     if (ring) CUDA_OK(cudaMalloc(&s.d_text, (size_t)text_bytes + 64));
-    if (need_host_text && si == 0) CUDA_OK(cudaHostAlloc(&s.h_text, (size_t)text_bytes + 64, cudaHostAllocDefault));
+    if (need_host_text) {
+      s.h_text_block = pinned_alloc((size_t)text_bytes + 64);
+      s.h_text = s.h_text_block.p;
+    }
     CUDA_OK(cudaMalloc(&s.d_off, sizeof(int64_t) * batch));
     CUDA_OK(cudaHostAlloc(&s.h_off, sizeof(int64_t) * batch, cudaHostAllocDefault));
     CUDA_OK(cudaMalloc(&s.d_xyz8, sizeof(float) * 3 * (size_t)sys.n_pad * batch));
@@ -532,7 +587,8 @@ void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_ho
     CUDA_OK(cudaMemsetAsync(s.d_acc, 0, sizeof(double) * sg * batch, c->st_comp));
     if (ring) {
       CUDA_OK(cudaMalloc(&s.d_dE, sizeof(float) * sg * batch));
-      CUDA_OK(cudaHostAlloc(&s.h_dE, sizeof(float) * sg * batch, cudaHostAllocDefault));
+      s.h_dE_block = pinned_alloc(sizeof(float) * (size_t)(sg * batch));
+      s.h_dE = (float*)s.h_dE_block.p;
     }
     CUDA_OK(cudaEventCreateWithFlags(&s.ev_copied, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
@@ -545,24 +601,6 @@ void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_ho
   c->alloc_batch = batch;
   c->alloc_text = text_bytes;
   c->alloc_slots = n_slots;
-  if (need_host_text) {
-    // the rest of the staging ring is page-locked while the first batches already stream (run_impl waits on host_ready)
-    c->host_ready.store(1);
-    const int dev = c->device;
-    c->host_alloc_thread = std::thread([c, dev, text_bytes] {
-      cudaSetDevice(dev);
-      for (int i = 1; i < cgc_context::kSlots; i++) {
-        if (cudaHostAlloc(&c->slot[i].h_text, (size_t)text_bytes + 64, cudaHostAllocDefault) != cudaSuccess) {
-          c->slot[i].h_text = nullptr;
-          c->host_ready.store(-1);
-          return;
-        }
-        c->host_ready.store(i + 1);
-      }
-    });
-  } else {
-    c->host_ready.store(cgc_context::kSlots);
-  }
 }
 
 CopyPool* copy_pool(cgc_context* c) {
@@ -674,9 +712,10 @@ class TextSink {
 void ensure_sink_bufs(cgc_context* c, int64_t cap) {
   if (c->sink_cap >= cap) return;
   for (int i = 0; i < cgc_context::kSinkBufs; i++) {
-    if (c->sink_buf[i]) CUDA_OK(cudaFreeHost(c->sink_buf[i]));
+    pinned_free(c->sink_block[i]);
     c->sink_buf[i] = nullptr;
-    CUDA_OK(cudaHostAlloc(&c->sink_buf[i], (size_t)cap, cudaHostAllocDefault));
+    c->sink_block[i] = pinned_alloc((size_t)cap);
+    c->sink_buf[i] = c->sink_block[i].p;
     if (!c->sink_ev[i]) CUDA_OK(cudaEventCreateWithFlags(&c->sink_ev[i], cudaEventDisableTiming));
   }
   c->sink_cap = cap;
@@ -856,10 +895,15 @@ void accumulate_rows(cgc_context* c, const float* d_dE, int n_frames, cudaStream
     CUDA_OK(cudaStreamSynchronize(st));
     ensure_cov_buffers(c, n_frames);
   }
+  auto wall = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = wall();
   CUDA_OK(cudaMemcpyAsync(c->d_cov_rows + c->cov_rows_pending * sg, d_dE, sizeof(float) * (size_t)(n_frames * sg),
                           cudaMemcpyDeviceToDevice, st));
   c->cov_rows_pending += n_frames;
+  const double t1 = wall();
   if (c->cov_rows_pending >= kCovGather) flush_cov_rows(c, st);
+  c->host_cov_gather_s += t1 - t0;
+  c->host_cov_flush_s += wall() - t1;
 }
 
 // K1 -> K2 -> finish (-> K3) for one batch whose text is already in d_text; everything on `st`
@@ -1286,6 +1330,7 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       sl.text_out_pending = false;
     }
     ctx->cov_rows_pending = 0;
+    ctx->host_cov_gather_s = ctx->host_cov_flush_s = 0;
     const int64_t sg = (int64_t)sys.n_sites * sys.num_tot;
     const bool want_rows = dE_kcal != nullptr || sink != nullptr;   // the text path keeps the rows for its host fallback
 
@@ -1348,10 +1393,6 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
         if (want == 0) return false;
       }
       Slot& s = ctx->slot[n_staged % K];
-      if (!direct) {   // the slot's pinned staging buffer may still be on its way (first pass over the ring only)
-        while (ctx->host_ready.load() >= 0 && ctx->host_ready.load() <= (int)(n_staged % K)) std::this_thread::yield();
-        if (ctx->host_ready.load() < 0) throw CudaError("cudaHostAlloc of the pinned staging ring failed");
-      }
       const FrameSpan& fa = ctx->frames[(size_t)f_begin];
       const FrameSpan& fb = ctx->frames[(size_t)(f_begin + want - 1)];
       const int64_t b0 = fa.atoms & ~(int64_t)15;
@@ -1495,9 +1536,10 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
     }
     if (trace) {
       fprintf(stderr, "cgc trace: %lld frames in %.1f ms (+ %.1f ms buffer set-up: ring %.1f, Correlate %.1f, text %.1f) | host thread: wait for staging %.1f, enqueue %.1f, "
-                      "wait for GPU %.1f, rows to caller %.1f, text D2H + queue %.1f ms | %d frames per batch, %d copier threads\n",
+                      "(of which K3 gather copies %.1f, K3 launches %.1f), wait for GPU %.1f, rows to caller %.1f, text D2H + queue %.1f ms | %d frames per batch, %d copier threads\n",
               (long long)delivered, (now() - t_call0) * 1e3, t_setup * 1e3, (t_setup1 - t_setup0) * 1e3, (t_setup2 - t_setup1) * 1e3,
-              (t_setup - (t_setup2 - t_setup0)) * 1e3, t_wait_stage * 1e3, t_enqueue * 1e3, t_wait_gpu * 1e3,
+              (t_setup - (t_setup2 - t_setup0)) * 1e3, t_wait_stage * 1e3, t_enqueue * 1e3, ctx->host_cov_gather_s * 1e3,
+              ctx->host_cov_flush_s * 1e3, t_wait_gpu * 1e3,
               t_rows * 1e3, t_text * 1e3, B, pool->threads());
     }
     int flags = 0;
