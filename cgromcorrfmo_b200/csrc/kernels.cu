@@ -554,6 +554,34 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
                : "memory");
 }
 
+// Which 32 x 32 piece (row strip, column quarter) of its unit a warp computes; false: none.  Off the diagonal the four warps
+// of sub-partition k (warps k, k+4, k+8, k+12) are the four column quarters of row strip k.  On a diagonal tile the pieces
+// under the diagonal 64-block do not exist — strips 2 and 3 have no quarters 0 and 1 — so the twelve that do are dealt out
+// three to a sub-partition instead of 4/4/2/2.
+__host__ __device__ inline bool syrk_piece(int halves, bool diag, int warp, int& strip, int& quarter) {
+  if (!diag) {
+    strip = warp & 3;
+    quarter = warp >> 2;
+    return ((halves >> (quarter >> 1)) & 1) != 0;
+  }
+  int k = (warp >> 2) * 4 + (warp & 3);
+  if (halves & 1) {
+    if (k < 4) {   // strips 0, 1 x quarters 0, 1
+      strip = k >> 1;
+      quarter = k & 1;
+      return true;
+    }
+    k -= 4;
+  }
+  if ((halves & 2) && k < 8) {   // strips 0..3 x quarters 2, 3
+    strip = k & 3;
+    quarter = 2 + (k >> 2);
+    return true;
+  }
+  strip = quarter = 0;
+  return false;
+}
+
 // one k-step (4 frames) of a warp: 4 row tiles x kNJ column tiles.  a_addr / b_addr: this thread's element (frame tig of the
 // k-step, column gid) of the warp's first row / column tile
 template <int kNJ>
@@ -578,7 +606,6 @@ cov_syrk_kernel(const __grid_constant__ CUtensorMap dmap, int n_frames, double* 
   unsigned char* ring = syrk_smem_raw + ((128u - (smem_addr(syrk_smem_raw) & 127u)) & 127u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
-  const int strip = warp & 3, quarter = warp >> 2, half = quarter >> 1;   // the 4 warps of a sub-partition share a row strip
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < kSyrkStages; i++) {
@@ -619,9 +646,11 @@ cov_syrk_kernel(const __grid_constant__ CUtensorMap dmap, int n_frames, double* 
   for (int lu = 0; lu < my_units; lu++) {
     const int unit = sched_unit[u_begin + lu];
     const int halves = (unit >> 28) & 3, s = (unit >> 16) & 0xfff, bi = (unit >> 8) & 255, bj = unit & 255;
+    int strip, quarter;
+    const bool has_piece = syrk_piece(halves, bi == bj, warp, strip, quarter);
     const int wr0 = bi * kSyrkTile + 32 * strip, wc0 = bj * kSyrkTile + 32 * quarter;
     // this warp's 32 x 32 piece: in a half the unit covers, inside G, and not below the diagonal 64-block
-    const bool active = ((halves >> half) & 1) && wr0 < G && wc0 < G && (wr0 / kCovBlk) <= (wc0 / kCovBlk);
+    const bool active = has_piece && wr0 < G && wc0 < G && (wr0 / kCovBlk) <= (wc0 / kCovBlk);
     const int nj = active ? min(4, (G - wc0 + 7) / 8) : 0;   // column tiles of 8 that hold real columns
     // where this warp's B columns sit in the stage: inside the A operand on a diagonal tile, else in the B operand, whose
     // first column is the tile's column 64 when the unit covers only the second half
@@ -703,19 +732,17 @@ struct SyrkSchedule {
   int* d_unit = nullptr;   // [n_units]
 };
 static int syrk_unit_cost(int G, int bi, int bj, int halves) {
-  int cost = 0;   // max over the 4 row strips (= sub-partitions) of the column tiles its four warps compute
-  for (int strip = 0; strip < 4; strip++) {
-    int c = 0;
-    for (int quarter = 0; quarter < 4; quarter++) {
-      const int wr0 = bi * kSyrkTile + 32 * strip, wc0 = bj * kSyrkTile + 32 * quarter;
-      if (((halves >> (quarter >> 1)) & 1) && wr0 < G && wc0 < G && wr0 / kCovBlk <= wc0 / kCovBlk) {
-        const int nj = std::min(4, (G - wc0 + 7) / 8);
-        c += nj > 2 ? 4 : nj > 1 ? 2 : 1;
-      }
+  int per_sp[4] = {0, 0, 0, 0};   // column tiles per k-step each sub-partition's warps compute
+  for (int warp = 0; warp < kSyrkThreads / 32; warp++) {
+    int strip, quarter;
+    if (!syrk_piece(halves, bi == bj, warp, strip, quarter)) continue;
+    const int wr0 = bi * kSyrkTile + 32 * strip, wc0 = bj * kSyrkTile + 32 * quarter;
+    if (wr0 < G && wc0 < G && wr0 / kCovBlk <= wc0 / kCovBlk) {
+      const int nj = std::min(4, (G - wc0 + 7) / 8);
+      per_sp[warp & 3] += nj > 2 ? 4 : nj > 1 ? 2 : 1;
     }
-    cost = std::max(cost, c);
   }
-  return cost;
+  return std::max(std::max(per_sp[0], per_sp[1]), std::max(per_sp[2], per_sp[3]));
 }
 static const SyrkSchedule* syrk_schedule(int S, int G, int ctas) {
   static std::mutex mu;
