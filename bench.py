@@ -455,6 +455,18 @@ def cli_leg(shm_dir, top, itp, text, frame_bytes, frames_per_rank, rank, world, 
 # ----------------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
+def device_for_rank(local_rank: int, world: int, visible: int) -> int:
+    """LOCAL_RANK -> CUDA device.  Identity unless CGC_BENCH_DEVICES="a,b,c,.." names the devices to use (rank r takes the
+    r-th): the end-to-end legs are bound by host->device copies, and which GPUs share a host-side bottleneck is a property
+    of the box (scripts/h2d_matrix.cu measures it)."""
+    env = os.environ.get("CGC_BENCH_DEVICES", "")
+    if env:
+        devs = [int(x) for x in env.split(",") if x.strip() != ""]
+        if len(devs) >= world and all(0 <= d < visible for d in devs):
+            return devs[local_rank]
+    return local_rank
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -466,6 +478,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the hot path is CUDA-only, there is no CPU fallback")
+    local = device_for_rank(local, world, torch.cuda.device_count())
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa_cores = cdist.bind_to_gpu_numa(local) if world > 1 else None   # before any pinned allocation
@@ -775,7 +788,8 @@ def run_ours(args):
                         "step": "K1 decode + K2 CDC (all sites) + float32 rows" + (" + K3 Correlate" if cov_on else "") + " over one batch of frames",
                         "input_bytes_per_step": int(n_text), "dims": {"atoms": n_atoms, "sites": S, "dq_atoms_per_site": ndq, "numTot": G},
                         "parallelism": "frame-sharded x%d, one all-reduce of the Correlate sums" % world,
-                        "numa": ("rank 0 bound to %d cores local to its GPU" % len(numa_cores)) if numa_cores else "unbound",
+                        "numa": "rank 0 on CUDA device %d%s; %s" % (local, " (CGC_BENCH_DEVICES=%s)" % os.environ["CGC_BENCH_DEVICES"] if os.environ.get("CGC_BENCH_DEVICES") else "",
+                                                                  ("bound to %d cores local to its GPU" % len(numa_cores)) if numa_cores else "cores unbound (the box reports one NUMA node)"),
                         "pairs_per_frame": pairs_per_frame},
         "pairs_per_s": value * pairs_per_frame, "pairs_per_s_reference_count_140": value * pairs_per_frame_140,
         "clocks": clocks,

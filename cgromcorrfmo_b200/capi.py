@@ -51,7 +51,9 @@ SIGNATURES = {
     "cgc_get_option": (c_double, [c_void_p, c_char_p]),
     "cgc_run": (c_int, [c_void_p, c_int64, c_int64, c_void_p, POINTER(c_int64)]),
     "cgc_request_stop": (None, [c_void_p]),
-    "cgc_cov_allreduce": (c_int, [POINTER(c_void_p), c_int]),
+    "cgc_comm_create": (c_int, [POINTER(c_int), c_int, POINTER(c_void_p)]),
+    "cgc_comm_destroy": (None, [c_void_p]),
+    "cgc_cov_allreduce": (c_int, [POINTER(c_void_p), c_int, c_void_p]),
     "cgc_run_write_time": (c_int, [c_void_p, c_int64, c_int64, c_char_p, c_int, c_void_p, POINTER(c_int64)]),
     "cgc_format_text_device": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64, POINTER(c_int64), POINTER(c_int)]),
     "cgc_run_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
@@ -471,7 +473,7 @@ def cov_allreduce(contexts):
     sums of all frame ranges."""
     lib = load()
     arr = (c_void_p * len(contexts))(*[c._h for c in contexts])
-    rc = lib.cgc_cov_allreduce(arr, len(contexts))
+    rc = lib.cgc_cov_allreduce(arr, len(contexts), None)
     if rc != CGC_OK:
         contexts[0]._check(rc)
 

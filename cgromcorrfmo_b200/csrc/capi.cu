@@ -1801,7 +1801,39 @@ NcclApi& nccl_api() {
 }
 }  // namespace
 
-int cgc_cov_allreduce(cgc_context** ctxs, int n) {
+struct cgc_comm {
+  std::vector<int> devices;
+  std::vector<ncclComm_t> comms;
+};
+
+int cgc_comm_create(const int* devices, int n, cgc_comm** out) {
+  if (!devices || n < 1 || !out) return fail(nullptr, CGC_ERR_ARG, "null or empty device list");
+  *out = nullptr;
+  return guarded(nullptr, [&]() {
+    NcclApi& api = nccl_api();
+    if (!api.problem.empty()) throw Unsupported(api.problem);
+    cgc_comm* c = new cgc_comm();
+    c->devices.assign(devices, devices + n);
+    c->comms.assign((size_t)n, nullptr);
+    const ncclResult_t r = api.CommInitAll(c->comms.data(), n, c->devices.data());
+    if (r != ncclSuccess) {
+      delete c;
+      throw CudaError(std::string("ncclCommInitAll: ") + (api.GetErrorString ? api.GetErrorString(r) : "NCCL error"));
+    }
+    *out = c;
+    return CGC_OK;
+  });
+}
+
+void cgc_comm_destroy(cgc_comm* comm) {
+  if (!comm) return;
+  NcclApi& api = nccl_api();
+  for (auto cm : comm->comms)
+    if (cm && api.CommDestroy) api.CommDestroy(cm);
+  delete comm;
+}
+
+int cgc_cov_allreduce(cgc_context** ctxs, int n, cgc_comm* comm) {
   if (!ctxs || n < 1) return CGC_ERR_ARG;
   cgc_context* c0 = ctxs[0];
   if (!c0) return CGC_ERR_ARG;
@@ -1815,6 +1847,9 @@ int cgc_cov_allreduce(cgc_context** ctxs, int n) {
       }
       for (int j = 0; j < i; j++)
         if (ctxs[j]->device == c->device) throw std::invalid_argument("allreduce: two contexts share a device");
+      if (comm && ((int)comm->devices.size() != n || comm->devices[(size_t)i] != c->device)) {
+        throw std::invalid_argument("allreduce: the communicator was created for another device list");
+      }
     }
     if (n == 1) return CGC_OK;
     NcclApi& api = nccl_api();
@@ -1830,8 +1865,18 @@ int cgc_cov_allreduce(cgc_context** ctxs, int n) {
       flush_cov_rows(ctxs[i], ctxs[i]->st_comp);
       CUDA_OK(cudaStreamSynchronize(ctxs[i]->st_comp));
     }
-    std::vector<ncclComm_t> comms((size_t)n, nullptr);
-    NCCL_OK(api.CommInitAll(comms.data(), n, devs.data()), "ncclCommInitAll");
+    cgc_comm* own = nullptr;
+    if (!comm) {
+      own = new cgc_comm();
+      own->devices = devs;
+      own->comms.assign((size_t)n, nullptr);
+      const ncclResult_t r = api.CommInitAll(own->comms.data(), n, devs.data());
+      if (r != ncclSuccess) {
+        delete own;
+        NCCL_OK(r, "ncclCommInitAll");
+      }
+      comm = own;
+    }
     bool failed = false;
     std::string msg;
     try {
@@ -1840,8 +1885,8 @@ int cgc_cov_allreduce(cgc_context** ctxs, int n) {
       NCCL_OK(api.GroupStart(), "ncclGroupStart");
       for (int i = 0; i < n; i++) {
         double* b = ctxs[i]->d_cov;
-        NCCL_OK(api.AllReduce(b, b, 1, ncclDouble, ncclSum, comms[(size_t)i], ctxs[i]->st_comp), "ncclAllReduce");
-        NCCL_OK(api.AllReduce(b + 1 + SG, b + 1 + SG, (size_t)(SG + SG * c0->sys.num_tot), ncclDouble, ncclSum, comms[(size_t)i],
+        NCCL_OK(api.AllReduce(b, b, 1, ncclDouble, ncclSum, comm->comms[(size_t)i], ctxs[i]->st_comp), "ncclAllReduce");
+        NCCL_OK(api.AllReduce(b + 1 + SG, b + 1 + SG, (size_t)(SG + SG * c0->sys.num_tot), ncclDouble, ncclSum, comm->comms[(size_t)i],
                               ctxs[i]->st_comp), "ncclAllReduce");
       }
       NCCL_OK(api.GroupEnd(), "ncclGroupEnd");
@@ -1853,8 +1898,7 @@ int cgc_cov_allreduce(cgc_context** ctxs, int n) {
       failed = true;
       msg = e.what();
     }
-    for (auto cm : comms)
-      if (cm) api.CommDestroy(cm);
+    if (own) cgc_comm_destroy(own);
     if (failed) throw CudaError(msg);
     return CGC_OK;
   });

@@ -394,6 +394,21 @@ static int run_multi(const Options& o) {
     fprintf(stderr, "traj2dEcsv: --verbose, --npy, --host-format, --checkpoint and --resume are one-GPU options\n");
     return EXIT_FAILURE;
   }
+  // the NCCL communicator takes about a second to set up: that happens next to the frame loop, not after it
+  cgc_comm* comm = nullptr;
+  int comm_rc = CGC_OK;
+  std::string comm_err;
+  std::thread comm_thread;
+  if (!o.no_mtx) {
+    comm_thread = std::thread([&] {
+      comm_rc = cgc_comm_create(o.devices.data(), R, &comm);
+      if (comm_rc != CGC_OK) comm_err = cgc_last_error(nullptr);
+    });
+  }
+  struct JoinComm {
+    std::thread& t;
+    ~JoinComm() { if (t.joinable()) t.join(); }
+  } join_comm{comm_thread};
   std::vector<cgc_context*> ctx((size_t)R, nullptr);
   std::vector<int> status((size_t)R, 0);
   const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
@@ -456,8 +471,13 @@ static int run_multi(const Options& o) {
     stopped = stopped || rrc[(size_t)r] == CGC_STOPPED;
     done_total += rdone[(size_t)r];
   }
+  if (comm_thread.joinable()) comm_thread.join();
   if (want_mtx && done_total > 0) {
-    rc = cgc_cov_allreduce(ctx.data(), R);   // the one collective: n, sum(x-c), sum (x-c)(x-c)^T
+    if (comm_rc != CGC_OK) {
+      fprintf(stderr, "traj2dEcsv: %s while setting up NCCL: %s\n", error_class(comm_rc), comm_err.c_str());
+      return exit_status(comm_rc);
+    }
+    rc = cgc_cov_allreduce(ctx.data(), R, comm);   // the one collective: n, sum(x-c), sum (x-c)(x-c)^T
     if (rc != CGC_OK) return die(ctx[0], rc, "combining the Correlate sums (NCCL all-reduce)");
   }
   const double t_reduced = now_s();

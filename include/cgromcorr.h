@@ -25,6 +25,7 @@ extern "C" {
 #endif
 
 typedef struct cgc_context cgc_context;
+typedef struct cgc_comm cgc_comm;   /* an NCCL communicator set over the GPUs one process drives (cgc_comm_create) */
 
 /* ---- status codes.  The three reference exception classes (src/grom2atomFMO.h:12-27) map to the first three. ---- */
 #define CGC_OK                    0
@@ -172,13 +173,18 @@ int cgc_cov_reset(cgc_context *ctx);
 int cgc_cov_partials(cgc_context *ctx, double *host_out);           /* copy the flat buffer to HOST */
 /* The ONE collective of the hot path for a process that drives several GPUs itself (one context and one host thread per
  * GPU, each run over its own frame range — what the reference's authors did with one process per trajectory chunk,
- * scripts/2014-06-gro2dEcsv.sh:3-27): ncclCommInitAll over the contexts' devices and one grouped ncclAllReduce(sum,
- * double) of n, sum(x-c) and sum (x-c)(x-c)^T; the shift block, identical everywhere, is left alone.  Afterwards every
- * context holds the sums of all frames.  NCCL is bound at run time (libnccl.so.2): CGC_ERR_UNSUPPORTED when it cannot be
- * loaded.  The float32 sums of the literal (compat) `.mtx` are per context and are NOT combined: their sequential order
- * is the point of that mode.  (One process per GPU instead: all-reduce the cgc_cov_bind buffer with the caller's own
- * communicator, cgromcorrfmo_b200/dist.py.) */
-int cgc_cov_allreduce(cgc_context **ctxs, int n);
+ * scripts/2014-06-gro2dEcsv.sh:3-27): one grouped ncclAllReduce(sum, double) of n, sum(x-c) and sum (x-c)(x-c)^T; the shift
+ * block, identical everywhere, is left alone.  Afterwards every context holds the sums of all frames.
+ * cgc_comm_create = ncclCommInitAll over `devices` (in the order of the contexts handed to cgc_cov_allreduce later).  It
+ * takes about a second: call it from a helper thread while the frames stream.  comm == NULL makes cgc_cov_allreduce create
+ * (and destroy) a communicator itself.  NCCL is bound at run time (libnccl.so.2): CGC_ERR_UNSUPPORTED when it cannot be
+ * loaded; the message of a failed cgc_comm_create is cgc_last_error(NULL) on the calling thread.  The float32 sums of the
+ * literal (compat) `.mtx` are per context and are NOT combined: their sequential order is the point of that mode.  (One
+ * process per GPU instead: all-reduce the cgc_cov_bind buffer with the caller's own communicator,
+ * cgromcorrfmo_b200/dist.py.) */
+int cgc_comm_create(const int *devices, int n, cgc_comm **out);
+void cgc_comm_destroy(cgc_comm *comm);
+int cgc_cov_allreduce(cgc_context **ctxs, int n, cgc_comm *comm);
 /* Checkpoint / resume of the Correlate state (the reference loses its accumulators when a run is killed; its `.time`
  * prefix survives because the file only grows, src/FMOparse.cpp:48-50,158-165 — SURVEY.md section 5).  The blob holds
  * the flat partial sums and the two float32 sums of the literal `.mtx`; loading it into a context opened on the same
