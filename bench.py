@@ -131,9 +131,9 @@ def time_corr_leg(capi, top, itp, device, fp64_peak):
 
 def calibrate_h2d(torch, dist, world, host, d_text, seconds=0.5):
     """Yard-stick for the end-to-end leg: pinned host -> device copies of the same text buffer.  Returns
-    (alone_gbs, concurrent_gbs): best single copy on this rank, and — the ceiling the e2e leg is held against — the
-    rate sustained while EVERY rank copies at the same time (barrier-synchronised start, `seconds` of back-to-back copies,
-    the slowest rank's rate)."""
+    (alone_gbs, [concurrent_gbs of every rank]): best single copy on this rank, and — the ceiling the e2e leg is held
+    against — the rate every rank sustains while ALL ranks copy at the same time (barrier-synchronised start, `seconds` of
+    back-to-back copies)."""
     nbytes = host.numel()
     best = 1e9
     for _ in range(4):
@@ -155,11 +155,13 @@ def calibrate_h2d(torch, dist, world, host, d_text, seconds=0.5):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     conc = reps * nbytes / dt / 1e9
+    rates = [conc]
     if world > 1:
-        t = torch.tensor([conc], dtype=torch.float64, device=d_text.device)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        conc = float(t.item())
-    return alone, conc
+        t = torch.zeros(world, dtype=torch.float64, device=d_text.device)
+        t[dist.get_rank()] = conc
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        rates = [float(v) for v in t.tolist()]
+    return alone, rates
 
 
 def cores_available() -> int:
@@ -394,7 +396,10 @@ def run_cli(traj, top, itp, out, frames, gpus, extra=()):
     from cgromcorrfmo_b200 import build
     cmd = [build.CLI, traj, top, itp, out, str(frames), "--timing"] + (["--gpus", str(gpus)] if gpus > 1 else []) + list(extra)
     t0 = time.perf_counter()
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    except subprocess.TimeoutExpired:
+        return dict(rc=-9, wall_s=time.perf_counter() - t0, in_loop=None, timing="timed out after 240 s")
     wall = time.perf_counter() - t0
     m = re.search(r"in-loop (\d+) frames/s", r.stderr)
     return dict(rc=r.returncode, wall_s=wall, in_loop=float(m.group(1)) if m else None, timing=r.stderr.strip().split("\n")[-1][-900:])
@@ -456,14 +461,18 @@ def cli_leg(shm_dir, top, itp, text, frame_bytes, frames_per_rank, rank, world, 
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
 def device_for_rank(local_rank: int, world: int, visible: int) -> int:
-    """LOCAL_RANK -> CUDA device.  Identity unless CGC_BENCH_DEVICES="a,b,c,.." names the devices to use (rank r takes the
-    r-th): the end-to-end legs are bound by host->device copies, and which GPUs share a host-side bottleneck is a property
-    of the box (scripts/h2d_matrix.cu measures it)."""
+    """LOCAL_RANK -> CUDA device.  CGC_BENCH_DEVICES="a,b,c,.." names the devices to use (rank r takes the r-th); otherwise
+    identity, except on an 8-GPU box with fewer ranks than GPUs (below).  The end-to-end legs are bound by host->device
+    copies, and which GPUs share a host-side bottleneck is a property of the box (scripts/h2d_matrix.cu measures it)."""
     env = os.environ.get("CGC_BENCH_DEVICES", "")
     if env:
         devs = [int(x) for x in env.split(",") if x.strip() != ""]
         if len(devs) >= world and all(0 <= d < visible for d in devs):
             return devs[local_rank]
+    if 1 < world < visible and visible == 8:
+        # This pool's 8-GPU boxes (profiles/r02_h2d_matrix_8gpu.txt): GPUs 0-3 share one ~115 GB/s host path (28.9 GB/s each
+        # when all four copy), GPUs 4-7 keep 55 GB/s each when all four copy.  Fewer ranks than GPUs: take the upper ones.
+        return visible - world + local_rank
     return local_rank
 
 
@@ -589,17 +598,25 @@ def run_ours(args):
             return 0
 
         # ---------------- end to end through cgc_run: pinned host text in, dE rows out to host memory
+        # The leg is bound by the host->device copies, and the GPUs of a box do not get equal shares of the host's
+        # bandwidth when all of them copy (8-GPU boxes of this pool: 23 GB/s each for GPUs 0-3, 35 GB/s each for 4-7).  Frames
+        # are therefore dealt out in proportion to the rate each rank's link sustains under full load, measured here: rank r
+        # streams F_r = F * rate_r / max(rate) frames per step (the fastest links keep F).
+        h2d_alone, h2d_rates = calibrate_h2d(torch, dist, world, host, d_text)
+        share = [max(1, int(round(F * r / max(h2d_rates)))) for r in h2d_rates]
+        F_me = share[rank]
         out_host = np.empty((F, S, G), dtype=np.float32)
         e2e_batch = args.e2e_batch or int(min(F, max(1, (144 << 20) // frame_bytes)))
         ctx.set_option("batch_frames", e2e_batch)                    # several batches per call: H2D overlaps the kernels
+        ctx.run(0, F, out=out_host)                                   # all F rows once, for the comparisons below
         for _ in range(max(3, args.warmup)):
-            ctx.run(0, F, out=out_host)
+            ctx.run(0, F_me, out=out_host)
         barrier()
         ctx.kernel_times(reset=True)
         t0 = time.perf_counter()
         e0.record()
         for _ in range(args.steps):
-            ctx.run(0, F, out=out_host)
+            ctx.run(0, F_me, out=out_host)
         combine(cov)
         e1.record()
         barrier()
@@ -608,10 +625,10 @@ def run_ours(args):
             t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
-        e2e_value = world * args.steps * F / e2e_s
+        e2e_value = sum(share) * args.steps / e2e_s
         e2e_ktimes = ctx.kernel_times(reset=True)
         same = bool(np.array_equal(out_host.view(np.uint32), d_dE.cpu().numpy().view(np.uint32)))
-        h2d_alone, h2d_conc = calibrate_h2d(torch, dist, world, host, d_text)
+        h2d_ceiling_fps = sum(h2d_rates) * 1e9 / frame_bytes           # every link at its concurrent rate
 
         # ---------------- the one collective, checked: merged sums == one rank over all the frames
         allreduce_check = None
@@ -678,14 +695,19 @@ def run_ours(args):
             ctx2.cov_bind(cov2.data_ptr())
             ctx2.cov_set_shift_device(row0.data_ptr(), stream)            # the same shift on every rank, as above
         out_trr = np.empty((F, S, G), dtype=np.float32)
+        d_trr = torch.empty(n_trr + 64, dtype=torch.uint8, device=dev)
+        trr_alone, trr_rates = calibrate_h2d(torch, dist, world, host_trr, d_trr)
+        del d_trr
+        trr_share = [max(1, int(round(F * r / max(trr_rates)))) for r in trr_rates]
+        ctx2.run(0, F, out=out_trr)
         for _ in range(max(3, args.warmup)):
-            ctx2.run(0, F, out=out_trr)
+            ctx2.run(0, trr_share[rank], out=out_trr)
         barrier()
         ctx2.kernel_times(reset=True)
         t0 = time.perf_counter()
         e0.record()
         for _ in range(args.steps):
-            ctx2.run(0, F, out=out_trr)
+            ctx2.run(0, trr_share[rank], out=out_trr)
         combine(cov2)
         e1.record()
         barrier()
@@ -695,11 +717,8 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             trr_s = float(t.item())
         trr_ktimes = ctx2.kernel_times(reset=True)
-        trr_value = world * args.steps * F / trr_s
+        trr_value = sum(trr_share) * args.steps / trr_s
         trr_same = bool(np.array_equal(out_trr.view(np.uint32), out_host.view(np.uint32)))
-        d_trr = torch.empty(n_trr + 64, dtype=torch.uint8, device=dev)
-        trr_alone, trr_conc = calibrate_h2d(torch, dist, world, host_trr, d_trr)
-        del d_trr
         ctx2.close()
         del cov2, cov, d_text, d_dE
 
@@ -796,17 +815,20 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_text + 8 * F), "d2h_bytes_per_step": int(F * S * G * 4),
                 "api": "cgc_run (C-ABI) on pinned host text, %d-frame batches in a 6-slot ring; dE rows copied back to host" % e2e_batch,
                 "rows_bit_identical_to_device_path": same, "kernel_ms": {k: v[0] for k, v in e2e_ktimes.items()}, "wall_ms": e2e_s * 1e3,
-                "bound": "PCIe host->device copy of the text", "h2d_gbs": e2e_value / world * frame_bytes / 1e9,
-                "h2d_peak_gbs": h2d_conc, "frac_of_h2d_peak": (e2e_value / world * frame_bytes / 1e9) / h2d_conc,
-                "h2d_peak_source": "pinned cudaMemcpyAsync of the same text buffer sustained for 0.5 s on ALL ranks at once (barrier-"
-                                   "synchronised start), slowest rank; measured in this run",
-                "h2d_alone_gbs": h2d_alone},
+                "bound": "PCIe host->device copy of the text", "h2d_gbs": e2e_value * frame_bytes / 1e9,
+                "h2d_peak_gbs": sum(h2d_rates), "frac_of_h2d_peak": e2e_value / h2d_ceiling_fps,
+                "h2d_peak_source": "sum over ranks of the rate each rank's pinned cudaMemcpyAsync of the same text buffer sustains for 0.5 s "
+                                   "while ALL ranks copy (barrier-synchronised start); measured in this run, just before the leg",
+                "h2d_concurrent_gbs_per_rank": h2d_rates, "h2d_alone_gbs": h2d_alone,
+                "frames_per_step_per_rank": share,
+                "sharding": "frames dealt out in proportion to each rank's concurrent H2D rate"},
         "e2e_trr": {"value": trr_value, "unit": UNIT, "h2d_bytes_per_step": int(n_trr + 8 * F), "d2h_bytes_per_step": int(F * S * G * 4),
                     "api": "cgc_open_memory_trr + cgc_run on pinned .trr frames (float32 coordinates + box, %d B/frame), %d-frame batches"
                            % (n_trr // F, trr_batch),
                     "note": "same frames as the headline; not the reference's input format (it reads .gro text)",
-                    "rows_bit_identical_to_gro_path": trr_same, "h2d_gbs": trr_value / world * (n_trr / F) / 1e9,
-                    "h2d_peak_gbs": trr_conc, "h2d_alone_gbs": trr_alone,
+                    "rows_bit_identical_to_gro_path": trr_same, "h2d_gbs": trr_value * (n_trr / F) / 1e9,
+                    "h2d_peak_gbs": sum(trr_rates), "frac_of_h2d_peak": trr_value * (n_trr / F) / 1e9 / sum(trr_rates),
+                    "h2d_concurrent_gbs_per_rank": trr_rates, "h2d_alone_gbs": trr_alone, "frames_per_step_per_rank": trr_share,
                     "kernel_ms": {k: v[0] for k, v in trr_ktimes.items()}, "wall_ms": trr_s * 1e3},
         "e2e_cli": cli,
         "allreduce_check": allreduce_check,

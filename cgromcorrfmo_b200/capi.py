@@ -51,6 +51,7 @@ SIGNATURES = {
     "cgc_get_option": (c_double, [c_void_p, c_char_p]),
     "cgc_run": (c_int, [c_void_p, c_int64, c_int64, c_void_p, POINTER(c_int64)]),
     "cgc_request_stop": (None, [c_void_p]),
+    "cgc_prepare": (c_int, [c_void_p, c_int]),
     "cgc_comm_create": (c_int, [POINTER(c_int), c_int, POINTER(c_void_p)]),
     "cgc_comm_destroy": (None, [c_void_p]),
     "cgc_cov_allreduce": (c_int, [POINTER(c_void_p), c_int, c_void_p]),
@@ -60,6 +61,7 @@ SIGNATURES = {
     "cgc_decode_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "cgc_kernel_times": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "cgc_launch_count": (c_int64, [c_void_p]),
+    "cgc_debug_guard_check": (c_int, [POINTER(c_int), POINTER(c_int)]),
     "cgc_decode_errors": (c_int, [c_void_p, POINTER(c_int)]),
     "cgc_cov_size": (c_int64, [c_void_p]),
     "cgc_cov_bind": (c_int, [c_void_p, c_void_p]),
@@ -295,6 +297,11 @@ class Context:
     def get_option(self, key: str) -> float:
         return float(self._lib.cgc_get_option(self._h, key.encode()))
 
+    def prepare(self, with_time_text: bool = False):
+        """Allocate the streaming buffers now rather than inside the first run()."""
+        self._check(self._lib.cgc_prepare(self._h, 1 if with_time_text else 0))
+        return self
+
     def request_stop(self):
         """Ask the run in progress (or the next one) to stop after the batches under way (the reference's SIGINT flag)."""
         self._lib.cgc_request_stop(self._h)
@@ -465,6 +472,17 @@ class Context:
 
     def write_mtx(self, path: str, compat: bool = False):
         self._check(self._lib.cgc_write_mtx(self._h, os.fsencode(path), 1 if compat else 0))
+
+
+def debug_guard_check():
+    """(buffers guarded, buffers with a damaged guard band) — needs CGC_GUARD=1 in the environment before the library
+    allocates anything; raises otherwise."""
+    lib = load()
+    n, bad = c_int(0), c_int(0)
+    rc = lib.cgc_debug_guard_check(ctypes.byref(n), ctypes.byref(bad))
+    if rc != CGC_OK:
+        raise CgcError(rc, "guard bands are off (set CGC_GUARD=1 before the first context is created)")
+    return n.value, bad.value
 
 
 def cov_allreduce(contexts):

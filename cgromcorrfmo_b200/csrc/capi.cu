@@ -14,6 +14,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <map>
 #include <mutex>
 #include <cmath>
 #include <cstdio>
@@ -34,6 +35,48 @@ using namespace cgc;
 namespace {
 
 thread_local std::string g_create_error;
+
+// Guard bands (CGC_GUARD=1 in the environment; developer aid): every device buffer a context owns is allocated with 4 KiB
+// of a known byte pattern in front of it and behind it.  cgc_debug_guard_check reads the bands back: a kernel that wrote
+// before or past one of its buffers has changed them.  (compute-sanitizer is closed on the B200 pool this was developed
+// on; this covers the out-of-bounds WRITES of the hot-path kernels on all their buffers, at full speed.)
+constexpr size_t kGuardBytes = 4096;
+constexpr unsigned char kGuardByte = 0xA5;
+struct GuardInfo { char* base; size_t bytes, padded; int device; };   // bytes: what was asked for; padded: rounded up to 256
+std::mutex g_guard_mu;
+std::map<void*, GuardInfo> g_guard_map;
+bool guard_on() {
+  static const bool on = [] { const char* e = getenv("CGC_GUARD"); return e && *e && *e != '0'; }();
+  return on;
+}
+cudaError_t guard_malloc(void** p, size_t bytes) {
+  if (!guard_on()) return cudaMalloc(p, bytes);
+  const size_t padded = (bytes + 255) & ~(size_t)255;   // the band behind the buffer starts right after its (256-byte rounded) end
+  char* base = nullptr;
+  cudaError_t e = cudaMalloc(&base, padded + 2 * kGuardBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaMemset(base, kGuardByte, padded + 2 * kGuardBytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();   // the fill runs on the legacy stream; the owners use non-blocking streams
+  if (e != cudaSuccess) return e;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  *p = base + kGuardBytes;
+  std::lock_guard<std::mutex> g(g_guard_mu);
+  g_guard_map[*p] = {base, bytes, padded, dev};
+  return cudaSuccess;
+}
+cudaError_t guard_free(void* p) {
+  if (!guard_on() || !p) return cudaFree(p);
+  char* base = nullptr;
+  {
+    std::lock_guard<std::mutex> g(g_guard_mu);
+    auto it = g_guard_map.find(p);
+    if (it == g_guard_map.end()) return cudaFree(p);
+    base = it->second.base;
+    g_guard_map.erase(it);
+  }
+  return cudaFree(base);
+}
 
 struct CudaError : std::runtime_error {
   using std::runtime_error::runtime_error;
@@ -248,7 +291,7 @@ struct cgc_context {
   // batches in the ring: up to three staged ahead by the background copiers, up to three on the device (H2D copy, queued,
   // computing) — the host thread only enqueues and drains
   static constexpr int kSlots = 6;
-  static constexpr int kStageAhead = 3, kInFlight = 3;
+  int ring_slots = kSlots;      // option "ring_slots" (2..kSlots): half of them staged ahead, half on the device
   Slot slot[kSlots];
   bool dev_pipeline = false;
   int alloc_batch = 0;
@@ -310,18 +353,18 @@ void free_pipeline(cgc_context* c) {
   cudaSetDevice(c->device);
   for (auto& s : c->slot) {
     pinned_free(s.h_text_block);
-    if (s.d_text) cudaFree(s.d_text);
-    if (s.d_off) cudaFree(s.d_off);
+    if (s.d_text) guard_free(s.d_text);
+    if (s.d_off) guard_free(s.d_off);
     if (s.h_off) cudaFreeHost(s.h_off);
-    if (s.d_xyz8) cudaFree(s.d_xyz8);
-    if (s.d_sites) cudaFree(s.d_sites);
-    if (s.d_acc) cudaFree(s.d_acc);
-    if (s.d_dE) cudaFree(s.d_dE);
+    if (s.d_xyz8) guard_free(s.d_xyz8);
+    if (s.d_sites) guard_free(s.d_sites);
+    if (s.d_acc) guard_free(s.d_acc);
+    if (s.d_dE) guard_free(s.d_dE);
     pinned_free(s.h_dE_block);
-    if (s.d_ttext) cudaFree(s.d_ttext);
-    if (s.d_rowoff) cudaFree(s.d_rowoff);
+    if (s.d_ttext) guard_free(s.d_ttext);
+    if (s.d_rowoff) guard_free(s.d_rowoff);
     if (s.h_tinfo) cudaFreeHost(s.h_tinfo);
-    if (s.d_fmt_flag) cudaFree(s.d_fmt_flag);
+    if (s.d_fmt_flag) guard_free(s.d_fmt_flag);
     if (s.ev_copied) cudaEventDestroy(s.ev_copied);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     if (s.ev_text_out) cudaEventDestroy(s.ev_text_out);
@@ -346,20 +389,20 @@ void free_pipeline(cgc_context* c) {
 void free_static(cgc_context* c) {
   if (c->device < 0) return;
   cudaSetDevice(c->device);
-  if (c->sys.kq) cudaFree(c->sys.kq);
-  if (c->sys.col) cudaFree(c->sys.col);
-  if (c->sys.slot) cudaFree(c->sys.slot);
-  if (c->sys.slot_dq) cudaFree(c->sys.slot_dq);
+  if (c->sys.kq) guard_free(c->sys.kq);
+  if (c->sys.col) guard_free(c->sys.col);
+  if (c->sys.slot) guard_free(c->sys.slot);
+  if (c->sys.slot_dq) guard_free(c->sys.slot_dq);
   c->sys.kq = nullptr; c->sys.col = nullptr; c->sys.slot = nullptr; c->sys.slot_dq = nullptr;
-  if (c->d_cov && !c->cov_bound) cudaFree(c->d_cov);
+  if (c->d_cov && !c->cov_bound) guard_free(c->d_cov);
   c->d_cov = nullptr;
   c->cov_bound = false;
-  if (c->d_compat) cudaFree(c->d_compat);
+  if (c->d_compat) guard_free(c->d_compat);
   c->d_compat = nullptr;
-  if (c->d_centred) cudaFree(c->d_centred);
+  if (c->d_centred) guard_free(c->d_centred);
   c->d_centred = nullptr;
   c->centred_frames = 0;
-  if (c->d_cov_rows) cudaFree(c->d_cov_rows);
+  if (c->d_cov_rows) guard_free(c->d_cov_rows);
   c->d_cov_rows = nullptr;
   c->cov_rows_cap = c->cov_rows_pending = 0;
   c->shift_set = false;
@@ -379,8 +422,8 @@ cgc_context::~cgc_context() {
     if (st_copy) cudaStreamDestroy(st_copy);
     if (st_comp) cudaStreamDestroy(st_comp);
     if (st_out) cudaStreamDestroy(st_out);
-    if (d_fmt_flags) cudaFree(d_fmt_flags);
-    if (d_err) cudaFree(d_err);
+    if (d_fmt_flags) guard_free(d_fmt_flags);
+    if (d_err) guard_free(d_err);
   }
   release_text(this);
 }
@@ -410,6 +453,13 @@ int guarded(cgc_context* c, F&& fn) {
     if (c) c->err = e.what(); else g_create_error = e.what();
     return CGC_ERR_ARG;
   }
+}
+
+// Set-up-time zeroing: cudaMemset of device memory returns before the fill has run, on the legacy stream, and the contexts'
+// streams are non-blocking (not ordered after it): wait, so that nothing enqueued later on any stream can overtake the fill.
+cudaError_t zero_now(void* p, size_t bytes) {
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  return e == cudaSuccess ? cudaDeviceSynchronize() : e;
 }
 
 int fail(const cgc_context* c, int code, const std::string& msg) {
@@ -499,10 +549,10 @@ void build_static(cgc_context* c) {
     kq[a] = (double)33.2f * (double)c->q_ground[a];  // reference src/grom2atomFMO.cpp:666,687
     col[a] = c->col[a];
   }
-  CUDA_OK(cudaMalloc(&sys.kq, sizeof(double) * sys.n_pad));
-  CUDA_OK(cudaMalloc(&sys.col, sizeof(int32_t) * sys.n_pad));
-  CUDA_OK(cudaMalloc(&sys.slot, sizeof(int32_t) * sys.n_pad));
-  CUDA_OK(cudaMalloc(&sys.slot_dq, sizeof(float) * slot_dq.size()));
+  CUDA_OK(guard_malloc((void**)&sys.kq, sizeof(double) * sys.n_pad));
+  CUDA_OK(guard_malloc((void**)&sys.col, sizeof(int32_t) * sys.n_pad));
+  CUDA_OK(guard_malloc((void**)&sys.slot, sizeof(int32_t) * sys.n_pad));
+  CUDA_OK(guard_malloc((void**)&sys.slot_dq, sizeof(float) * slot_dq.size()));
   CUDA_OK(cudaMemcpy(sys.kq, kq.data(), sizeof(double) * sys.n_pad, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(sys.col, col.data(), sizeof(int32_t) * sys.n_pad, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(sys.slot, slot.data(), sizeof(int32_t) * sys.n_pad, cudaMemcpyHostToDevice));
@@ -511,12 +561,12 @@ void build_static(cgc_context* c) {
   if (!c->st_comp) CUDA_OK(cudaStreamCreateWithFlags(&c->st_comp, cudaStreamNonBlocking));
   if (!c->st_out) CUDA_OK(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
   if (!c->d_fmt_flags) {
-    CUDA_OK(cudaMalloc(&c->d_fmt_flags, sizeof(int)));
-    CUDA_OK(cudaMemset(c->d_fmt_flags, 0, sizeof(int)));
+    CUDA_OK(guard_malloc((void**)&c->d_fmt_flags, sizeof(int)));
+    CUDA_OK(zero_now(c->d_fmt_flags, sizeof(int)));
   }
   if (!c->d_err) {
-    CUDA_OK(cudaMalloc(&c->d_err, sizeof(int)));
-    CUDA_OK(cudaMemset(c->d_err, 0, sizeof(int)));
+    CUDA_OK(guard_malloc((void**)&c->d_err, sizeof(int)));
+    CUDA_OK(zero_now(c->d_err, sizeof(int)));
   }
   c->dev_static = true;
 }
@@ -536,14 +586,14 @@ void ensure_cov(cgc_context* c) {
   if (!cov_enabled(c)) return;
   const int64_t SG = (int64_t)c->sys.n_sites * c->sys.num_tot;
   if (!c->d_cov) {
-    CUDA_OK(cudaMalloc(&c->d_cov, sizeof(double) * cov_doubles(c)));
-    CUDA_OK(cudaMemset(c->d_cov, 0, sizeof(double) * cov_doubles(c)));
+    CUDA_OK(guard_malloc((void**)&c->d_cov, sizeof(double) * cov_doubles(c)));
+    CUDA_OK(zero_now(c->d_cov, sizeof(double) * cov_doubles(c)));
     c->cov_bound = false;
     c->shift_set = false;
   }
   if (!c->d_compat) {
-    CUDA_OK(cudaMalloc(&c->d_compat, sizeof(float) * 2 * SG));
-    CUDA_OK(cudaMemset(c->d_compat, 0, sizeof(float) * 2 * SG));
+    CUDA_OK(guard_malloc((void**)&c->d_compat, sizeof(float) * 2 * SG));
+    CUDA_OK(zero_now(c->d_compat, sizeof(float) * 2 * SG));
   }
 }
 
@@ -574,19 +624,19 @@ void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_ho
   const bool ring = n_slots > 1;
   for (int si = 0; si < n_slots; si++) {
     Slot& s = c->slot[si];
-    if (ring) CUDA_OK(cudaMalloc(&s.d_text, (size_t)text_bytes + 64));
+    if (ring) CUDA_OK(guard_malloc((void**)&s.d_text, (size_t)text_bytes + 64));
     if (need_host_text) {
       s.h_text_block = pinned_alloc((size_t)text_bytes + 64);
       s.h_text = s.h_text_block.p;
     }
-    CUDA_OK(cudaMalloc(&s.d_off, sizeof(int64_t) * batch));
+    CUDA_OK(guard_malloc((void**)&s.d_off, sizeof(int64_t) * batch));
     CUDA_OK(cudaHostAlloc(&s.h_off, sizeof(int64_t) * batch, cudaHostAllocDefault));
-    CUDA_OK(cudaMalloc(&s.d_xyz8, sizeof(float) * 3 * (size_t)sys.n_pad * batch));
-    CUDA_OK(cudaMalloc(&s.d_sites, (size_t)16 * sys.n_sites * sys.site_cap * batch));
-    CUDA_OK(cudaMalloc(&s.d_acc, sizeof(double) * sg * batch));
+    CUDA_OK(guard_malloc((void**)&s.d_xyz8, sizeof(float) * 3 * (size_t)sys.n_pad * batch));
+    CUDA_OK(guard_malloc((void**)&s.d_sites, (size_t)16 * sys.n_sites * sys.site_cap * batch));
+    CUDA_OK(guard_malloc((void**)&s.d_acc, sizeof(double) * sg * batch));
     CUDA_OK(cudaMemsetAsync(s.d_acc, 0, sizeof(double) * sg * batch, c->st_comp));
     if (ring) {
-      CUDA_OK(cudaMalloc(&s.d_dE, sizeof(float) * sg * batch));
+      CUDA_OK(guard_malloc((void**)&s.d_dE, sizeof(float) * sg * batch));
       s.h_dE_block = pinned_alloc(sizeof(float) * (size_t)(sg * batch));
       s.h_dE = (float*)s.h_dE_block.p;
     }
@@ -726,13 +776,13 @@ void ensure_time_text(cgc_context* c, int batch) {
   const int64_t cap = format_time_capacity(rows, c->sys.num_tot) + 64;
   for (auto& s : c->slot) {
     if (s.ttext_cap >= cap) continue;
-    if (s.d_ttext) CUDA_OK(cudaFree(s.d_ttext));
-    if (s.d_rowoff) CUDA_OK(cudaFree(s.d_rowoff));
+    if (s.d_ttext) CUDA_OK(guard_free(s.d_ttext));
+    if (s.d_rowoff) CUDA_OK(guard_free(s.d_rowoff));
     s.d_ttext = nullptr; s.d_rowoff = nullptr; s.ttext_cap = 0;
-    CUDA_OK(cudaMalloc(&s.d_ttext, (size_t)cap));
-    CUDA_OK(cudaMalloc(&s.d_rowoff, sizeof(int64_t) * (size_t)(rows + 1)));
+    CUDA_OK(guard_malloc((void**)&s.d_ttext, (size_t)cap));
+    CUDA_OK(guard_malloc((void**)&s.d_rowoff, sizeof(int64_t) * (size_t)(rows + 1)));
     if (!s.h_tinfo) CUDA_OK(cudaHostAlloc(&s.h_tinfo, sizeof(int64_t) * 2, cudaHostAllocDefault));
-    if (!s.d_fmt_flag) CUDA_OK(cudaMalloc(&s.d_fmt_flag, sizeof(int)));
+    if (!s.d_fmt_flag) CUDA_OK(guard_malloc((void**)&s.d_fmt_flag, sizeof(int)));
     s.ttext_cap = cap;
   }
   ensure_sink_bufs(c, cap);
@@ -838,10 +888,10 @@ void collect_kernel_times(cgc_context* c) {
 
 double* centred_scratch(cgc_context* c, int n_frames) {
   if (c->centred_frames < n_frames) {
-    if (c->d_centred) CUDA_OK(cudaFree(c->d_centred));  // synchronises: nothing in flight still reads it
+    if (c->d_centred) CUDA_OK(guard_free(c->d_centred));  // synchronises: nothing in flight still reads it
     c->d_centred = nullptr;
     const int64_t want = std::max<int64_t>(n_frames, 64);
-    CUDA_OK(cudaMalloc(&c->d_centred, sizeof(double) * (size_t)cov_centred_doubles((int)want, c->sys.n_sites, c->sys.num_tot)));
+    CUDA_OK(guard_malloc((void**)&c->d_centred, sizeof(double) * (size_t)cov_centred_doubles((int)want, c->sys.n_sites, c->sys.num_tot)));
     c->centred_frames = want;
   }
   return c->d_centred;
@@ -871,10 +921,10 @@ void ensure_cov_buffers(cgc_context* c, int batch) {
   const int64_t sg = (int64_t)sys.n_sites * sys.num_tot;
   const int64_t cap = kCovGather + batch;
   if (c->cov_rows_cap < cap) {
-    if (c->d_cov_rows) CUDA_OK(cudaFree(c->d_cov_rows));
+    if (c->d_cov_rows) CUDA_OK(guard_free(c->d_cov_rows));
     c->d_cov_rows = nullptr;
     c->cov_rows_cap = 0;
-    CUDA_OK(cudaMalloc(&c->d_cov_rows, sizeof(float) * (size_t)(cap * sg)));
+    CUDA_OK(guard_malloc((void**)&c->d_cov_rows, sizeof(float) * (size_t)(cap * sg)));
     c->cov_rows_cap = cap;
   }
   centred_scratch(c, (int)cap);
@@ -1222,6 +1272,9 @@ int cgc_set_option(cgc_context* ctx, const char* key, double value) {
     } else if (k == "batch_frames") {
       if (value < 1 || value > 65535) throw std::invalid_argument("batch_frames must be within 1..65535");
       ctx->batch_frames = (int)value;
+    } else if (k == "ring_slots") {
+      if (value < 2 || value > cgc_context::kSlots) throw std::invalid_argument("ring_slots must be within 2..6");
+      ctx->ring_slots = (int)value;
     } else if (k == "stage_threads") {
       if (value < 1 || value > 256) throw std::invalid_argument("stage_threads must be within 1..256");
       if ((int)value != ctx->stage_threads) {
@@ -1243,6 +1296,7 @@ double cgc_get_option(const cgc_context* ctx, const char* key) {
   if (k == "mtx_compat") return ctx->compat_on ? 1 : 0;
   if (k == "covariance") return ctx->device >= 0 && ctx->dev_static ? (cov_enabled(ctx) ? 1 : 0) : ctx->cov_opt;
   if (k == "batch_frames") return ctx->batch_frames > 0 ? ctx->batch_frames : default_batch(ctx);
+  if (k == "ring_slots") return ctx->ring_slots;
   if (k == "stage_threads") return ctx->pool ? ctx->pool->threads() : ctx->stage_threads;
   if (k == "site_cap") return ctx->sys.site_cap;
   if (k == "n_pad") return ctx->sys.n_pad;
@@ -1250,6 +1304,33 @@ double cgc_get_option(const cgc_context* ctx, const char* key) {
 }
 
 int64_t cgc_launch_count(const cgc_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int cgc_debug_guard_check(int* n_buffers, int* n_damaged) {
+  if (n_buffers) *n_buffers = 0;
+  if (n_damaged) *n_damaged = 0;
+  if (!guard_on()) return CGC_ERR_STATE;
+  std::lock_guard<std::mutex> g(g_guard_mu);
+  std::vector<unsigned char> band(kGuardBytes + 256);
+  int bad = 0, n = 0, dev0 = 0;
+  cudaGetDevice(&dev0);
+  for (const auto& kv : g_guard_map) {
+    const GuardInfo& gi = kv.second;
+    if (cudaSetDevice(gi.device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return CGC_ERR_CUDA;
+    bool damaged = false;
+    for (int side = 0; side < 2; side++) {   // behind the buffer the band starts at its very last byte + 1
+      const char* src = side == 0 ? gi.base : gi.base + kGuardBytes + gi.bytes;
+      const size_t len = side == 0 ? kGuardBytes : kGuardBytes + (gi.padded - gi.bytes);
+      if (cudaMemcpy(band.data(), src, len, cudaMemcpyDeviceToHost) != cudaSuccess) return CGC_ERR_CUDA;
+      for (size_t k = 0; k < len; k++) damaged = damaged || band[k] != kGuardByte;
+    }
+    n++;
+    bad += damaged ? 1 : 0;
+  }
+  cudaSetDevice(dev0);
+  if (n_buffers) *n_buffers = n;
+  if (n_damaged) *n_damaged = bad;
+  return CGC_OK;
+}
 
 int cgc_kernel_times(cgc_context* ctx, double* ms, int64_t* launches, int reset) {
   if (!ctx || !ms || !launches) return fail(ctx, CGC_ERR_ARG, "null argument");
@@ -1299,7 +1380,7 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
   return guarded(ctx, [&]() {
     need_device(ctx);
     const DeviceSystem& sys = ctx->sys;
-    constexpr int K = cgc_context::kSlots;
+    const int K = ctx->ring_slots, kInFlight = K / 2, kStageAhead = K - kInFlight;
     const int B = ctx->batch_frames > 0 ? ctx->batch_frames : default_batch(ctx);
     const int64_t frame_text_max = std::max<int64_t>((int64_t)sys.n_atoms * sys.line_bytes, ctx->frame_span_max) + 4096;
     // is the text already page-locked (caller-pinned memory given to cgc_open_memory)?
@@ -1311,7 +1392,7 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
     }
     const double t_setup0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     auto wall = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    ensure_pipeline(ctx, B, frame_text_max * B, !direct);
+    ensure_pipeline(ctx, B, frame_text_max * B, !direct, K);
     const double t_setup1 = wall();
     ensure_cov(ctx);
     ensure_cov_buffers(ctx, B);
@@ -1490,7 +1571,7 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
 
     try {
       for (;;) {
-        while (n_staged < n_drained + K && n_staged < n_enq + cgc_context::kStageAhead + 1) {
+        while (n_staged < n_drained + K && n_staged < n_enq + kStageAhead + 1) {
           if (!plan_and_stage()) break;
         }
         if (n_enq == n_staged) break;   // everything planned is on the device, and there is nothing left to plan
@@ -1502,7 +1583,7 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
         enqueue(s);
         t_enqueue += now() - t0;
         n_enq++;
-        while (n_enq - n_drained > cgc_context::kInFlight) {
+        while (n_enq - n_drained > kInFlight) {
           drain(ctx->slot[n_drained % K]);
           n_drained++;
         }
@@ -1545,7 +1626,7 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
     int flags = 0;
     CUDA_OK(cudaMemcpy(&flags, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
     if (flags) {
-      CUDA_OK(cudaMemset(ctx->d_err, 0, sizeof(int)));
+      CUDA_OK(zero_now(ctx->d_err, sizeof(int)));
       std::string m = "device decode found malformed coordinate text:";
       if (flags & kDecBadChar) m += " unexpected character in a coordinate field;";
       if (flags & kDecBadPoint) m += " decimal point not at the column found in frame 0;";
@@ -1561,6 +1642,29 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
 }
 
 }  // namespace
+
+int cgc_prepare(cgc_context* ctx, int with_time_text) {
+  if (!ctx) return CGC_ERR_ARG;
+  if (!ctx->opened) return fail(ctx, CGC_ERR_STATE, "no trajectory opened");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    const DeviceSystem& sys = ctx->sys;
+    const int B = ctx->batch_frames > 0 ? ctx->batch_frames : default_batch(ctx);
+    const int64_t frame_text_max = std::max<int64_t>((int64_t)sys.n_atoms * sys.line_bytes, ctx->frame_span_max) + 4096;
+    bool direct = false;
+    if (!ctx->mapped) {
+      cudaPointerAttributes at;
+      direct = cudaPointerGetAttributes(&at, ctx->text) == cudaSuccess && at.type == cudaMemoryTypeHost;
+      cudaGetLastError();
+    }
+    ensure_pipeline(ctx, B, frame_text_max * B, !direct, ctx->ring_slots);
+    ensure_cov(ctx);
+    ensure_cov_buffers(ctx, B);
+    if (with_time_text) ensure_time_text(ctx, B);
+    copy_pool(ctx);
+    return CGC_OK;
+  });
+}
 
 void cgc_request_stop(cgc_context* ctx) {
   if (ctx) ctx->stop_requested.store(true);   // one atomic store: safe to call from a signal handler
@@ -1680,15 +1784,15 @@ int cgc_cov_bind(cgc_context* ctx, double* d_buffer) {
   return guarded(ctx, [&]() {
     need_device(ctx);
     if (!cov_enabled(ctx)) throw std::invalid_argument("covariance is switched off for this trajectory");
-    if (ctx->d_cov && !ctx->cov_bound) CUDA_OK(cudaFree(ctx->d_cov));
+    if (ctx->d_cov && !ctx->cov_bound) CUDA_OK(guard_free(ctx->d_cov));
     ctx->d_cov = d_buffer;
     ctx->cov_bound = true;
     ctx->shift_set = false;
     ctx->cov_rows_pending = 0;
-    CUDA_OK(cudaMemset(ctx->d_cov, 0, sizeof(double) * cov_doubles(ctx)));
+    CUDA_OK(zero_now(ctx->d_cov, sizeof(double) * cov_doubles(ctx)));
     ensure_cov(ctx);
     const int64_t SG = (int64_t)ctx->sys.n_sites * ctx->sys.num_tot;
-    CUDA_OK(cudaMemset(ctx->d_compat, 0, sizeof(float) * 2 * SG));
+    CUDA_OK(zero_now(ctx->d_compat, sizeof(float) * 2 * SG));
     return CGC_OK;
   });
 }
@@ -1700,8 +1804,8 @@ int cgc_cov_reset(cgc_context* ctx) {
     ensure_cov(ctx);
     if (!ctx->d_cov) throw std::invalid_argument("covariance is switched off for this trajectory");
     const int64_t SG = (int64_t)ctx->sys.n_sites * ctx->sys.num_tot;
-    CUDA_OK(cudaMemset(ctx->d_cov, 0, sizeof(double) * cov_doubles(ctx)));
-    CUDA_OK(cudaMemset(ctx->d_compat, 0, sizeof(float) * 2 * SG));
+    CUDA_OK(zero_now(ctx->d_cov, sizeof(double) * cov_doubles(ctx)));
+    CUDA_OK(zero_now(ctx->d_compat, sizeof(float) * 2 * SG));
     ctx->shift_set = false;
     ctx->cov_rows_pending = 0;
     return CGC_OK;
@@ -2481,7 +2585,7 @@ int cgc_write_mtx(cgc_context* ctx, const char* path, int compat) {
             m.resize((size_t)n);
             ok(cudaMemcpy(m.data(), d_m32, sizeof(float) * n, cudaMemcpyDeviceToHost));
           }
-          if (flag) cudaMemset(ctx->d_fmt_flags, 0, sizeof(int));
+          if (flag) zero_now(ctx->d_fmt_flags, sizeof(int));
         }
       }
       cudaFree(d_mean); cudaFree(d_covm); cudaFree(d_m32); cudaFree(d_txt); cudaFree(d_off);

@@ -135,9 +135,10 @@ static int die(cgc_context* ctx, int rc, const char* what) {
 struct Options {
   std::string traj, top, itp, out, structure, ckpt_path, resume_path;
   long long num_frames = 0, first = 0;
-  int sites = 0, batch = 0, stage_threads = 0;
+  int sites = 0, batch = 0, stage_threads = 0, ring_slots = 0;
   std::vector<int> devices;
   bool compat = false, no_mtx = false, verbose = false, timing = false, npy = false, host_format = false;
+  bool halve_batch = false;   // several contexts in one process: half the default batch (see run_multi)
 };
 
 // cgc_create + open + options for one device; on failure prints the reason and returns the exit status through *status
@@ -169,12 +170,23 @@ static cgc_context* open_context(const Options& o, int device, bool announce, in
     *status = die(ctx, rc, "setting --no-mtx");
     return nullptr;
   }
-  if (o.batch > 0 && (rc = cgc_set_option(ctx, "batch_frames", o.batch)) != CGC_OK) {
+  int batch = o.batch;
+  if (batch <= 0 && o.halve_batch) batch = std::max(1, (int)cgc_get_option(ctx, "batch_frames") / 2);
+  if (batch > 0 && (rc = cgc_set_option(ctx, "batch_frames", batch)) != CGC_OK) {
     *status = die(ctx, rc, "setting --batch-frames");
     return nullptr;
   }
   if (o.stage_threads > 0 && (rc = cgc_set_option(ctx, "stage_threads", o.stage_threads)) != CGC_OK) {
     *status = die(ctx, rc, "setting --stage-threads");
+    return nullptr;
+  }
+  if (o.ring_slots > 0 && (rc = cgc_set_option(ctx, "ring_slots", o.ring_slots)) != CGC_OK) {
+    *status = die(ctx, rc, "setting --ring-slots");
+    return nullptr;
+  }
+  // buffers before the frame loop (the device text path unless the host formatter was asked for)
+  if ((rc = cgc_prepare(ctx, o.host_format ? 0 : 1)) != CGC_OK) {
+    *status = die(ctx, rc, "allocating the streaming buffers");
     return nullptr;
   }
   return ctx;
@@ -414,6 +426,10 @@ static int run_multi(const Options& o) {
   const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
   Options per = o;
   if (per.stage_threads <= 0) per.stage_threads = (int)std::max(2u, std::min(16u, hw / (unsigned)R));
+  // R contexts in one process: every page-locked buffer is mapped into all R devices, so the ring costs R times what it
+  // costs alone, and with hw / R copier threads per GPU a batch is staged slowly anyway: a smaller ring of smaller batches
+  if (per.ring_slots <= 0) per.ring_slots = 4;
+  per.halve_batch = true;
   {
     std::vector<std::thread> th;
     for (int r = 0; r < R; r++) th.emplace_back([&, r] { ctx[(size_t)r] = open_context(per, o.devices[(size_t)r], r == 0, &status[(size_t)r]); });
@@ -526,7 +542,7 @@ int main(int argc, char** argv) {
     printf("Five inputs required for this program.\n");
     printf("Order of args: fmo_traj_path, fmo_top_path, bcx_itp_path, output_path, num_frames "
            "[--sites N] [--mtx-compat] [--no-mtx] [--device D] [--gpus N | --devices a,b,..] [--first-frame F] [--batch-frames B] "
-           "[--stage-threads T] [--verbose] [--structure frame0.gro (traj_in is then a .trr)] [--npy] [--host-format] "
+           "[--stage-threads T] [--ring-slots K] [--verbose] [--structure frame0.gro (traj_in is then a .trr)] [--npy] [--host-format] "
            "[--checkpoint FILE] [--resume FILE]\n"
            "Byte-for-byte the stock program's files: add --sites 7 --mtx-compat (defaults: every chromophore is a site, "
            "csv_out.mtx holds the covariance).\n");
@@ -561,6 +577,7 @@ int main(int argc, char** argv) {
     else if (a == "--first-frame") o.first = atoll(val("--first-frame"));
     else if (a == "--batch-frames") o.batch = atoi(val("--batch-frames"));
     else if (a == "--stage-threads") o.stage_threads = atoi(val("--stage-threads"));
+    else if (a == "--ring-slots") o.ring_slots = atoi(val("--ring-slots"));
     else if (a == "--structure") o.structure = val("--structure");
     else if (a == "--checkpoint") o.ckpt_path = val("--checkpoint");
     else if (a == "--resume") o.resume_path = val("--resume");

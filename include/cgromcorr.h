@@ -104,6 +104,7 @@ int64_t cgc_frame_atoms_offset(cgc_context *ctx, int64_t frame);
  *                src/FMOparse.cpp:133)
  * "covariance"   0/1: accumulate n, sum(x-c), sum (x-c)(x-c)^T per site while running (default 1 when it fits)
  * "batch_frames" frames per device batch (default: sized from the frame text size)
+ * "ring_slots"   batches in the streaming ring, 2..6 (default 6: three staged ahead by the copier threads, three on the device)
  * "stage_threads" host threads that copy trajectory text into the pinned staging ring (default min(16, cores); a process
  *                that runs one context per GPU divides its cores between them)
  * "profile"      0/1: time every hot-path kernel with CUDA events (see cgc_kernel_times)
@@ -123,6 +124,10 @@ double cgc_get_option(const cgc_context *ctx, const char *key);
  * On an error in the middle of the range (a malformed later frame) *frames_done, the rows delivered so far, the `.time`
  * text and the Correlate sums all cover the same frames: the sound batches before the error. */
 int cgc_run(cgc_context *ctx, int64_t first_frame, int64_t n_frames, float *dE_kcal, int64_t *frames_done);
+/* Allocate everything the streaming loop needs (device buffers, the pinned staging ring, the Correlate sums; with_time_text
+ * != 0: the buffers of the device text formatter and its writer) now instead of inside the first cgc_run /
+ * cgc_run_write_time — so that a caller can keep buffer set-up (tens of milliseconds) out of its frame loop.  Optional. */
+int cgc_prepare(cgc_context *ctx, int with_time_text);
 /* Ask the cgc_run / cgc_run_write_time in progress on this context (or the next one) to stop after the batches already
  * under way — the reference's SIGINT handling, "finish the current frame, then write .mtx" (src/FMOparse.cpp:24-29,62).
  * One atomic store: callable from a signal handler or another thread. */
@@ -159,6 +164,10 @@ int cgc_decode_device(cgc_context *ctx, const void *d_text, int64_t text_bytes, 
 int cgc_kernel_times(cgc_context *ctx, double *ms4, int64_t *launches4, int reset);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t cgc_launch_count(const cgc_context *ctx);
+/* Developer aid.  With CGC_GUARD=1 in the environment (read once per process) every device buffer the contexts own carries
+ * 4 KiB of a known byte pattern in front of it and behind it; this reads all bands back: *n_buffers guarded buffers alive,
+ * *n_damaged of them with a changed band, i.e. some kernel wrote out of bounds.  CGC_ERR_STATE when guarding is off. */
+int cgc_debug_guard_check(int *n_buffers, int *n_damaged);
 /* device-side decode error flags accumulated so far (0 = every coordinate field was well-formed) */
 int cgc_decode_errors(cgc_context *ctx, int *flags);
 

@@ -34,8 +34,12 @@ for g in gpu_list:
                        ("trr", [d + "/traj.trr", top, itp, d + "/out_trr", str(frames), "--structure", d + "/frame0.gro"])):
         for rep in range(2):
             t0 = time.time()
-            r = subprocess.run([build.CLI] + args + extra + ["--timing"], capture_output=True, text=True,
-                               env=dict(os.environ, CGC_TRACE="1") if rep == 1 else None)
+            try:
+                r = subprocess.run([build.CLI] + args + extra + ["--timing"], capture_output=True, text=True, timeout=180,
+                                   env=dict(os.environ, CGC_TRACE="1") if rep == 1 else None)
+            except subprocess.TimeoutExpired as e:
+                print("gpus %d %-14s rep %d TIMED OUT after 180 s | %s" % (g, name, rep, (e.stderr or b"")[-800:]), flush=True)
+                continue
             dt = time.time() - t0
             print("gpus %d %-14s rep %d rc %d wall %.2f s = %.0f frames/s | %s" % (g, name, rep, r.returncode, dt, frames / dt, r.stderr.strip()[-2400:]), flush=True)
     import hashlib

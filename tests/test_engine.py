@@ -210,3 +210,83 @@ def test_cli_two_gpus_in_one_process(small_inputs, tmp_path):
     assert ma.shape == mb.shape and np.all(np.abs(ma - mb) <= 2e-6 * np.abs(ma).max())
     r = subprocess.run([build.CLI, long_traj, top, itp, two, str(total), "--gpus", "2", "--mtx-compat"], capture_output=True, text=True)
     assert r.returncode == 1 and "one GPU" in r.stderr
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# What stands in for compute-sanitizer (closed on the B200 pool, profiles/r02_compute_sanitizer_refused.log): guard bands
+# around every device buffer, and a stress run whose results must be bit-identical — a race in K2's lock-free ring or its
+# per-warp reduction rows would show up as a changed bit.
+# ----------------------------------------------------------------------------------------------------------------------
+def test_guard_bands_stay_intact(small_inputs, tmp_path):
+    """Every hot-path kernel, all its buffers with 4 KiB guard bands on both sides (CGC_GUARD=1, own process): no band changes.
+    Covers K1 (text and .trr modes), K2, rows, K3 (several launch sizes), K5 text formatting, the device entry points."""
+    import sys
+    traj, top, itp, frames = small_inputs("permol")
+    traj2, top2, itp2, frames2 = small_inputs("tiny")
+    script = r'''
+import sys, os, numpy as np
+sys.path.insert(0, %r)
+from cgromcorrfmo_b200 import capi, synth
+import torch
+checked = 0
+for traj, top, itp, frames, reps in ((%r, %r, %r, %d, 7), (%r, %r, %r, %d, 30)):
+    blob = open(traj, "rb").read() * reps
+    path = os.path.join(%r, "g_%%d.gro" %% reps)
+    open(path, "wb").write(blob)
+    total = frames * reps
+    for batch in (1, 3, 0):
+        with capi.Context(top, itp, 0) as c:
+            c.open(path)
+            if batch:
+                c.set_option("batch_frames", batch)
+            c.set_option("mtx_compat", 1)
+            dE, done, rc = c.run_write_time(0, total, path + ".time", want_dE=True)
+            assert done == total
+            c.cov_finalize(1)
+            c.write_mtx(path + ".mtx")
+            text = np.frombuffer(blob, dtype=np.uint8)
+            d_text = torch.from_numpy(np.concatenate([text, np.zeros(((-text.size) %% 16) + 16, np.uint8)])).cuda()
+            offs = [c.frame_atoms_offset(f) for f in range(total)]
+            d_dE = torch.empty((total, c.n_sites, c.num_tot), dtype=torch.float32, device="cuda")
+            c.run_device(d_text.data_ptr(), text.size, offs, total, d_dE.data_ptr())
+            c.cov_accumulate_device(d_dE.data_ptr(), total)
+            xyz = torch.empty((total, c.dims()[0], 3), dtype=torch.float32, device="cuda")
+            c.decode_device(d_text.data_ptr(), text.size, offs, total, xyz.data_ptr())
+            torch.cuda.synchronize()
+            assert np.array_equal(d_dE.cpu().numpy().view(np.uint32), dE.view(np.uint32))
+            n, bad = capi.debug_guard_check()
+            assert n >= 10 and bad == 0, (n, bad)
+            checked += n
+print("GUARDS_OK", checked)
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), traj, top, itp, frames, traj2, top2, itp2, frames2, str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=dict(os.environ, CGC_GUARD="1"))
+    assert r.returncode == 0 and "GUARDS_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_stress_many_launch_shapes_bit_identical(small_inputs, capi_mod, tmp_path):
+    """K2's warps run free on an mbarrier ring and reuse per-warp shared-memory rows behind __syncwarp; K3 is a persistent
+    kernel on a TMA ring.  A hazard in either shows up as a result that depends on timing: 40 runs over different batch sizes
+    (hence unit ranges, chunk sizes, CTA counts, gather boundaries) must give bit-identical rows and covariance sums."""
+    capi = capi_mod
+    traj, top, itp, frames = small_inputs("nosolv")
+    long_traj = _repeat(traj, 24, str(tmp_path / "long.gro"))
+    total = frames * 24
+    ref_rows = ref_cov = None
+    for rep in range(40):
+        batch = (1, 2, 3, 5, 7, 11, 16, 48)[rep % 8]
+        with capi.Context(top, itp, 0) as c:
+            c.open(long_traj)
+            c.set_option("batch_frames", batch)
+            dE, done, _ = c.run(0, total)
+            assert done == total
+            part = c.cov_partials()
+        if ref_rows is None:
+            ref_rows = dE.copy()
+        assert np.array_equal(dE.view(np.uint32), ref_rows.view(np.uint32)), "rows differ at repetition %d (batch %d)" % (rep, batch)
+        # the Correlate sums depend on how the frames were cut into K3 launches only through FP64 rounding of exact sums of
+        # products: equal to 1e-12; for the SAME batch size they must be bit-identical
+        if rep < 8:
+            ref_cov = ref_cov or {}
+            ref_cov[batch] = part.copy()
+        else:
+            assert np.array_equal(part.view(np.uint64), ref_cov[batch].view(np.uint64)), "sums differ at repetition %d" % rep
