@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -433,14 +434,14 @@ void launch_finish(double* acc, float* dE, int64_t n, cudaStream_t st) {
 // keeps the reference's two float32 running sums when the literal .mtx is wanted.
 // cov_syrk_kernel is a persistent kernel, ONE CTA of 8 warps per SM.  Work unit = one 128 x 128 tile of one site's sumsq, or
 // one 128 x 64 half of it; the host deals the units out longest-first (LPT) into one list per CTA, the cheapest tiles cut in
-// halves so that the tail is short.  For every 16 frames the two operands — 128 (+4) columns of D each — arrive in shared
-// memory as TWO TMA tiled copies (cp.async.bulk.tensor.3d, SASS UTMALDG; box = 132 columns x 1 site x 16 frames: rows of
+// halves so that the tail is short.  For every 32 frames the two operands — 128 (+4) columns of D each — arrive in shared
+// memory as TWO TMA tiled copies (cp.async.bulk.tensor.3d, SASS UTMALDG; box = 132 columns x 1 site x 32 frames: rows of
 // 1056 contiguous bytes) of a tensor map over D; frames beyond the batch and columns beyond Gp are zero-filled by the TMA
 // unit, so the loop has no bounds.  The 132-column box makes the shared-memory row pitch 1056 B = 264 words == 8 (mod 32),
 // which puts the four frames of a DMMA fragment load into four different bank groups: every LDS.64 is conflict-free without
 // any swizzle.  (History, all at 19-21 TFLOP/s: 64 x 64 tiles staged by cp.async; 128 x 64 and 128 x 128 tiles fed by
 // sixteen 16-column boxes with 128-byte swizzle per stage — ncu put 26 % of the stall samples on the full-barrier wait with
-// L2 at 6 %: 256 row requests of 128 B per stage is more than the TMA unit turns around.)  A ring of 5 stages with a full /
+// L2 at 6 %: 256 row requests of 128 B per stage is more than the TMA unit turns around.)  A ring of 3 stages with a full /
 // empty mbarrier pair per stage runs ahead across tile boundaries; one elected thread issues the copies, no CTA-wide
 // barrier exists after start-up.  16 warps: warp w owns rows 32 (w & 3) .. +32 and columns 32 (w >> 2) .. +32 of the tile = 4 x 4
 // DMMA m8n8k4 tiles (32 FP64 accumulators per thread): per k-step of 4 frames 8 shared-memory loads feed 16 DMMAs, and
@@ -452,8 +453,16 @@ void launch_finish(double* acc, float* dE, int64_t n, cudaStream_t st) {
 // thread per launch and launches are stream-ordered, so the result is deterministic.
 constexpr int kCovBlk = 64;        // granularity of the stored upper triangle
 constexpr int kSyrkTile = 128;     // tile edge
-constexpr int kSyrkK = 16;         // frames per stage
-constexpr int kSyrkStages = 5;
+// measured on C5 (TFLOP/s): 8 frames x 8 stages 25.7, 16 x 6 27.8, 16 x 5 27.7, 16 x 4 28.4, 24 x 4 28.6, 32 x 3 28.7, 32 x 2 28.9,
+// 48 x 2 28.5 (profiles/r02_k3_variants.log): fewer, larger stages — fewer barrier round trips per DMMA
+#ifndef CGC_SYRK_K
+#define CGC_SYRK_K 32
+#endif
+#ifndef CGC_SYRK_STAGES
+#define CGC_SYRK_STAGES 3
+#endif
+constexpr int kSyrkK = CGC_SYRK_K;             // frames per stage (tuning builds override the two macros)
+constexpr int kSyrkStages = CGC_SYRK_STAGES;
 constexpr int kSyrkBoxCols = 132;  // columns per TMA box: the tile's 128 + 4, for a bank-conflict-free row pitch
 constexpr int kSyrkPitch = kSyrkBoxCols * 8;                                      // 1056 B
 constexpr int kSyrkOperandBytes = kSyrkPitch * kSyrkK;                            // 16896
@@ -675,13 +684,13 @@ cov_syrk_kernel(const __grid_constant__ CUtensorMap dmap, int n_frames, double* 
       const uint32_t b_addr = ring_addr + (uint32_t)st * kSyrkStageBytes + b_off + t_off;
       if (nj > 2) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) syrk_kstep<4>(acc, a_addr + q * 4 * kSyrkPitch, b_addr + q * 4 * kSyrkPitch);
+        for (int q = 0; q < kSyrkK / 4; q++) syrk_kstep<4>(acc, a_addr + q * 4 * kSyrkPitch, b_addr + q * 4 * kSyrkPitch);
       } else if (nj > 1) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) syrk_kstep<2>(acc, a_addr + q * 4 * kSyrkPitch, b_addr + q * 4 * kSyrkPitch);
+        for (int q = 0; q < kSyrkK / 4; q++) syrk_kstep<2>(acc, a_addr + q * 4 * kSyrkPitch, b_addr + q * 4 * kSyrkPitch);
       } else if (nj > 0) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) syrk_kstep<1>(acc, a_addr + q * 4 * kSyrkPitch, b_addr + q * 4 * kSyrkPitch);
+        for (int q = 0; q < kSyrkK / 4; q++) syrk_kstep<1>(acc, a_addr + q * 4 * kSyrkPitch, b_addr + q * 4 * kSyrkPitch);
       }
       // every read of the stage is done (the values are in registers): hand it back to the producer
       __syncwarp();
@@ -762,7 +771,10 @@ static const SyrkSchedule* syrk_schedule(int S, int G, int ctas) {
       }
   std::stable_sort(units.begin(), units.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
   // cut the cheapest tiles in halves
-  const size_t n_split = std::min(units.size(), (size_t)2 * ctas);
+  // half a round's worth, measured (C5, TFLOP/s): none 27.4, 0.5 rounds 27.8, 1 round 27.6, 2 rounds 26.0, 3 rounds 25.5 — a half
+  // unit leaves two of a sub-partition's four warps without work, so every split costs pipe utilisation while it runs
+  size_t n_split = std::min(units.size(), (size_t)ctas / 2);
+  if (const char* e = getenv("CGC_SYRK_SPLIT_PCT")) n_split = std::min(units.size(), (size_t)(atoll(e) * ctas / 100));   // tuning hook
   std::vector<U> tail(units.end() - (long)n_split, units.end());
   units.resize(units.size() - n_split);
   for (const U& t : tail) {
