@@ -392,9 +392,10 @@ def write_shared_trajectory(path, blob_text, frame_bytes, frames_per_rank, rank,
     barrier()
 
 
-def run_cli(traj, top, itp, out, frames, gpus, extra=()):
+def run_cli(traj, top, itp, out, frames, devices, extra=()):
     from cgromcorrfmo_b200 import build
-    cmd = [build.CLI, traj, top, itp, out, str(frames), "--timing"] + (["--gpus", str(gpus)] if gpus > 1 else []) + list(extra)
+    multi = ["--devices", ",".join(str(d) for d in devices)] if len(devices) > 1 else ["--device", str(devices[0])]
+    cmd = [build.CLI, traj, top, itp, out, str(frames), "--timing"] + multi + list(extra)
     t0 = time.perf_counter()
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
@@ -405,7 +406,7 @@ def run_cli(traj, top, itp, out, frames, gpus, extra=()):
     return dict(rc=r.returncode, wall_s=wall, in_loop=float(m.group(1)) if m else None, timing=r.stderr.strip().split("\n")[-1][-900:])
 
 
-def cli_leg(shm_dir, top, itp, text, frame_bytes, frames_per_rank, rank, world, barrier, expect_rows, S, G):
+def cli_leg(shm_dir, top, itp, text, frame_bytes, frames_per_rank, rank, world, barrier, expect_rows, S, G, devices):
     """traj2dEcsv on a real .gro file in the page cache (tmpfs).  Rank 0 runs it (N > 1: ONE process, --gpus N) while the
     other ranks stay out of the way; returns the result dict on rank 0."""
     from cgromcorrfmo_b200 import capi
@@ -419,7 +420,7 @@ def cli_leg(shm_dir, top, itp, text, frame_bytes, frames_per_rank, rank, world, 
         try:
             total = frames_per_rank * world
             out = os.path.join(shm_dir, "cgc_bench_out")
-            runs = [run_cli(traj, top, itp, out, total, world) for _ in range(2)]   # the first run also warms the driver caches
+            runs = [run_cli(traj, top, itp, out, total, devices) for _ in range(2)]   # the first run also warms the driver caches
             best = min((r for r in runs if r["rc"] == 0), key=lambda r: r["wall_s"], default=None)
             res = {"runs": runs}
             if best is not None:
@@ -437,7 +438,7 @@ def cli_leg(shm_dir, top, itp, text, frame_bytes, frames_per_rank, rank, world, 
                     "input": "%.2f GB .gro in %s" % (total * frame_bytes / 1e9, shm_dir),
                     "outputs": "csv_out.time %.2f GB + csv_out.mtx, also in %s" % (size / 1e9, shm_dir),
                     "time_text_matches_cgc_run_rows": bool(gb == wb), "time_text_bytes_checked": len(wb),
-                    "api": "traj2dEcsv traj_in topology excited_itp csv_out num_frames" + (" --gpus %d" % world if world > 1 else ""),
+                    "api": "traj2dEcsv traj_in topology excited_itp csv_out num_frames" + (" --devices %s" % ",".join(str(d) for d in devices) if world > 1 else ""),
                     "timing": best["timing"]})
                 os.remove(want)
             for suffix in (".time", ".mtx"):
@@ -730,7 +731,8 @@ def run_ours(args):
             try:
                 free = shutil.disk_usage(shm).free
                 per_rank = int(max(F, min(per_rank, (free // 3) // (frame_bytes * world))))
-                cli = cli_leg(shm, top, itp, bytes(blob), frame_bytes, per_rank, rank, world, barrier, out_host, S, G)
+                devices = [device_for_rank(r, world, torch.cuda.device_count()) for r in range(world)]
+                cli = cli_leg(shm, top, itp, bytes(blob), frame_bytes, per_rank, rank, world, barrier, out_host, S, G, devices)
             except Exception as e:  # reported, never required
                 log("bench: e2e_cli leg failed:", e)
                 barrier()
