@@ -616,8 +616,15 @@ def run_ours(args):
         ctx.kernel_times(reset=True)
         t0 = time.perf_counter()
         e0.record()
+        step_s = []
         for _ in range(args.steps):
+            ts = time.perf_counter()
             ctx.run(0, F_me, out=out_host)
+            step_s.append(time.perf_counter() - ts)
+        if os.environ.get("CGC_BENCH_STEP_TIMES") and rank == 0:
+            log("bench: e2e per-step ms: first %s ... last %s | min %.2f median %.2f max %.2f" % (
+                ["%.1f" % (x * 1e3) for x in step_s[:6]], ["%.1f" % (x * 1e3) for x in step_s[-6:]],
+                min(step_s) * 1e3, float(np.median(step_s)) * 1e3, max(step_s) * 1e3))
         combine(cov)
         e1.record()
         barrier()
@@ -785,7 +792,7 @@ def run_ours(args):
     ]
     if cov_on:
         others.append(
-            {"kernel": "cov_syrk_kernel+cov_sum_kernel (K3)", "bound": "fp64 tensor (DMMA)", "achieved": k3_flop / k3_avg_s / 1e12 if k3_avg_s else 0.0,
+            {"kernel": "cov_centre_kernel+cov_syrk_kernel (K3)", "bound": "fp64 tensor (DMMA)", "achieved": k3_flop / k3_avg_s / 1e12 if k3_avg_s else 0.0,
              "peak": fp64_peak, "unit": "TFLOP/s", "frac": (k3_flop / k3_avg_s / 1e12 / fp64_peak) if (k3_avg_s and fp64_peak) else None,
              "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)",
              "algorithmic_flop_per_launch": k3_flop, "avg_launch_ms": k3_avg_s * 1e3,
@@ -943,8 +950,11 @@ def run_c5(args, torch, dist, capi, world, rank, local, dev, F, peaks):
                 "api": "float32 rows from pinned host memory -> cgc_cov_accumulate_device; the frame count read back"},
         "gpu_launches": int(launches), "kernel_ms": {k: v[0] for k, v in ktimes.items()},
         "covariance_max_scaled_error_vs_numpy": err,
-        "roofline": {"kernel": "cov_syrk_kernel+cov_sum_kernel (K3)", "bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": ach / fp64_peak if fp64_peak else None, "traffic": None,
+        "roofline": {"kernel": "cov_centre_kernel+cov_syrk_kernel (K3)", "bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": ach / fp64_peak if fp64_peak else None,
+                     "traffic": 902321408.0 if F == 1024 else None,
+                     "traffic_source": "profiles/r02_k3_cov_syrk_kernel_ncu.txt (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum of one cov_syrk launch of 1024 frames)",
+                     "algorithmic_bytes_per_launch": F * S * ((G + 15) // 16 * 16) * 8 + 2 * S * G * G * 8,
                      "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (no FP64 figure in MEASURED_PEAKS.json)",
                      "algorithmic_flop_per_launch": k3_flop, "avg_launch_ms": k3_avg_s * 1e3},
         "cpu_baseline": cpu,

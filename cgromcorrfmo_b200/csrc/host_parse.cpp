@@ -1,6 +1,10 @@
 // Host-side text front end (see host_parse.h).  Runs once per trajectory.
 #include "host_parse.h"
 
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
 #include <cctype>
 #include <cstdlib>
 #include <cstring>
@@ -453,6 +457,39 @@ bool locate_trr_frame(const char* data, int64_t nbytes, int64_t pos, TrrFrame& o
   out.step = step;
   if (out.end > nbytes) return cut();
   return true;
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static void copy_nt_avx2(char* dst, const char* src, size_t n) {
+  size_t head = (32 - ((uintptr_t)dst & 31)) & 31;
+  if (head > n) head = n;
+  memcpy(dst, src, head);
+  dst += head; src += head; n -= head;
+  const size_t blocks = n / 128;
+  for (size_t i = 0; i < blocks; i++) {
+    const __m256i a = _mm256_loadu_si256((const __m256i*)(src + 128 * i));
+    const __m256i b = _mm256_loadu_si256((const __m256i*)(src + 128 * i + 32));
+    const __m256i c = _mm256_loadu_si256((const __m256i*)(src + 128 * i + 64));
+    const __m256i d = _mm256_loadu_si256((const __m256i*)(src + 128 * i + 96));
+    _mm256_stream_si256((__m256i*)(dst + 128 * i), a);
+    _mm256_stream_si256((__m256i*)(dst + 128 * i + 32), b);
+    _mm256_stream_si256((__m256i*)(dst + 128 * i + 64), c);
+    _mm256_stream_si256((__m256i*)(dst + 128 * i + 96), d);
+  }
+  memcpy(dst + 128 * blocks, src + 128 * blocks, n - 128 * blocks);
+  _mm_sfence();   // the copy engine reads the buffer next: the streamed lines must be globally visible
+}
+#endif
+
+void stream_copy(char* dst, const char* src, size_t n, bool streaming) {
+#if defined(__x86_64__)
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (streaming && avx2 && n >= 4096) {
+    copy_nt_avx2(dst, src, n);
+    return;
+  }
+#endif
+  memcpy(dst, src, n);
 }
 
 }  // namespace cgc

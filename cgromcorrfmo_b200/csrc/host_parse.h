@@ -90,4 +90,9 @@ bool locate_trr_frame(const char* data, int64_t nbytes, int64_t pos, TrrFrame& o
 // fixed-column layout check.  Throws Unsupported when the atom lines are not fixed-column.
 void scan_first_frame(const char* text, int64_t nbytes, FrameLayout& out, FrameSpan& span);
 
+// memcpy for the staging copies (page cache -> pinned ring): with `streaming` the destination is written with
+// non-temporal stores (AVX2, when the CPU has it), which spares the read-for-ownership of the destination lines — a
+// third of the copy's DRAM traffic on a host whose memory system is what bounds the file path.
+void stream_copy(char* dst, const char* src, size_t n, bool streaming);
+
 }  // namespace cgc
