@@ -614,6 +614,7 @@ def run_ours(args):
             ctx.run(0, F_me, out=out_host)
         barrier()
         ctx.kernel_times(reset=True)
+        ctx.copy_times(reset=True)
         t0 = time.perf_counter()
         e0.record()
         step_s = []
@@ -635,6 +636,13 @@ def run_ours(args):
             e2e_s = float(t.item())
         e2e_value = sum(share) * args.steps / e2e_s
         e2e_ktimes = ctx.kernel_times(reset=True)
+        copy_ms, n_copies = ctx.copy_times(reset=True)
+        link = [copy_ms / (e2e_s * 1e3), F_me * args.steps * frame_bytes / max(copy_ms, 1e-9) / 1e6]   # busy fraction, GB/s while copying
+        if world > 1:
+            t = torch.zeros(2 * world, dtype=torch.float64, device=dev)
+            t[2 * rank], t[2 * rank + 1] = link[0], link[1]
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            link = [float(v) for v in t.tolist()]
         same = bool(np.array_equal(out_host.view(np.uint32), d_dE.cpu().numpy().view(np.uint32)))
         h2d_ceiling_fps = sum(h2d_rates) * 1e9 / frame_bytes           # every link at its concurrent rate
 
@@ -830,6 +838,7 @@ def run_ours(args):
                                    "while ALL ranks copy (barrier-synchronised start); measured in this run, just before the leg",
                 "h2d_concurrent_gbs_per_rank": h2d_rates, "h2d_alone_gbs": h2d_alone,
                 "frames_per_step_per_rank": share,
+                "h2d_link_busy_fraction_per_rank": link[0::2], "h2d_gbs_while_copying_per_rank": link[1::2],
                 "sharding": "frames dealt out in proportion to each rank's concurrent H2D rate"},
         "e2e_trr": {"value": trr_value, "unit": UNIT, "h2d_bytes_per_step": int(n_trr + 8 * F), "d2h_bytes_per_step": int(F * S * G * 4),
                     "api": "cgc_open_memory_trr + cgc_run on pinned .trr frames (float32 coordinates + box, %d B/frame), %d-frame batches"

@@ -60,6 +60,7 @@ SIGNATURES = {
     "cgc_run_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "cgc_decode_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "cgc_kernel_times": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
+    "cgc_copy_times": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), c_int]),
     "cgc_launch_count": (c_int64, [c_void_p]),
     "cgc_debug_guard_check": (c_int, [POINTER(c_int), POINTER(c_int)]),
     "cgc_decode_errors": (c_int, [c_void_p, POINTER(c_int)]),
@@ -353,6 +354,12 @@ class Context:
         off = np.ascontiguousarray(atoms_offset, dtype=np.int64)
         self._check(self._lib.cgc_decode_device(self._h, _ptr(d_text), int(text_bytes), _ptr(off), int(n_frames),
                                                 _ptr(d_xyz), c_void_p(int(stream))))
+
+    def copy_times(self, reset: bool = False):
+        """(ms, copies): device time of the H2D copies of the trajectory text since "profile" was switched on."""
+        ms, n = c_double(0), c_int64(0)
+        self._check(self._lib.cgc_copy_times(self._h, ctypes.byref(ms), ctypes.byref(n), 1 if reset else 0))
+        return ms.value, n.value
 
     def kernel_times(self, reset: bool = False):
         """{kernel: (ms, launches)} accumulated since option "profile" was switched on (CUDA events on the launch stream)."""

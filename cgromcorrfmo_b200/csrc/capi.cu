@@ -321,8 +321,8 @@ struct cgc_context {
   struct Timed { cudaEvent_t a, b; int kind; };
   std::vector<Timed> timed;            // recorded, not yet read
   std::vector<cudaEvent_t> ev_pool;    // recycled events
-  double kernel_ms[4] = {0, 0, 0, 0};  // K1 decode, K2 cdc, finish, K3 cov
-  int64_t kernel_n[4] = {0, 0, 0, 0};
+  double kernel_ms[5] = {0, 0, 0, 0, 0};  // K1 decode, K2 cdc, finish, K3 cov, [4] the H2D copies of the text
+  int64_t kernel_n[5] = {0, 0, 0, 0, 0};
 
   // Correlate
   double* d_cov = nullptr;
@@ -861,8 +861,9 @@ struct ScopedKernelTimer {
   bool on;
   ScopedKernelTimer(cgc_context* c_, int kind, cudaStream_t st_) : c(c_), st(st_), on(c_->profile) {
     // the reference's timer scopes FileRead / dE_compute / Correlate (src/FMOparse.cpp:33-36) as NVTX ranges
-    static const char* const kNames[4] = {"cgc:FileRead(K1 decode)", "cgc:dE_compute(K2 CDC)", "cgc:dE_rows(finish)", "cgc:Correlate(K3)"};
-    nvtxRangePushA(kNames[kind & 3]);
+    static const char* const kNames[5] = {"cgc:FileRead(K1 decode)", "cgc:dE_compute(K2 CDC)", "cgc:dE_rows(finish)", "cgc:Correlate(K3)",
+                                          "cgc:FileRead(H2D copy)"};
+    nvtxRangePushA(kNames[kind < 5 ? kind : 0]);
     if (!on) return;
     t.a = take_event(c);
     t.b = take_event(c);
@@ -1353,6 +1354,21 @@ int cgc_kernel_times(cgc_context* ctx, double* ms, int64_t* launches, int reset)
   });
 }
 
+int cgc_copy_times(cgc_context* ctx, double* ms, int64_t* copies, int reset) {
+  if (!ctx || !ms || !copies) return fail(ctx, CGC_ERR_ARG, "null argument");
+  return guarded(ctx, [&]() {
+    need_device(ctx);
+    collect_kernel_times(ctx);
+    *ms = ctx->kernel_ms[4];
+    *copies = ctx->kernel_n[4];
+    if (reset) {
+      ctx->kernel_ms[4] = 0;
+      ctx->kernel_n[4] = 0;
+    }
+    return CGC_OK;
+  });
+}
+
 int cgc_decode_errors(cgc_context* ctx, int* flags) {
   if (!ctx || !flags) return fail(ctx, CGC_ERR_ARG, "null argument");
   return guarded(ctx, [&]() {
@@ -1513,7 +1529,10 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
 
     auto enqueue = [&](Slot& s) {
       const int want = s.frames;
-      CUDA_OK(cudaMemcpyAsync(s.d_text, s.src, (size_t)s.nb, cudaMemcpyHostToDevice, ctx->st_copy));
+      {
+        ScopedKernelTimer t(ctx, 4, ctx->st_copy);
+        CUDA_OK(cudaMemcpyAsync(s.d_text, s.src, (size_t)s.nb, cudaMemcpyHostToDevice, ctx->st_copy));
+      }
       CUDA_OK(cudaMemcpyAsync(s.d_off, s.h_off, sizeof(int64_t) * want, cudaMemcpyHostToDevice, ctx->st_copy));
       CUDA_OK(cudaEventRecord(s.ev_copied, ctx->st_copy));
       CUDA_OK(cudaStreamWaitEvent(ctx->st_comp, s.ev_copied, 0));

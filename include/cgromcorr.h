@@ -162,6 +162,9 @@ int cgc_decode_device(cgc_context *ctx, const void *d_text, int64_t text_bytes, 
  * accumulated device time in ms and the launch count per kernel: [0] K1 decode, [1] K2 CDC pair sum, [2] FP64 bins ->
  * float32 rows, [3] K3 Correlate.  Synchronises on the recorded events.  reset != 0 clears the totals. */
 int cgc_kernel_times(cgc_context *ctx, double *ms4, int64_t *launches4, int reset);
+/* With option "profile" = 1 the host->device copies of the trajectory text (cgc_run's copy stream) are bracketed by events
+ * too: accumulated device time of those copies in ms and their count.  Copy time / wall time of a run = how busy the link was. */
+int cgc_copy_times(cgc_context *ctx, double *ms, int64_t *copies, int reset);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t cgc_launch_count(const cgc_context *ctx);
 /* Developer aid.  With CGC_GUARD=1 in the environment (read once per process) every device buffer the contexts own carries
