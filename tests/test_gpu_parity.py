@@ -520,6 +520,8 @@ def test_kernel_timing_hook(small_inputs, capi_mod):
         assert all(ms > 0 for ms, _ in kt.values())
         assert c.launch_count - n0 >= 5
         assert c.kernel_times()["cdc"] == (0.0, 0)
+        ms, copies = c.copy_times(reset=True)              # the H2D copy of the batch's text, on the copy stream
+        assert copies == 1 and ms > 0 and c.copy_times() == (0.0, 0)
 
 
 def test_c1_shape_against_the_stock_reference_program(tmp_path, oracle_mod, capi_mod):
