@@ -16,8 +16,8 @@ F = 256) is far larger than the 126 MB L2.
   value     frames/s, whole job, text resident in HBM when the timed region starts (cgc_run_device + K3)
   e2e       frames/s through the C-ABI call a user makes (cgc_run) with HOST buffers: pinned text in, H2D copies, kernels,
             D2H of the dE rows — all inside the timed region
-  e2e_cli   the drop-in program itself (traj2dEcsv, C++): a real .gro file in /dev/shm -> csv_out.time + csv_out.mtx, whole
-            process and frame loop; at N > 1 ONE process drives the N GPUs (traj2dEcsv --gpus N, ncclAllReduce)
+  e2e_cli   the drop-in program itself (traj2dEcsv, C++): a real .gro file in /dev/shm (6144 frames = 27.6 GB at N = 1, 1024 per
+            GPU at N > 1) -> csv_out.time + csv_out.mtx, whole process and frame loop; at N > 1 ONE process drives the N GPUs (traj2dEcsv --gpus N, ncclAllReduce)
   N > 1     one process per GPU (torchrun), every rank streams its own frame range (weak scaling, no data-path
             collective); the Correlate partial sums are combined by ONE NCCL all-reduce, inside the timed region;
             allreduce_check compares the merged covariance with a single-rank run over the same frames
@@ -742,7 +742,7 @@ def run_ours(args):
         cli = None
         if not args.no_cli and name in ("C1", "C2"):
             shm = "/dev/shm" if os.path.isdir("/dev/shm") else d
-            per_rank = args.cli_frames or (2048 if world == 1 else 1024)
+            per_rank = args.cli_frames or (6144 if world == 1 else 1024)   # long enough that the fill and drain of the pipeline do not dominate
             try:
                 free = shutil.disk_usage(shm).free
                 per_rank = int(max(F, min(per_rank, (free // 3) // (frame_bytes * world))))
