@@ -15,8 +15,9 @@ CLI = os.path.join(HERE, "traj2dEcsv")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-pthread"]
-LIB_SOURCES = ["kernels.cu", "format_kernel.cu", "eigh_kernel.cu", "timecorr_kernel.cu", "parse_kernel.cu", "capi.cu", "host_parse.cpp"]
-LIB_DEPS = LIB_SOURCES + ["kernels.cuh", "cdc_kernel.cuh", "ptx_helpers.cuh", "fmt_g.h", "host_parse.h", "../../include/cgromcorr.h"]
+LIB_SOURCES = ["kernels.cu", "format_kernel.cu", "eigh_kernel.cu", "timecorr_kernel.cu", "parse_kernel.cu", "xtc_kernel.cu", "capi.cu",
+               "host_parse.cpp", "xtc_host.cpp"]
+LIB_DEPS = LIB_SOURCES + ["kernels.cuh", "cdc_kernel.cuh", "ptx_helpers.cuh", "fmt_g.h", "host_parse.h", "xtc_bits.h", "../../include/cgromcorr.h"]
 CLI_SOURCES = ["traj2dEcsv.cpp"]
 
 

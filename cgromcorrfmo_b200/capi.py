@@ -39,6 +39,9 @@ SIGNATURES = {
     "cgc_open_memory": (c_int, [c_void_p, c_void_p, c_int64]),
     "cgc_open_trr": (c_int, [c_void_p, c_char_p, c_char_p]),
     "cgc_open_memory_trr": (c_int, [c_void_p, c_void_p, c_int64, c_char_p]),
+    "cgc_open_xtc": (c_int, [c_void_p, c_char_p, c_char_p]),
+    "cgc_open_memory_xtc": (c_int, [c_void_p, c_void_p, c_int64, c_char_p]),
+    "cgc_xtc_encode": (c_int64, [c_void_p, c_int, c_int, c_float, c_void_p, c_float, c_void_p, c_int64]),
     "cgc_dims": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "cgc_get_groups": (c_int, [c_void_p, c_void_p]),
     "cgc_get_columns": (c_int, [c_void_p, c_void_p]),
@@ -130,6 +133,22 @@ def _ptr(a):
     if isinstance(a, np.ndarray):
         return a.ctypes.data_as(c_void_p)
     return c_void_p(int(a))  # a raw address (e.g. torch.Tensor.data_ptr())
+
+
+def xtc_encode(coords, step: int = 0, time_ps: float = 0.0, box=None, precision: float = 1000.0) -> bytes:
+    """One GROMACS .xtc frame from integer coordinates [n_atoms, 3] (units of 1 / precision nm); host only, no GPU."""
+    lib = load()
+    c = np.ascontiguousarray(coords, dtype=np.int32).reshape(-1, 3)
+    b = None if box is None else np.ascontiguousarray(box, dtype=np.float32).reshape(9)
+    cap = 64 + 16 * c.shape[0]
+    while True:
+        out = np.empty(cap, np.uint8)
+        n = lib.cgc_xtc_encode(_ptr(c), c.shape[0], int(step), float(time_ps), _ptr(b), float(precision), _ptr(out), cap)
+        if n < 0:
+            raise CgcError(CGC_ERR_UNSUPPORTED, lib.cgc_last_error(None).decode(errors="replace"))
+        if n <= cap:
+            return out[:n].tobytes()
+        cap = int(n)
 
 
 class Context:
@@ -228,6 +247,28 @@ class Context:
             self._keep = arr
             addr, n = arr.ctypes.data, arr.size
         self._check(self._lib.cgc_open_memory_trr(self._h, c_void_p(addr), n, os.fsencode(structure_gro)))
+        return self
+
+    def open_xtc(self, xtc_path: str, structure_gro: str):
+        """GROMACS .xtc (compressed) coordinates, decoded on the device; names / residues from frame 0 of `structure_gro`."""
+        self._keep = None
+        self._check(self._lib.cgc_open_xtc(self._h, os.fsencode(xtc_path), os.fsencode(structure_gro)))
+        return self
+
+    def open_memory_xtc(self, data, structure_gro: str):
+        """data: bytes / numpy uint8 array / (address, nbytes) holding .xtc frames.  NOT copied; kept alive here."""
+        if isinstance(data, tuple):
+            addr, n = data
+            self._keep = None
+        elif isinstance(data, (bytes, bytearray)):
+            arr = np.frombuffer(data, dtype=np.uint8)
+            self._keep = (data, arr)
+            addr, n = arr.ctypes.data, arr.size
+        else:
+            arr = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+            self._keep = arr
+            addr, n = arr.ctypes.data, arr.size
+        self._check(self._lib.cgc_open_memory_xtc(self._h, c_void_p(addr), n, os.fsencode(structure_gro)))
         return self
 
     def dims(self):

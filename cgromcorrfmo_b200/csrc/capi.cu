@@ -237,6 +237,7 @@ struct Slot {
   int64_t* d_off = nullptr;
   int64_t* h_off = nullptr;  // pinned
   float* d_xyz8 = nullptr;
+  void* d_xtc = nullptr;     // .xtc only: checkpoint table of K1x's index pass
   float4* d_sites = nullptr;
   double* d_acc = nullptr;   // K2's bins
   float* d_dE = nullptr;
@@ -277,7 +278,9 @@ struct cgc_context {
   bool index_complete = false;
   bool opened = false;
   int trr_real = 0;               // 0: .gro text; 4 / 8: .trr with single / double precision coordinates
-  int64_t frame_span_max = 0;     // .trr: largest distance between the coordinate arrays of consecutive frames
+  bool xtc = false;               // GROMACS .xtc (compressed coordinates, frames of varying size)
+  float xtc_precision = 0.f;      // of frame 0
+  int64_t frame_span_max = 0;     // .trr / .xtc: largest distance between the coordinate data of consecutive frames
 
   // static per-atom data (host copies kept for the getters)
   std::vector<float> q_ground;    // table charge of the atom's own key
@@ -361,6 +364,7 @@ void free_pipeline(cgc_context* c) {
     if (s.d_off) guard_free(s.d_off);
     if (s.h_off) cudaFreeHost(s.h_off);
     if (s.d_xyz8) guard_free(s.d_xyz8);
+    if (s.d_xtc) guard_free(s.d_xtc);
     if (s.d_sites) guard_free(s.d_sites);
     if (s.d_acc) guard_free(s.d_acc);
     if (s.d_dE) guard_free(s.d_dE);
@@ -372,7 +376,7 @@ void free_pipeline(cgc_context* c) {
     if (s.ev_copied) cudaEventDestroy(s.ev_copied);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     if (s.ev_text_out) cudaEventDestroy(s.ev_text_out);
-    s.h_text = nullptr; s.d_text = nullptr; s.d_off = nullptr; s.h_off = nullptr; s.d_xyz8 = nullptr; s.d_sites = nullptr;
+    s.h_text = nullptr; s.d_text = nullptr; s.d_off = nullptr; s.h_off = nullptr; s.d_xyz8 = nullptr; s.d_xtc = nullptr; s.d_sites = nullptr;
     s.d_acc = nullptr; s.d_dE = nullptr; s.h_dE = nullptr; s.d_ttext = nullptr; s.d_rowoff = nullptr; s.h_tinfo = nullptr;
     s.d_fmt_flag = nullptr; s.ttext_cap = 0; s.ev_copied = s.ev_done = s.ev_text_out = nullptr;
     s.text_out_pending = false; s.staged_here = false; s.src = nullptr; s.nb = 0; s.frames = 0; s.out_frame = 0; s.busy = false;
@@ -521,7 +525,7 @@ void build_static(cgc_context* c) {
   sys.x_col = L.x_col;
   sys.field_w = L.field_w;
   sys.ndec = L.ndec;
-  sys.traj_mode = c->trr_real == 4 ? 1 : c->trr_real == 8 ? 2 : 0;
+  sys.traj_mode = c->xtc ? 3 : c->trr_real == 4 ? 1 : c->trr_real == 8 ? 2 : 0;
   // dQ != 0 atoms of every computed site, in file order (zero-dQ atoms add exactly +-0 to every bin)
   std::vector<int> count(sys.n_sites, 0);
   std::vector<int32_t> slot(sys.n_pad, -1);
@@ -636,6 +640,7 @@ void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_ho
     CUDA_OK(guard_malloc((void**)&s.d_off, sizeof(int64_t) * batch));
     CUDA_OK(cudaHostAlloc(&s.h_off, sizeof(int64_t) * batch, cudaHostAllocDefault));
     CUDA_OK(guard_malloc((void**)&s.d_xyz8, sizeof(float) * 3 * (size_t)sys.n_pad * batch));
+    if (sys.traj_mode == 3) CUDA_OK(guard_malloc(&s.d_xtc, xtc_scratch_bytes(sys, batch)));
     CUDA_OK(guard_malloc((void**)&s.d_sites, (size_t)16 * sys.n_sites * sys.site_cap * batch));
     CUDA_OK(guard_malloc((void**)&s.d_acc, sizeof(double) * sg * batch));
     CUDA_OK(cudaMemsetAsync(s.d_acc, 0, sizeof(double) * sg * batch, c->st_comp));
@@ -819,7 +824,21 @@ int64_t index_upto(cgc_context* c, int64_t upto) {
     int64_t pos = c->frames.empty() ? 0 : c->frames.back().end;
     FrameSpan sp;
     bool trunc = false;
-    if (c->trr_real) {
+    if (c->xtc) {
+      XtcFrame xf;
+      if (!locate_xtc_frame(c->text, c->nbytes, pos, xf, &trunc)) {
+        c->index_complete = true;
+        break;
+      }
+      if (xf.n_atoms != c->L.n_atoms) {
+        throw InputFileMalformed("Number of atoms changes between frames; the group layout of the structure file no longer applies.");
+      }
+      sp.begin = xf.begin;
+      sp.atoms = xf.coords;
+      sp.end = xf.end;
+      if (!c->frames.empty()) c->frame_span_max = std::max(c->frame_span_max, sp.end - c->frames.back().atoms);
+      c->frame_span_max = std::max(c->frame_span_max, sp.end - sp.begin);
+    } else if (c->trr_real) {
       TrrFrame tf;
       if (!locate_trr_frame(c->text, c->nbytes, pos, tf, &trunc)) {
         c->index_complete = true;
@@ -962,13 +981,25 @@ void accumulate_rows(cgc_context* c, const float* d_dE, int n_frames, cudaStream
 }
 
 // K1 -> K2 -> finish (-> K3) for one batch whose text is already in d_text; everything on `st`
-void enqueue_compute(cgc_context* c, const char* d_text, int64_t text_bytes, const int64_t* d_off, int n_frames,
-                     float* d_xyz8, float4* d_sites, double* d_acc, float* d_dE, bool accumulate, cudaStream_t st) {
-  const DeviceSystem& sys = c->sys;
-  {
-    ScopedKernelTimer t(c, 0, st);
-    launch_decode(sys, d_text, text_bytes, d_off, n_frames, d_xyz8, d_sites, c->d_err, st);
+void enqueue_decode(cgc_context* c, const char* d_text, int64_t text_bytes, const int64_t* d_off, int n_frames, const Slot& s,
+                    cudaStream_t st) {
+  ScopedKernelTimer t(c, 0, st);
+  if (c->sys.traj_mode == 3) {
+    launch_xtc_decode(c->sys, d_text, text_bytes, d_off, n_frames, s.d_xtc, s.d_xyz8, s.d_sites, c->d_err, st);
+    c->launches += 1;   // index pass + unpack pass: one launch more than the callers count for the decode step
+  } else {
+    launch_decode(c->sys, d_text, text_bytes, d_off, n_frames, s.d_xyz8, s.d_sites, c->d_err, st);
   }
+}
+
+// `s`: the slot whose scratch (coordinates, site blocks, bins, .xtc checkpoints) the batch uses
+void enqueue_compute(cgc_context* c, const char* d_text, int64_t text_bytes, const int64_t* d_off, int n_frames,
+                     const Slot& s, float* d_dE, bool accumulate, cudaStream_t st) {
+  const DeviceSystem& sys = c->sys;
+  float* d_xyz8 = s.d_xyz8;
+  float4* d_sites = s.d_sites;
+  double* d_acc = s.d_acc;
+  enqueue_decode(c, d_text, text_bytes, d_off, n_frames, s, st);
   {
     ScopedKernelTimer t(c, 1, st);
     launch_cdc(sys, d_xyz8, d_sites, d_acc, n_frames, c->sm_count, st);
@@ -1014,11 +1045,14 @@ struct MappedFile {
 
 // structure_gro == nullptr: c->text is .gro text and frame 0 is its own structure.  Otherwise c->text is a .trr and
 // the names, residue numbers and hence groups/keys come from the first frame of the .gro file `structure_gro`.
-void open_common(cgc_context* c, const char* structure_gro = nullptr) {
+enum TrajKind { kTrajGro = 0, kTrajTrr = 1, kTrajXtc = 2 };
+void open_common(cgc_context* c, const char* structure_gro = nullptr, TrajKind kind = kTrajGro) {
   c->frames.clear();
   c->index_complete = false;
   c->opened = false;
   c->trr_real = 0;
+  c->xtc = false;
+  c->xtc_precision = 0.f;
   c->frame_span_max = 0;
   FrameSpan sp;
   c->L = FrameLayout();
@@ -1027,19 +1061,37 @@ void open_common(cgc_context* c, const char* structure_gro = nullptr) {
       MappedFile st(structure_gro);
       scan_first_frame(st.p, st.n, c->L, sp);
     }
-    TrrFrame tf;
-    bool trunc = false;
-    if (!locate_trr_frame(c->text, c->nbytes, 0, tf, &trunc)) {
-      throw InputFileMalformed(trunc ? "first frame of the .trr trajectory is incomplete" : "empty .trr trajectory");
+    if (kind == kTrajXtc) {
+      XtcFrame xf;
+      bool cut = false;
+      if (!locate_xtc_frame(c->text, c->nbytes, 0, xf, &cut)) {
+        throw InputFileMalformed(cut ? "first frame of the .xtc trajectory is incomplete" : "empty .xtc trajectory");
+      }
+      if (xf.n_atoms != c->L.n_atoms) {
+        throw InputFileMalformed("the structure file has " + std::to_string(c->L.n_atoms) + " atoms, the .xtc trajectory " +
+                                 std::to_string(xf.n_atoms));
+      }
+      c->xtc = true;
+      c->xtc_precision = xf.precision;
+      // the whole index up front (one header per frame): frames differ in size, the staging buffers take the largest
+      index_upto(c, INT64_MAX - 1);
+      // "bytes per atom" of the largest frame: what the batch sizing works with
+      c->L.line_bytes = (int)std::max<int64_t>(1, (c->frame_span_max + c->L.n_atoms - 1) / c->L.n_atoms);
+    } else {
+      TrrFrame tf;
+      bool trunc = false;
+      if (!locate_trr_frame(c->text, c->nbytes, 0, tf, &trunc)) {
+        throw InputFileMalformed(trunc ? "first frame of the .trr trajectory is incomplete" : "empty .trr trajectory");
+      }
+      if (tf.n_atoms != c->L.n_atoms) {
+        throw InputFileMalformed("the structure file has " + std::to_string(c->L.n_atoms) + " atoms, the .trr trajectory " +
+                                 std::to_string(tf.n_atoms));
+      }
+      c->trr_real = tf.real_bytes;
+      c->L.line_bytes = 3 * tf.real_bytes;   // one "line" = the coordinates of one atom
+      // the whole index up front (one header per frame): the staging buffers are sized from the largest frame
+      index_upto(c, INT64_MAX - 1);
     }
-    if (tf.n_atoms != c->L.n_atoms) {
-      throw InputFileMalformed("the structure file has " + std::to_string(c->L.n_atoms) + " atoms, the .trr trajectory " +
-                               std::to_string(tf.n_atoms));
-    }
-    c->trr_real = tf.real_bytes;
-    c->L.line_bytes = 3 * tf.real_bytes;   // one "line" = the coordinates of one atom
-    // the whole index up front (one header per frame): the staging buffers are sized from the largest frame
-    index_upto(c, INT64_MAX - 1);
   } else {
     scan_first_frame(c->text, c->nbytes, c->L, sp);
     c->frames.push_back(sp);
@@ -1171,7 +1223,7 @@ int cgc_open_trr(cgc_context* ctx, const char* trr_path, const char* structure_g
     ctx->nbytes = sb.st_size;
     ctx->mapped = true;
     ctx->fd = fd;
-    open_common(ctx, structure_gro_path);
+    open_common(ctx, structure_gro_path, kTrajTrr);
     return CGC_OK;
   });
 }
@@ -1184,9 +1236,67 @@ int cgc_open_memory_trr(cgc_context* ctx, const char* data, int64_t nbytes, cons
     ctx->text = data;
     ctx->nbytes = nbytes;
     ctx->mapped = false;
-    open_common(ctx, structure_gro_path);
+    open_common(ctx, structure_gro_path, kTrajTrr);
     return CGC_OK;
   });
+}
+
+int cgc_open_xtc(cgc_context* ctx, const char* xtc_path, const char* structure_gro_path) {
+  if (!ctx || !xtc_path || !structure_gro_path) return fail(ctx, CGC_ERR_ARG, "null argument");
+  return guarded(ctx, [&]() {
+    if (ctx->device >= 0) { free_pipeline(ctx); }
+    release_text(ctx);
+    int fd = open(xtc_path, O_RDONLY);
+    if (fd < 0) throw ReadError("Open failed on file passed in.");
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || sb.st_size == 0) {
+      close(fd);
+      throw ReadError("trajectory file is empty or cannot be stat'ed");
+    }
+    void* p = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_SHARED, fd, 0);
+    if (p == MAP_FAILED) {
+      close(fd);
+      throw ReadError("mmap of the trajectory failed");
+    }
+    ctx->text = (const char*)p;
+    ctx->nbytes = sb.st_size;
+    ctx->mapped = true;
+    ctx->fd = fd;
+    open_common(ctx, structure_gro_path, kTrajXtc);
+    return CGC_OK;
+  });
+}
+
+int cgc_open_memory_xtc(cgc_context* ctx, const char* data, int64_t nbytes, const char* structure_gro_path) {
+  if (!ctx || !data || nbytes <= 0 || !structure_gro_path) return fail(ctx, CGC_ERR_ARG, "null or empty argument");
+  return guarded(ctx, [&]() {
+    if (ctx->device >= 0) { free_pipeline(ctx); }
+    release_text(ctx);
+    ctx->text = data;
+    ctx->nbytes = nbytes;
+    ctx->mapped = false;
+    open_common(ctx, structure_gro_path, kTrajXtc);
+    return CGC_OK;
+  });
+}
+
+int64_t cgc_xtc_encode(const int32_t* coords, int n_atoms, int step, float time_ps, const float* box9, float precision,
+                       char* out, int64_t cap) {
+  if (!coords || n_atoms < 1 || !(precision > 0.f) || (cap > 0 && !out)) {
+    fail(nullptr, CGC_ERR_ARG, "bad argument");
+    return -1;
+  }
+  int64_t n = -1;
+  guarded(nullptr, [&]() {
+    static const float zero_box[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    std::vector<char> buf;
+    buf.reserve((size_t)n_atoms * 8 + 128);
+    xtc_encode_frame(coords, n_atoms, step, time_ps, box9 ? box9 : zero_box, precision, buf);
+    n = (int64_t)buf.size();
+    if (n <= cap) memcpy(out, buf.data(), (size_t)n);
+    return CGC_OK;
+  });
+  return n;
 }
 
 int cgc_dims(const cgc_context* ctx, int* n_atoms, int* n_chromo, int* n_groups, int* num_tot) {
@@ -1441,12 +1551,12 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       Slot& s = ctx->slot[0];
       const FrameSpan& f0 = ctx->frames[0];
       const int64_t b0 = f0.atoms & ~(int64_t)15;
-      const int64_t nb = f0.atoms + (int64_t)sys.n_atoms * sys.line_bytes - b0;
+      const int64_t nb = (ctx->xtc ? f0.end : f0.atoms + (int64_t)sys.n_atoms * sys.line_bytes) - b0;
       const int64_t nb_clamped = std::min(nb, ctx->nbytes - b0);
       CUDA_OK(cudaMemcpyAsync(s.d_text, ctx->text + b0, (size_t)nb_clamped, cudaMemcpyHostToDevice, ctx->st_comp));
       s.h_off[0] = f0.atoms - b0;
       CUDA_OK(cudaMemcpyAsync(s.d_off, s.h_off, sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st_comp));
-      enqueue_compute(ctx, s.d_text, nb_clamped, s.d_off, 1, s.d_xyz8, s.d_sites, s.d_acc, s.d_dE, false, ctx->st_comp);
+      enqueue_compute(ctx, s.d_text, nb_clamped, s.d_off, 1, s, s.d_dE, false, ctx->st_comp);
       launch_cov_set_shift(s.d_dE, ctx->d_cov, sys.n_sites, sys.num_tot, ctx->st_comp);
       ctx->launches++;
       ctx->shift_set = true;
@@ -1497,7 +1607,7 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       const FrameSpan& fa = ctx->frames[(size_t)f_begin];
       const FrameSpan& fb = ctx->frames[(size_t)(f_begin + want - 1)];
       const int64_t b0 = fa.atoms & ~(int64_t)15;
-      int64_t b1 = fb.atoms + (int64_t)sys.n_atoms * sys.line_bytes;
+      int64_t b1 = ctx->xtc ? fb.end : fb.atoms + (int64_t)sys.n_atoms * sys.line_bytes;
       b1 = std::min(b1, ctx->nbytes);
       const int64_t nb = b1 - b0;
       if (nb > ctx->alloc_text) throw std::runtime_error("internal: batch text larger than the staging buffer");
@@ -1536,7 +1646,7 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       CUDA_OK(cudaMemcpyAsync(s.d_off, s.h_off, sizeof(int64_t) * want, cudaMemcpyHostToDevice, ctx->st_copy));
       CUDA_OK(cudaEventRecord(s.ev_copied, ctx->st_copy));
       CUDA_OK(cudaStreamWaitEvent(ctx->st_comp, s.ev_copied, 0));
-      enqueue_compute(ctx, s.d_text, s.nb, s.d_off, want, s.d_xyz8, s.d_sites, s.d_acc, s.d_dE, true, ctx->st_comp);
+      enqueue_compute(ctx, s.d_text, s.nb, s.d_off, want, s, s.d_dE, true, ctx->st_comp);
       if (want_rows) {
         CUDA_OK(cudaMemcpyAsync(s.h_dE, s.d_dE, sizeof(float) * (size_t)(sg * want), cudaMemcpyDeviceToHost, ctx->st_comp));
       }
@@ -1654,6 +1764,7 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       if (flags & kDecBadChar) m += " unexpected character in a coordinate field;";
       if (flags & kDecBadPoint) m += " decimal point not at the column found in frame 0;";
       if (flags & kDecBadNewline) m += " atom line of a different length than in frame 0;";
+      if (flags & kDecBadXtc) m = "device decode found an impossible .xtc frame (atom count, header fields, or a bit stream whose runs do not add up)";
       throw InputFileMalformed(m);
     }
     if (stopped) {
@@ -1768,8 +1879,7 @@ int cgc_run_device(cgc_context* ctx, const void* d_text, int64_t text_bytes, con
     cudaStream_t st = (cudaStream_t)stream;
     // pageable source: the runtime stages it before returning, so the caller's array may be reused at once
     CUDA_OK(cudaMemcpyAsync(s.d_off, atoms_offset, sizeof(int64_t) * n_frames, cudaMemcpyHostToDevice, st));
-    enqueue_compute(ctx, (const char*)d_text, text_bytes, s.d_off, n_frames, s.d_xyz8, s.d_sites, s.d_acc, d_dE_kcal,
-                    false, st);
+    enqueue_compute(ctx, (const char*)d_text, text_bytes, s.d_off, n_frames, s, d_dE_kcal, false, st);
     return CGC_OK;
   });
 }
@@ -1787,7 +1897,7 @@ int cgc_decode_device(cgc_context* ctx, const void* d_text, int64_t text_bytes, 
     Slot& s = ctx->slot[0];
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_OK(cudaMemcpyAsync(s.d_off, atoms_offset, sizeof(int64_t) * n_frames, cudaMemcpyHostToDevice, st));
-    launch_decode(ctx->sys, (const char*)d_text, text_bytes, s.d_off, n_frames, s.d_xyz8, s.d_sites, ctx->d_err, st);
+    enqueue_decode(ctx, (const char*)d_text, text_bytes, s.d_off, n_frames, s, st);
     launch_unblock(ctx->sys, s.d_xyz8, d_xyz, n_frames, st);
     ctx->launches += 2;
     CUDA_OK(cudaGetLastError());

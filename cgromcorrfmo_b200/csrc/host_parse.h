@@ -86,6 +86,27 @@ struct TrrFrame {
 // coordinates.
 bool locate_trr_frame(const char* data, int64_t nbytes, int64_t pos, TrrFrame& out, bool* truncated);
 
+// ---- GROMACS .xtc (compressed coordinates, XDR big-endian; layout and stream format: xtc_bits.h) ----------------------
+// Frame = int magic 1995, int natoms, int step, float time, float box[9], then the coordinate block: int natoms, float
+// precision, int minint[3], int maxint[3], int smallidx, int nbytes, nbytes of bit stream padded to a multiple of 4.
+struct XtcFrame {
+  int64_t begin = 0;     // offset of the magic number
+  int64_t coords = 0;    // offset of the coordinate block (its atom count field): what the device kernels are pointed at
+  int64_t end = 0;       // offset one past the frame
+  int n_atoms = 0;
+  int64_t step = 0;
+  double time = 0.0;
+  float precision = 0.f;
+};
+// Parse the frame header at `pos`.  Returns false at a clean end of data or when the frame is cut short (*truncated).
+// Throws InputFileMalformed for a bad magic number or impossible fields, Unsupported for frames of at most 9 atoms (they
+// are stored uncompressed).
+bool locate_xtc_frame(const char* data, int64_t nbytes, int64_t pos, XtcFrame& out, bool* truncated);
+// Append one frame holding the integer coordinates ints[3 * natoms] (units of 1 / precision nm) to `out`, compressed the
+// way GROMACS' writer chooses runs and table indices.  natoms > 9.
+void xtc_encode_frame(const int32_t* ints, int natoms, int step, float time, const float box[9], float precision,
+                      std::vector<char>& out);
+
 // Frame-0 pass with the reference's whitespace-token rules (reference src/grom2atomFMO.cpp:396-462), then the
 // fixed-column layout check.  Throws Unsupported when the atom lines are not fixed-column.
 void scan_first_frame(const char* text, int64_t nbytes, FrameLayout& out, FrameSpan& span);

@@ -18,6 +18,7 @@ enum : int {
   kDecBadChar = 1,      // a coordinate field holds something other than [ -.0-9]
   kDecBadPoint = 2,     // the decimal point is not where the frame-0 layout says
   kDecBadNewline = 4,   // an atom line does not end where the frame-0 layout says
+  kDecBadXtc = 8,       // an .xtc frame's header or bit stream is impossible (wrong atom count, a run past the last atom, ...)
 };
 
 struct DeviceSystem {
@@ -27,7 +28,8 @@ struct DeviceSystem {
   int n_sites = 0;                      // sites computed (<= n_chromo)
   int site_cap = 0;                     // P: dQ atoms per site, padded to the largest site
   int line_bytes = 0, x_col = 20, field_w = 8, ndec = 3;
-  int traj_mode = 0;                    // 0 .gro text; 1 / 2: .trr coordinates, single / double (line_bytes = 12 / 24)
+  int traj_mode = 0;                    // 0 .gro text; 1 / 2: .trr coordinates, single / double (line_bytes = 12 / 24);
+                                        // 3: .xtc compressed coordinates (frames of varying size, launch_xtc_decode)
   double* kq = nullptr;                 // [n_pad] (double)33.2f * (double)q
   int32_t* col = nullptr;               // [n_pad] dE column, -1 = contributes nowhere (pads)
   int32_t* slot = nullptr;              // [n_pad] s*P + c for the c-th dQ atom of site s, else -1
@@ -39,6 +41,11 @@ struct DeviceSystem {
 // text: device pointer, 16-byte aligned.  atoms_off: DEVICE int64[n_frames].
 void launch_decode(const DeviceSystem& sys, const char* text, int64_t text_bytes, const int64_t* atoms_off,
                    int n_frames, float* xyz8, float4* sites, int* err_flags, cudaStream_t st);
+// K1x (xtc_kernel.cu): the same outputs from GROMACS .xtc frames.  coords_off: DEVICE int64[n_frames], offset of every
+// frame's coordinate block (its atom-count field; a multiple of 4) inside `text`.  scratch: xtc_scratch_bytes() bytes.
+size_t xtc_scratch_bytes(const DeviceSystem& sys, int n_frames);
+void launch_xtc_decode(const DeviceSystem& sys, const char* text, int64_t text_bytes, const int64_t* coords_off, int n_frames,
+                       void* scratch, float* xyz8, float4* sites, int* err_flags, cudaStream_t st);
 // xyz8 -> plain float32 [n_frames][n_atoms][3]
 void launch_unblock(const DeviceSystem& sys, const float* xyz8, float* xyz, int n_frames, cudaStream_t st);
 

@@ -9,8 +9,9 @@
 //     BYTE-LEVEL drop-in for the stock program's files therefore needs exactly two flags: --sites 7 --mtx-compat;
 //   * asking for more frames than the file holds stops cleanly (the reference segfaults, README.md:31);
 //   * stdout is quiet unless --verbose (per-frame site totals in cm^-1, the reference's "=<sum> cm-1" log).
-//   * traj_in may be a GROMACS .trr (binary) when --structure some.gro names a .gro of the same system: the authors'
-//     trjconv step (reference scripts/2014-09-trr2dEcsv.sh:22) and its 45-69 bytes of text per atom are skipped.
+//   * traj_in may be a GROMACS .trr (binary) or .xtc (compressed, decoded on the device) when --structure some.gro names
+//     a .gro of the same system: the authors' trjconv step (reference scripts/2014-09-trr2dEcsv.sh:22) and its 45-69
+//     bytes of text per atom are skipped; an .xtc moves 3-6 bytes per atom and frame to the GPU.
 //   * csv_out.time is formatted on the device (cgc_run_write_time); --host-format uses the host formatter instead
 //     (cgc_run + cgc_write_time, what the first version did; the bytes are the same);
 //   * --checkpoint FILE saves, after every chunk of frames, how far the run got together with the Correlate sums;
@@ -139,6 +140,7 @@ struct Options {
   std::vector<int> devices;
   bool compat = false, no_mtx = false, verbose = false, timing = false, npy = false, host_format = false;
   bool halve_batch = false;   // several contexts in one process: half the default batch (see run_multi)
+  bool xtc = false;           // traj_in is a GROMACS .xtc (by its extension)
 };
 
 // cgc_create + open + options for one device; on failure prints the reason and returns the exit status through *status
@@ -153,7 +155,9 @@ static cgc_context* open_context(const Options& o, int device, bool announce, in
     printf("Minor issues found with the topology input (%d conflicting duplicate entries; first entry kept)\n",
            cgc_topology_warnings(ctx));
   }
-  rc = o.structure.empty() ? cgc_open(ctx, o.traj.c_str()) : cgc_open_trr(ctx, o.traj.c_str(), o.structure.c_str());
+  rc = o.structure.empty() ? cgc_open(ctx, o.traj.c_str())
+       : o.xtc           ? cgc_open_xtc(ctx, o.traj.c_str(), o.structure.c_str())
+                         : cgc_open_trr(ctx, o.traj.c_str(), o.structure.c_str());
   if (rc != CGC_OK) {
     *status = die(ctx, rc, "opening the trajectory");
     return nullptr;
@@ -542,7 +546,7 @@ int main(int argc, char** argv) {
     printf("Five inputs required for this program.\n");
     printf("Order of args: fmo_traj_path, fmo_top_path, bcx_itp_path, output_path, num_frames "
            "[--sites N] [--mtx-compat] [--no-mtx] [--device D] [--gpus N | --devices a,b,..] [--first-frame F] [--batch-frames B] "
-           "[--stage-threads T] [--ring-slots K] [--verbose] [--structure frame0.gro (traj_in is then a .trr)] [--npy] [--host-format] "
+           "[--stage-threads T] [--ring-slots K] [--verbose] [--structure frame0.gro (traj_in is then a .trr or .xtc)] [--npy] [--host-format] "
            "[--checkpoint FILE] [--resume FILE]\n"
            "Byte-for-byte the stock program's files: add --sites 7 --mtx-compat (defaults: every chromophore is a site, "
            "csv_out.mtx holds the covariance).\n");
@@ -602,8 +606,10 @@ int main(int argc, char** argv) {
     return EXIT_FAILURE;
   }
   const bool is_trr = o.traj.size() > 4 && o.traj.compare(o.traj.size() - 4, 4, ".trr") == 0;
-  if (is_trr && o.structure.empty()) {
-    fprintf(stderr, "traj2dEcsv: a .trr trajectory holds no atom names: pass --structure <file.gro> (any .gro frame of the same system)\n");
+  o.xtc = o.traj.size() > 4 && o.traj.compare(o.traj.size() - 4, 4, ".xtc") == 0;
+  if ((is_trr || o.xtc) && o.structure.empty()) {
+    fprintf(stderr, "traj2dEcsv: a %s trajectory holds no atom names: pass --structure <file.gro> (any .gro frame of the same system)\n",
+            o.xtc ? ".xtc" : ".trr");
     return EXIT_FAILURE;
   }
   return o.devices.size() > 1 ? run_multi(o) : run_single(o);

@@ -339,6 +339,27 @@ def write_trr(path: str, s: System, n_frames: int, double: bool = False, velocit
     return fb
 
 
+def xtc_frame_bytes(s: System, frame: int, jitter: float = 0.01, dt_ps: float = 0.2, precision: float = 1000.0) -> bytes:
+    """One GROMACS .xtc frame holding exactly the integers frame_bytes() prints as "%8.3f" text (precision 1000: the
+    stored integer is the milli-nm value).  Compressed by the library's writer (cgc_xtc_encode, host code)."""
+    from . import capi
+    milli = frame_milli(s, frame, jitter)
+    if precision != 1000.0:
+        milli = np.round(milli * (precision / 1000.0)).astype(np.int64)
+    return capi.xtc_encode(milli, step=frame, time_ps=frame * dt_ps, box=np.eye(3) * s.box, precision=precision)
+
+
+def write_xtc(path: str, s: System, n_frames: int, jitter: float = 0.01, precision: float = 1000.0) -> int:
+    """The .xtc twin of write_gro (same frames).  Returns the byte size of the largest frame."""
+    fb = 0
+    with open(path, "wb") as f:
+        for t in range(n_frames):
+            b = xtc_frame_bytes(s, t, jitter, precision=precision)
+            fb = max(fb, len(b))
+            f.write(b)
+    return fb
+
+
 def write_inputs(outdir: str, s: System, n_frames: int, velocities: bool = False, jitter: float = 0.01):
     """Write traj.gro / topol.top / bcx.itp into outdir and return their absolute paths."""
     os.makedirs(outdir, exist_ok=True)

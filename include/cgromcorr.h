@@ -82,6 +82,25 @@ int cgc_open_memory(cgc_context *ctx, const char *text, int64_t nbytes);
  * count different from the structure file's, CGC_ERR_UNSUPPORTED for frames without coordinates. */
 int cgc_open_trr(cgc_context *ctx, const char *trr_path, const char *structure_gro_path);
 int cgc_open_memory_trr(cgc_context *ctx, const char *data, int64_t nbytes, const char *structure_gro_path);
+/* GROMACS .xtc trajectories (compressed integer coordinates, the format production runs are usually kept in) read
+ * directly and DECODED ON THE DEVICE: 3-6 bytes per atom and frame cross the PCIe link instead of the 45-69 bytes of .gro
+ * text or the 12 of a .trr ("a binary trr/xtc reader").  Not a reference format either (same trjconv
+ * step, scripts/2014-09-trr2dEcsv.sh:22).  Names and residues come from `structure_gro_path` as for cgc_open_trr.  A stored
+ * integer k becomes the float32 nearest to k / precision — the value (float)atof (src/grom2atomFMO.cpp:448-450) yields on
+ * the "%8.3f" text trjconv would have written — so an .xtc of precision 1000 and the .gro of the same frames give
+ * bit-identical dE.  The host only walks the frame headers; CGC_ERR_INPUT_MALFORMED for a bad magic number, impossible
+ * header fields, an atom count different from the structure file's, or (from cgc_run) a bit stream whose runs do not add
+ * up; CGC_ERR_UNSUPPORTED for frames of at most 9 atoms (stored uncompressed).  For cgc_run_device / cgc_decode_device the
+ * offsets are those of cgc_frame_atoms_offset: the frame's coordinate block (a multiple of 4 inside a 16-byte aligned
+ * buffer), and text_bytes must cover the last frame's stream. */
+int cgc_open_xtc(cgc_context *ctx, const char *xtc_path, const char *structure_gro_path);
+int cgc_open_memory_xtc(cgc_context *ctx, const char *data, int64_t nbytes, const char *structure_gro_path);
+/* Write one .xtc frame (host; no device needed): coords = int32[3 * n_atoms] in units of 1 / precision nm, box9 = the nine
+ * box floats (NULL: zeros), compressed the way GROMACS' writer chooses runs and table indices (n_atoms > 9).  Returns the
+ * frame's size in bytes — the frame is stored in `out` when it fits `cap` (call with cap 0 to size the buffer) — or -1
+ * (cgc_last_error(NULL)).  What trjconv -o traj.xtc does for files; used here to produce test and benchmark inputs. */
+int64_t cgc_xtc_encode(const int32_t *coords, int n_atoms, int step, float time_ps, const float *box9, float precision,
+                       char *out, int64_t cap);
 
 int cgc_dims(const cgc_context *ctx, int *n_atoms, int *n_chromo, int *n_groups, int *num_tot);
 /* atomGroupi of ReadOneTimeGrom2Atom: -k for the k-th chromophore, +g for the g-th other residue. int32[n_atoms] */
