@@ -16,6 +16,8 @@ F = 256) is far larger than the 126 MB L2.
   value     frames/s, whole job, text resident in HBM when the timed region starts (cgc_run_device + K3)
   e2e       frames/s through the C-ABI call a user makes (cgc_run) with HOST buffers: pinned text in, H2D copies, kernels,
             D2H of the dE rows — all inside the timed region
+  e2e_xtc   the same frames as a GROMACS .xtc (compressed integers, ~5 B/atom instead of 45), decoded on the device (K1x): the
+            leg is bound by the kernels, not by the PCIe link, so it scales with the GPUs; rows bit-identical to the .gro path
   e2e_cli   the drop-in program itself (traj2dEcsv, C++): a real .gro file in /dev/shm (6144 frames = 27.6 GB at N = 1, 1024 per
             GPU at N > 1) -> csv_out.time + csv_out.mtx, whole process and frame loop; at N > 1 ONE process drives the N GPUs (traj2dEcsv --gpus N, ncclAllReduce)
   N > 1     one process per GPU (torchrun), every rank streams its own frame range (weak scaling, no data-path
@@ -736,7 +738,89 @@ def run_ours(args):
         trr_value = sum(trr_share) * args.steps / trr_s
         trr_same = bool(np.array_equal(out_trr.view(np.uint32), out_host.view(np.uint32)))
         ctx2.close()
-        del cov2, cov, d_text, d_dE
+        del cov2
+
+        # ---------------- the same frames as a GROMACS .xtc (compressed integers, precision 1000): ~5 B/atom over PCIe, decoded
+        # on the device (K1x, csrc/xtc_kernel.cu).  The leg is kernel-bound, so every rank streams F frames.  Reported, never
+        # required: a failure leaves "e2e_xtc": {"failed": ...} and the line stands.
+        xtc = None
+        xtc_s, xtc_err = float("inf"), None
+        xtc_ktimes, xtc_same, n_xtc, xtc_batch = {}, False, 0, 0
+        ctx3 = cov3 = host_xtc = None
+        try:
+            t_enc = time.time()
+            xtc_blob = b"".join(synth.xtc_frame_bytes(s, rank * F + f) for f in range(F))
+            n_xtc = len(xtc_blob)
+            host_xtc = torch.empty(n_xtc + 64, dtype=torch.uint8).pin_memory()
+            host_xtc[:n_xtc] = torch.from_numpy(np.frombuffer(xtc_blob, dtype=np.uint8).copy())
+            host_xtc[n_xtc:] = 0
+            del xtc_blob
+            if rank == 0:
+                log("bench: %d .xtc frames encoded in %.1f s (%.2f B/atom)" % (F, time.time() - t_enc, n_xtc / F / n_atoms))
+            ctx3 = capi.Context(top, itp, local)
+            ctx3.open_memory_xtc((host_xtc.data_ptr(), n_xtc), struct_gro)
+            xtc_batch = args.e2e_batch or int(min(F, 128))            # the index pass costs the same for 32 frames as for 256
+            ctx3.set_option("batch_frames", xtc_batch)
+            ctx3.set_option("profile", 1)
+            if not cov_on:
+                ctx3.set_option("covariance", 0)
+            if cov_on:
+                cov3 = torch.zeros(ctx3.cov_size(), dtype=torch.float64, device=dev)
+                ctx3.cov_bind(cov3.data_ptr())
+                ctx3.cov_set_shift_device(row0.data_ptr(), stream)
+            out_xtc = np.empty((F, S, G), dtype=np.float32)
+            ctx3.run(0, F, out=out_xtc)
+            xtc_same = bool(np.array_equal(out_xtc.view(np.uint32), out_host.view(np.uint32)))
+            for _ in range(max(3, args.warmup)):
+                ctx3.run(0, F, out=out_xtc)
+            torch.cuda.synchronize()
+            ctx3.kernel_times(reset=True)
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(args.steps):
+                ctx3.run(0, F, out=out_xtc)
+            e1.record()
+            torch.cuda.synchronize()
+            xtc_s = max(time.perf_counter() - t0, e0.elapsed_time(e1) / 1e3)
+            xtc_ktimes = ctx3.kernel_times(reset=True)
+        except Exception as e:  # reported, never required
+            xtc_err = "%s: %s" % (type(e).__name__, e)
+            log("bench: e2e_xtc leg failed:", xtc_err)
+        if world > 1:
+            # the ranks first agree that the leg ran everywhere; only then the one collective (timed, added to the leg)
+            t = torch.tensor([xtc_s if xtc_err is None else 1e30], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if float(t.item()) >= 1e29:
+                xtc_err = xtc_err or "failed on another rank"
+            elif cov3 is not None:
+                e0.record()
+                combine(cov3)
+                e1.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([xtc_s + e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            xtc_s = float(t.item())
+        try:
+            if ctx3 is not None:
+                ctx3.close()
+        except Exception:
+            pass
+        del cov3, host_xtc
+        if xtc_err is None:
+            kd_ms, kd_n = xtc_ktimes.get("decode", (0.0, 0))
+            xtc = {"value": world * F * args.steps / xtc_s, "unit": UNIT, "h2d_bytes_per_step": n_xtc + 8 * F,
+                   "d2h_bytes_per_step": int(out_host.nbytes),
+                   "api": "cgc_open_memory_xtc + cgc_run on pinned .xtc frames (compressed integers, precision 1000, %.2f B/atom, "
+                          "%d B/frame on average), %d-frame batches; decoded on the device (K1x: index pass + unpack pass)" % (
+                              n_xtc / F / n_atoms, n_xtc // F, xtc_batch),
+                   "note": "same frames as the headline; not the reference's input format (it reads .gro text); at N > 1 the one all-reduce of the Correlate sums is timed after the ranks agreed that the leg ran and added to the leg's time",
+                   "rows_bit_identical_to_gro_path": xtc_same,
+                   "kernel_ms": {k: v[0] for k, v in xtc_ktimes.items()},
+                   "k1x_ms_per_launch": (kd_ms / kd_n) if kd_n else None, "k1x_launches": int(kd_n),
+                   "k1x_frames_per_launch": xtc_batch, "wall_ms": xtc_s * 1e3}
+        else:
+            xtc = {"failed": xtc_err}
+        del cov, d_text, d_dE
 
         # ---------------- the drop-in program on a real file (tmpfs = a file in the page cache)
         cli = None
@@ -848,6 +932,7 @@ def run_ours(args):
                     "h2d_peak_gbs": sum(trr_rates), "frac_of_h2d_peak": trr_value * (n_trr / F) / 1e9 / sum(trr_rates),
                     "h2d_concurrent_gbs_per_rank": trr_rates, "h2d_alone_gbs": trr_alone, "frames_per_step_per_rank": trr_share,
                     "kernel_ms": {k: v[0] for k, v in trr_ktimes.items()}, "wall_ms": trr_s * 1e3},
+        "e2e_xtc": xtc,
         "e2e_cli": cli,
         "allreduce_check": allreduce_check,
         "gpu_launches": int(launches),
