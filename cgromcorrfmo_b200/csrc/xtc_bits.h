@@ -485,6 +485,111 @@ XTC_HD bool index_advance(Cursor& c, uint32_t& prev_atom, const IndexStep& st, i
   return c.atom <= natoms;
 }
 
+// ---- the index pass's window on the stream -----------------------------------------------------------------------
+// The walk reads a few bytes per step, each step a little further on: from global memory every step would pay a cache-line
+// miss.  The warp therefore keeps the stream in a ring of shared-memory words that it fills AHEAD of the walk with
+// asynchronous copies (cp.async, 4 bytes each: a frame's stream is only 4-byte aligned), a chunk at a time, as soon as the
+// slots of a chunk hold words the walk has passed.  A step may look at words [cw, cw + kRingLook): 32 groups of the
+// longest possible kind.  On the host the copies "land" when they are waited for (until then their slots hold a poison
+// value), so the emulation fails if the kernel's waits were ever in the wrong place.
+constexpr uint32_t kRingWords = 4096;      // 16 KB per warp
+constexpr uint32_t kRingChunk = 1024;
+constexpr uint32_t kRingLook = 704;        // 31 * (96 + 1 + 8 * 72) + 96 + 32 bits, rounded up, in words
+constexpr uint32_t kRingPoison = 0xDEADBEEFu;
+struct Ring {
+  uint32_t* w;           // [kRingWords]
+  const uint32_t* src;   // the frame's stream in global memory
+  uint32_t nwords;
+  uint32_t issued;       // words [0, issued) have been asked for
+  uint32_t ready;        // words [0, ready) have landed (those of them that are younger than issued - kRingWords are in the ring)
+};
+XTC_HD void ring_init(Ring& r, uint32_t* words, const uint32_t* src, uint32_t nwords) {
+  r.w = words;
+  r.src = src;
+  r.nwords = nwords;
+  r.issued = r.ready = 0u;
+}
+// may the next chunk be asked for while the walk stands at word cw?  (its slots hold words below cw by then)
+XTC_HD bool ring_can_issue(const Ring& r, uint32_t cw) { return r.issued < r.nwords && r.issued + kRingChunk <= cw + kRingWords; }
+// one lane's share of the next chunk
+XTC_HD void ring_issue_lane(const Ring& r, uint32_t lane) {
+  for (uint32_t j = lane; j < kRingChunk; j += 32u) {
+    const uint32_t k = r.issued + j;
+    if (k < r.nwords) {
+#if defined(__CUDA_ARCH__)
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(r.w + (k & (kRingWords - 1u)));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(r.src + k) : "memory");
+#else
+      r.w[k & (kRingWords - 1u)] = kRingPoison;
+#endif
+    }
+  }
+}
+XTC_HD void ring_issued(Ring& r) {   // after every lane has issued its share
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+  r.issued += kRingChunk;
+}
+// does the step at word cw need words that are still on their way?
+XTC_HD bool ring_must_wait(const Ring& r, uint32_t cw) { return r.ready < r.issued && cw + kRingLook > r.ready; }
+XTC_HD void ring_wait(Ring& r) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncwarp();
+#else
+  for (uint32_t k = r.ready; k < r.issued && k < r.nwords; k++) r.w[k & (kRingWords - 1u)] = r.src[k];
+#endif
+  r.ready = r.issued;
+}
+XTC_HD uint32_t ring_peek32(const Ring& r, uint32_t p) {
+  const uint32_t idx = p >> 5, sh = p & 31u;
+  const uint32_t a = bswap32(r.w[idx & (kRingWords - 1u)]), b = bswap32(r.w[(idx + 1u) & (kRingWords - 1u)]);
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(b, a, sh);
+#else
+  return sh ? (a << sh) | (b >> (32 - sh)) : a;
+#endif
+}
+// probe_group out of the ring; len / gs: bits and atoms of a group whose flag bit is clear (warp-uniform)
+XTC_HD Probe probe_ring(const Ring& r, const Cursor& c, uint32_t len, uint32_t gs, int large_bits, uint32_t lane) {
+  Probe p;
+  p.pos = c.pos + lane * len;
+  p.atom = c.atom + lane * gs;
+  const uint32_t v = ring_peek32(r, p.pos + (uint32_t)large_bits);
+  p.flag = v >> 31;
+  p.r5 = (v >> 26) & 31u;
+  return p;
+}
+// What the walk's cursor becomes if this lane's group turns out to be the first one with a set flag: every lane works it
+// out for itself while the ballot is under way, the warp then takes the winner's (four shuffles instead of a dependent
+// chain behind the ballot).
+struct Cand {
+  uint32_t pos, atom;
+  int smallidx, run, ok;
+};
+XTC_HD Cand cand_after(const Probe& p, const Cursor& c, int large_bits, uint32_t natoms) {
+  Cursor at, next;
+  at.pos = p.pos; at.atom = p.atom; at.smallidx = c.smallidx; at.run = c.run;
+  Cand cd;
+  cd.ok = after_flagged(at, p.r5, large_bits, natoms, next) ? 1 : 0;
+  cd.pos = next.pos; cd.atom = next.atom; cd.smallidx = next.smallidx; cd.run = next.run;
+  return cd;
+}
+// index_advance with the winner's candidate (fc: lane st.fl's, used only when st.fl < nv; fl_atom: where its group starts)
+XTC_HD bool index_advance_cand(Cursor& c, uint32_t& prev_atom, const IndexStep& st, int nv, const Cand& fc, uint32_t len, uint32_t gs,
+                               uint32_t natoms) {
+  if (st.fl < nv) {
+    prev_atom = c.atom + (uint32_t)st.fl * gs;
+    c.pos = fc.pos; c.atom = fc.atom; c.smallidx = fc.smallidx; c.run = fc.run;
+    return fc.ok != 0;
+  }
+  prev_atom = c.atom + (uint32_t)(nv - 1) * gs;
+  c.pos += (uint32_t)nv * len;
+  c.atom += (uint32_t)nv * gs;
+  return c.atom <= natoms;
+}
+
 // ---- decode pass: one CTA of kXtcThreads threads per window of kXtcWindow atoms ------------------------------------------
 constexpr int kXtcThreads = 256;                                  // checkpoints per CTA
 constexpr int kXtcWindow = kXtcThreads * kCkAtoms;                // atoms per CTA: 4096

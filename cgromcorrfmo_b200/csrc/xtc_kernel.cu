@@ -34,6 +34,7 @@ static_assert(sizeof(U4) == sizeof(uint4) && sizeof(F4) == sizeof(float4), "reco
 __global__ void __launch_bounds__(32)
 xtc_index_kernel(const char* __restrict__ text, int64_t text_bytes, const int64_t* __restrict__ coords_off, int n_atoms,
                  int n_ck, U4* __restrict__ ck, int* __restrict__ err_flags) {
+  __shared__ uint32_t ring_words[kRingWords];
   const int f = blockIdx.x;
   const uint32_t lane = threadIdx.x;
   FrameHdr h;
@@ -42,27 +43,39 @@ xtc_index_kernel(const char* __restrict__ text, int64_t text_bytes, const int64_
     if (lane == 0) raise_flag(err_flags, kDecBadXtcBit);
     return;
   }
-  const Stream s{hw + 10, 0u, (h.nbytes + 3u) >> 2, true};
+  Ring r;
+  ring_init(r, ring_words, hw + 10, (h.nbytes + 3u) >> 2);
   Cursor c{0u, 0u, h.smallidx, 0};
   uint32_t prev_atom = kNoAtom;
   U4* table = ck + (size_t)f * n_ck;
   const uint32_t natoms = (uint32_t)n_atoms;
   bool ok = true;
   while (ok && c.atom < natoms) {
-    const Probe p = probe_group(s, c, h.large_bits, lane);
+    const uint32_t nsm = (uint32_t)c.run / 3u;
+    const uint32_t len = (uint32_t)h.large_bits + 1u + nsm * (uint32_t)c.smallidx, gs = 1u + nsm;
+    const uint32_t cw = c.pos >> 5;
+    while (ring_can_issue(r, cw)) {
+      ring_issue_lane(r, lane);
+      ring_issued(r);
+    }
+    if (ring_must_wait(r, cw)) ring_wait(r);
+    const Probe p = probe_ring(r, c, len, gs, h.large_bits, lane);
     const bool valid = p.atom < natoms;
     const uint32_t set = __ballot_sync(0xFFFFFFFFu, valid && p.flag != 0u);
     const int nv = __popc(__ballot_sync(0xFFFFFFFFu, valid));
+    const Cand mine = cand_after(p, c, h.large_bits, natoms);
     const IndexStep st = plan_index_step(set, nv);
     index_lane_emit(lane, p, c, prev_atom, st, table);
-    Probe fp;   // lane st.fl's view (any lane's when no flag is set: unused then)
     const int src = st.fl & 31;
-    fp.pos = __shfl_sync(0xFFFFFFFFu, p.pos, src);
-    fp.atom = __shfl_sync(0xFFFFFFFFu, p.atom, src);
-    fp.r5 = __shfl_sync(0xFFFFFFFFu, p.r5, src);
-    fp.flag = 1u;
-    ok = index_advance(c, prev_atom, st, nv, fp, h.large_bits, natoms);
+    Cand fc;
+    fc.pos = __shfl_sync(0xFFFFFFFFu, mine.pos, src);
+    fc.atom = __shfl_sync(0xFFFFFFFFu, mine.atom, src);
+    fc.smallidx = __shfl_sync(0xFFFFFFFFu, mine.smallidx, src);
+    fc.run = __shfl_sync(0xFFFFFFFFu, mine.run, src);
+    fc.ok = __shfl_sync(0xFFFFFFFFu, mine.ok, src);
+    ok = index_advance_cand(c, prev_atom, st, nv, fc, len, gs, natoms);
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");   // nothing may still be landing in shared memory when the CTA ends
   if (ok && c.pos > 8u * h.nbytes) ok = false;
   if (!ok && lane == 0) raise_flag(err_flags, kDecBadXtcBit);
 }

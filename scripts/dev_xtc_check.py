@@ -1,6 +1,6 @@
 """Developer check of the .xtc path on a B200: C2-shaped frames through cgc_run from pinned memory, kernel times of K1x (index
 pass + unpack pass, one CUDA-event pair around both) for several batch sizes and both index kernels, rows compared with the
-.gro path.   python scripts/dev_xtc_check.py [frames]"""
+.gro path.   python scripts/dev_xtc_check.py [frames [modes [batches]]]"""
 import os
 import sys
 import tempfile
@@ -17,6 +17,8 @@ from cgromcorrfmo_b200 import capi, synth  # noqa: E402
 
 def main():
     F = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+    modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["0", "1"]      # 0: warp-speculative index pass, 1: scalar
+    batches = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [32, 64, 128, 256]
     s = synth.named_system("C2")
     with tempfile.TemporaryDirectory() as d:
         top, itp, gro = os.path.join(d, "t.top"), os.path.join(d, "b.itp"), os.path.join(d, "f0.gro")
@@ -33,9 +35,9 @@ def main():
         with capi.Context(top, itp, 0) as c:
             c.open_memory(text)
             ref, done, rc = c.run(0, 8)
-        for scalar in ("0", "1"):
+        for scalar in modes:
             os.environ["CGC_XTC_SCALAR_INDEX"] = scalar
-            for batch in (32, 64, 128, 256):
+            for batch in batches:
                 if batch > F:
                     continue
                 with capi.Context(top, itp, 0) as c:

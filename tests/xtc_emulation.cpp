@@ -26,27 +26,37 @@ int64_t index_frame_warp(const char* text, int64_t text_bytes, int64_t off, int 
     raise_flag(err, kDecBadXtcBit);
     return 0;
   }
-  const Stream s{hw + 10, 0u, (h.nbytes + 3u) >> 2, true};
+  std::vector<uint32_t> ring_words(kRingWords, kRingPoison);   // the kernel's shared memory
+  Ring r;
+  ring_init(r, ring_words.data(), hw + 10, (h.nbytes + 3u) >> 2);
   Cursor c{0u, 0u, h.smallidx, 0};
   uint32_t prev_atom = kNoAtom;
   const uint32_t natoms = (uint32_t)n_atoms;
   bool ok = true;
   int64_t steps = 0;
   while (ok && c.atom < natoms) {
+    const uint32_t nsm = (uint32_t)c.run / 3u;
+    const uint32_t len = (uint32_t)h.large_bits + 1u + nsm * (uint32_t)c.smallidx, gs = 1u + nsm;
+    const uint32_t cw = c.pos >> 5;
+    while (ring_can_issue(r, cw)) {
+      for (uint32_t lane = 0; lane < 32; lane++) ring_issue_lane(r, lane);
+      ring_issued(r);
+    }
+    if (ring_must_wait(r, cw)) ring_wait(r);
     Probe p[32];
+    Cand mine[32];
     uint32_t set = 0, vmask = 0;
     for (uint32_t lane = 0; lane < 32; lane++) {
-      p[lane] = probe_group(s, c, h.large_bits, lane);
+      p[lane] = probe_ring(r, c, len, gs, h.large_bits, lane);
       const bool valid = p[lane].atom < natoms;
       if (valid) vmask |= 1u << lane;
       if (valid && p[lane].flag != 0u) set |= 1u << lane;
+      mine[lane] = cand_after(p[lane], c, h.large_bits, natoms);
     }
     const int nv = __builtin_popcount(vmask);
     const IndexStep st = plan_index_step(set, nv);
     for (uint32_t lane = 0; lane < 32; lane++) index_lane_emit(lane, p[lane], c, prev_atom, st, table);
-    Probe fp = p[st.fl & 31];
-    fp.flag = 1u;
-    ok = index_advance(c, prev_atom, st, nv, fp, h.large_bits, natoms);
+    ok = index_advance_cand(c, prev_atom, st, nv, mine[st.fl & 31], len, gs, natoms);
     steps++;
   }
   if (ok && c.pos > 8u * h.nbytes) ok = false;
