@@ -406,8 +406,8 @@ XTC_HD bool decode_groups(const Stream& s, const FrameHdr& h, Cursor c, uint32_t
 // (tests/xtc_emulation.cpp, which runs the lanes of a warp and the threads of a CTA one after the other between the
 // barriers) execute these same functions; only the collectives (ballot, shuffle, __syncthreads) differ.
 // ======================================================================================================================
-struct U4 { uint32_t x, y, z, w; };     // a checkpoint record (layout of CUDA's uint4)
-struct F4 { float x, y, z, w; };        // a site entry (layout of CUDA's float4)
+struct alignas(16) U4 { uint32_t x, y, z, w; };     // a checkpoint record (layout of CUDA's uint4)
+struct alignas(16) F4 { float x, y, z, w; };        // a site entry (layout of CUDA's float4)
 
 constexpr int kDecBadXtcBit = 8;        // == kDecBadXtc (kernels.cuh)
 XTC_HD void raise_flag(int* flags, int bit) {
@@ -551,43 +551,68 @@ XTC_HD uint32_t ring_peek32(const Ring& r, uint32_t p) {
   return sh ? (a << sh) | (b >> (32 - sh)) : a;
 #endif
 }
-// probe_group out of the ring; len / gs: bits and atoms of a group whose flag bit is clear (warp-uniform)
-XTC_HD Probe probe_ring(const Ring& r, const Cursor& c, uint32_t len, uint32_t gs, int large_bits, uint32_t lane) {
-  Probe p;
-  p.pos = c.pos + lane * len;
-  p.atom = c.atom + lane * gs;
-  const uint32_t v = ring_peek32(r, p.pos + (uint32_t)large_bits);
-  p.flag = v >> 31;
-  p.r5 = (v >> 26) & 31u;
-  return p;
-}
-// What the walk's cursor becomes if this lane's group turns out to be the first one with a set flag: every lane works it
-// out for itself while the ballot is under way, the warp then takes the winner's (four shuffles instead of a dependent
-// chain behind the ballot).
-struct Cand {
-  uint32_t pos, atom;
-  int smallidx, run, ok;
+// One step of the speculative walk, written for a short dependent chain (the walk is one warp's latency per step: nothing
+// else runs on its scheduler).  The warp-uniform state:
+struct Walk {
+  uint32_t pos;          // bit position of the next group
+  uint32_t atom;         // its first atom
+  uint32_t smallidx;     // table index of its small triples
+  uint32_t nsm;          // small atoms per group while the flag bits stay clear (run / 3)
+  uint32_t prev_atom;    // first atom of the last group consumed; kNoAtom before the first
 };
-XTC_HD Cand cand_after(const Probe& p, const Cursor& c, int large_bits, uint32_t natoms) {
-  Cursor at, next;
-  at.pos = p.pos; at.atom = p.atom; at.smallidx = c.smallidx; at.run = c.run;
-  Cand cd;
-  cd.ok = after_flagged(at, p.r5, large_bits, natoms, next) ? 1 : 0;
-  cd.pos = next.pos; cd.atom = next.atom; cd.smallidx = next.smallidx; cd.run = next.run;
-  return cd;
+// What lane l derives when it assumes that the l groups before its own had clear flag bits: where its group starts, its flag
+// bit, and the walk's state AFTER its group — for a clear flag as well as for a set one, so that the warp only has to pick
+// the right lane's answer (three shuffles behind the ballot; no branch).
+struct LaneView {
+  uint32_t pos, atom;    // the lane's group
+  uint32_t flag;         // its flag bit
+  uint32_t npos, natom;  // the group after it
+  uint32_t nstate;       // smallidx | nsm << 8 | ok << 16 after it
+};
+XTC_HD LaneView walk_lane(const Ring& r, const Walk& w, uint32_t large_bits, uint32_t natoms, uint32_t lane) {
+  const uint32_t len = large_bits + 1u + w.nsm * w.smallidx, gs = 1u + w.nsm;
+  LaneView v;
+  v.pos = w.pos + lane * len;
+  v.atom = w.atom + lane * gs;
+  const uint32_t bits = ring_peek32(r, v.pos + large_bits);
+  v.flag = bits >> 31;
+  const uint32_t r5 = (bits >> 26) & 31u;
+  const uint32_t q = (r5 * 11u) >> 5;                       // r5 / 3 for r5 < 32
+  const uint32_t nsm2 = v.flag ? q : w.nsm;
+  const uint32_t sidx2 = v.flag ? w.smallidx + (r5 - 3u * q) - 1u : w.smallidx;   // += r5 % 3 - 1
+  v.npos = v.pos + large_bits + (v.flag ? 6u : 1u) + nsm2 * w.smallidx;
+  v.natom = v.atom + 1u + nsm2;
+  const uint32_t ok = (nsm2 <= (uint32_t)kMaxRunAtoms && v.natom <= natoms && sidx2 >= (uint32_t)kFirstIdx && sidx2 <= (uint32_t)kLastIdx) ? 1u : 0u;
+  v.nstate = sidx2 | (nsm2 << 8) | (ok << 16);
+  return v;
 }
-// index_advance with the winner's candidate (fc: lane st.fl's, used only when st.fl < nv; fl_atom: where its group starts)
-XTC_HD bool index_advance_cand(Cursor& c, uint32_t& prev_atom, const IndexStep& st, int nv, const Cand& fc, uint32_t len, uint32_t gs,
-                               uint32_t natoms) {
-  if (st.fl < nv) {
-    prev_atom = c.atom + (uint32_t)st.fl * gs;
-    c.pos = fc.pos; c.atom = fc.atom; c.smallidx = fc.smallidx; c.run = fc.run;
-    return fc.ok != 0;
+// the lane whose group ends the step: the first valid lane with a set flag, else the last valid lane
+XTC_HD uint32_t walk_winner(uint32_t set, uint32_t nv) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t fl = set ? (uint32_t)__ffs((int)set) - 1u : 32u;
+#else
+  const uint32_t fl = set ? (uint32_t)__builtin_ctz(set) : 32u;
+#endif
+  return fl < nv ? fl : nv - 1u;
+}
+// the checkpoint a lane leaves when its group is consumed by the step and opens a 16-atom window
+XTC_HD void walk_lane_emit(uint32_t lane, const LaneView& v, const Walk& w, uint32_t winner, U4* table) {
+  if (lane > winner) return;
+  const uint32_t before = lane == 0u ? w.prev_atom : v.atom - (1u + w.nsm);
+  if (before == kNoAtom || (before / kCkAtoms) < (v.atom / kCkAtoms)) {
+    U4 rec;
+    rec.x = v.pos; rec.y = v.atom; rec.z = w.smallidx | ((3u * w.nsm) << 8); rec.w = 0u;
+    table[v.atom / kCkAtoms] = rec;
   }
-  prev_atom = c.atom + (uint32_t)(nv - 1) * gs;
-  c.pos += (uint32_t)nv * len;
-  c.atom += (uint32_t)nv * gs;
-  return c.atom <= natoms;
+}
+// the state after the step, from the winner's view (npos, natom, nstate as shuffled from lane `winner`).  False: impossible.
+XTC_HD bool walk_advance(Walk& w, uint32_t winner, uint32_t npos, uint32_t natom, uint32_t nstate) {
+  w.prev_atom = w.atom + winner * (1u + w.nsm);
+  w.pos = npos;
+  w.atom = natom;
+  w.smallidx = nstate & 0xFFu;
+  w.nsm = (nstate >> 8) & 0xFFu;
+  return (nstate >> 16) != 0u;
 }
 
 // ---- decode pass: one CTA of kXtcThreads threads per window of kXtcWindow atoms ------------------------------------------
@@ -595,7 +620,8 @@ constexpr int kXtcThreads = 256;                                  // checkpoints
 constexpr int kXtcWindow = kXtcThreads * kCkAtoms;                // atoms per CTA: 4096
 constexpr int kXtcStage = kXtcWindow + 16;                        // atoms staged: the last group may pass the window by up to 8
 constexpr int kXtcStagePitch = kXtcStage + kXtcStage / 16 + 1;    // one float of padding per 16 atoms (bank spread)
-constexpr int kXtcStreamWords = 10240;                            // 40 KB of stream staged per CTA; longer spans stay in global memory
+constexpr int kXtcStreamWords = 5888;                             // stream words staged per CTA by default: 23 KB, three CTAs per SM
+constexpr int kXtcStreamWordsMax = 12288;                         // ... when the frames need more per window (two CTAs per SM); longer spans stay in global memory
 
 struct DecodeArgs {
   const char* text;
@@ -606,13 +632,14 @@ struct DecodeArgs {
   const int32_t* slot;
   const float* slot_dq;
   int sites_stride;
+  int stream_words;           // capacity of the CTA's stream buffer (kXtcStreamWords .. kXtcStreamWordsMax)
   float* xyz8;
   F4* sites;
   int* err_flags;
 };
 struct DecodeCta {            // the CTA's shared state
   float* stage;               // [3][kXtcStagePitch]
-  uint32_t* sw;               // [kXtcStreamWords]
+  uint32_t* sw;               // [DecodeArgs::stream_words]
   FrameHdr h;
   const uint32_t* hw;         // the frame's coordinate block (null: unusable)
   uint32_t a_first, a_end;    // atoms this CTA owns: [a_first, a_end); a_first == kNoAtom: none
@@ -646,36 +673,61 @@ XTC_HD void decode_cta_setup(const DecodeArgs& a, DecodeCta& cta, int frame, uin
   cta.a_end = a_end;
   cta.w_lo = w_lo;
   cta.w_hi = w_hi;
-  cta.staged = (w_hi - w_lo) <= (uint32_t)kXtcStreamWords;
+  cta.staged = (w_hi - w_lo) <= (uint32_t)a.stream_words;
 }
-// every thread, between the first and the second barrier: the stream span into shared memory, byte order fixed
+// every thread, before the first barrier (the loads are in flight while thread 0 sets the CTA up): its own checkpoint and
+// the atom the next one starts at
+struct MyCheckpoint {
+  U4 me;
+  uint32_t next_atom;   // kNoAtom: there is no next checkpoint
+};
+XTC_HD MyCheckpoint decode_cta_my_checkpoint(const DecodeArgs& a, int frame, uint32_t cta_in_frame, uint32_t tid) {
+  const U4* my = a.ck + (size_t)frame * a.n_ck;
+  const uint32_t k = cta_in_frame * kXtcThreads + tid;
+  MyCheckpoint m;
+  m.me.x = 0u; m.me.y = kNoAtom; m.me.z = 0u; m.me.w = 0u;
+  m.next_atom = kNoAtom;
+  if (k < (uint32_t)a.n_ck) m.me = my[k];
+  if (k + 1u < (uint32_t)a.n_ck) m.next_atom = my[k + 1u].y;
+  return m;
+}
+// every thread, between the first and the second barrier: the stream span into shared memory.  On the device the copies are
+// asynchronous (cp.async, 4 bytes each: the span is only 4-byte aligned) so that all of them are in flight at once; they
+// are waited for just before the second barrier.  The words stay in file byte order (Stream.swap).
 XTC_HD void decode_cta_stage_stream(DecodeCta& cta, uint32_t tid) {
   if (cta.a_first == kNoAtom || !cta.staged) return;
-  for (uint32_t i = tid; i < cta.w_hi - cta.w_lo; i += kXtcThreads) cta.sw[i] = bswap32(cta.hw[10u + cta.w_lo + i]);
+  const uint32_t n = cta.w_hi - cta.w_lo;
+  const uint32_t* src = cta.hw + 10u + cta.w_lo;
+  for (uint32_t i = tid; i < n; i += kXtcThreads) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(cta.sw + i);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + i) : "memory");
+#else
+    cta.sw[i] = src[i];
+#endif
+  }
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
 }
 // every thread, between the second and the third barrier: the atoms of its checkpoint into the staging array
-XTC_HD void decode_cta_unpack(const DecodeArgs& a, DecodeCta& cta, int frame, uint32_t cta_in_frame, uint32_t tid) {
+XTC_HD void decode_cta_unpack(const DecodeArgs& a, DecodeCta& cta, uint32_t cta_in_frame, uint32_t tid, const MyCheckpoint& m) {
   if (cta.a_first == kNoAtom) return;
   const uint32_t natoms = (uint32_t)a.n_atoms;
   const uint32_t window = cta_in_frame * kXtcWindow;
   const uint32_t k = cta_in_frame * kXtcThreads + tid;
-  if (k >= (uint32_t)a.n_ck) return;
-  const U4* my = a.ck + (size_t)frame * a.n_ck;
-  const U4 me = my[k];
+  const U4 me = m.me;
   if (me.y >= natoms) return;
-  uint32_t next_atom = natoms;
-  if (k + 1u < (uint32_t)a.n_ck) {
-    const uint32_t nx = my[k + 1u].y;
-    if (nx < natoms) next_atom = nx;
-  }
+  const uint32_t next_atom = m.next_atom < natoms ? m.next_atom : natoms;
   uint32_t limit = window + (uint32_t)kXtcStage;
   if (limit > natoms) limit = natoms;
   // a checkpoint lies in its own 16-atom window; anything else is a damaged table
   bool ok = me.y / kCkAtoms == k && next_atom > me.y && next_atom <= limit;
   if (ok) {
     Stream s;
-    if (cta.staged) { s.w = cta.sw; s.lo = cta.w_lo; s.hi = cta.w_hi; s.swap = false; }
-    else { s.w = cta.hw + 10; s.lo = 0u; s.hi = (cta.h.nbytes + 3u) >> 2; s.swap = true; }
+    s.swap = true;
+    if (cta.staged) { s.w = cta.sw; s.lo = cta.w_lo; s.hi = cta.w_hi; }
+    else { s.w = cta.hw + 10; s.lo = 0u; s.hi = (cta.h.nbytes + 3u) >> 2; }
     const float precision = cta.h.precision;
     float* stage = cta.stage;
     ok = decode_groups(s, cta.h, unpack_cursor(me.x, me.y, me.z), next_atom, limit, [&](uint32_t atom, const int* kxyz) {
@@ -689,34 +741,54 @@ XTC_HD void decode_cta_unpack(const DecodeArgs& a, DecodeCta& cta, int frame, ui
   if (!ok) raise_flag(a.err_flags, kDecBadXtcBit);
 }
 // every thread, after the third barrier: coordinate blocks and site entries back to global memory.  The blocks of 8 atoms
-// of a window are contiguous in xyz8 ([x0..x7][y0..y7][z0..z7] per block), so consecutive threads write consecutive words.
+// of a window are contiguous in xyz8 ([x0..x7][y0..y7][z0..z7] per block): a thread writes four consecutive words — half a
+// row of a block, one 16-byte store when the CTA owns all four atoms — and consecutive threads consecutive quads.
 XTC_HD void decode_cta_write_back(const DecodeArgs& a, const DecodeCta& cta, int frame, uint32_t cta_in_frame, bool last_cta,
                                   uint32_t tid) {
   const uint32_t natoms = (uint32_t)a.n_atoms;
   const uint32_t window = cta_in_frame * kXtcWindow;
   const bool have = cta.a_first != kNoAtom;
   float* dst = a.xyz8 + ((size_t)frame * a.n_pad + window) * 3;
-  for (uint32_t idx = tid; idx < 3u * (uint32_t)kXtcStage; idx += kXtcThreads) {
-    const uint32_t blk = idx / 24u, rem = idx - 24u * blk;
-    const uint32_t j = blk * 8u + (rem & 7u), atom = window + j;
-    if (have && atom >= cta.a_first && atom < cta.a_end) {
-      dst[idx] = cta.stage[(rem >> 3) * kXtcStagePitch + j + (j >> 4)];
-    } else if (last_cta && atom >= natoms && atom < (uint32_t)a.n_pad) {
-      dst[idx] = 0.f;   // tile padding: its kq is 0 and its column is -1
+  for (uint32_t idx = 4u * tid; idx < 3u * (uint32_t)kXtcStage; idx += 4u * kXtcThreads) {
+    const uint32_t blk = idx / 24u, rem = idx - 24u * blk;             // rem: 0, 4, .., 20
+    const uint32_t j = blk * 8u + (rem & 7u), atom = window + j;       // the quad holds atoms atom .. atom + 3, one coordinate
+    const float* src = cta.stage + (rem >> 3) * kXtcStagePitch + j + (j >> 4);
+    if (have && atom >= cta.a_first && atom + 3u < cta.a_end) {
+      F4 q;
+      q.x = src[0]; q.y = src[1]; q.z = src[2]; q.w = src[3];
+      *reinterpret_cast<F4*>(dst + idx) = q;
+    } else {
+      for (uint32_t e = 0; e < 4u; e++) {
+        if (have && atom + e >= cta.a_first && atom + e < cta.a_end) {
+          dst[idx + e] = src[e];
+        } else if (last_cta && atom + e >= natoms && atom + e < (uint32_t)a.n_pad) {
+          dst[idx + e] = 0.f;   // tile padding: its kq is 0 and its column is -1
+        }
+      }
     }
   }
   if (!have) return;
-  for (uint32_t j = tid; j < (uint32_t)kXtcStage; j += kXtcThreads) {
-    const uint32_t atom = window + j;
-    if (atom >= cta.a_first && atom < cta.a_end) {
-      const int sl = a.slot[atom];
-      if (sl >= 0) {
-        const uint32_t at = j + (j >> 4);
-        F4 e;
-        e.x = -cta.stage[at]; e.y = -cta.stage[kXtcStagePitch + at]; e.z = -cta.stage[2 * kXtcStagePitch + at];
-        e.w = a.slot_dq[sl];
-        a.sites[(size_t)frame * a.sites_stride + sl] = e;
-      }
+  // site entries: the slot numbers of the window first (independent loads), then the few entries there are
+  constexpr int kRounds = (kXtcStage + kXtcThreads - 1) / kXtcThreads;
+  int sl[kRounds];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int rd = 0; rd < kRounds; rd++) {
+    const uint32_t j = (uint32_t)rd * kXtcThreads + tid, atom = window + j;
+    sl[rd] = (j < (uint32_t)kXtcStage && atom >= cta.a_first && atom < cta.a_end) ? a.slot[atom] : -1;
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int rd = 0; rd < kRounds; rd++) {
+    if (sl[rd] >= 0) {
+      const uint32_t j = (uint32_t)rd * kXtcThreads + tid;
+      const uint32_t at = j + (j >> 4);
+      F4 e;
+      e.x = -cta.stage[at]; e.y = -cta.stage[kXtcStagePitch + at]; e.z = -cta.stage[2 * kXtcStagePitch + at];
+      e.w = a.slot_dq[sl[rd]];
+      a.sites[(size_t)frame * a.sites_stride + sl[rd]] = e;
     }
   }
 }

@@ -21,6 +21,7 @@
 #include "kernels.cuh"
 #include "xtc_bits.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -45,38 +46,28 @@ xtc_index_kernel(const char* __restrict__ text, int64_t text_bytes, const int64_
   }
   Ring r;
   ring_init(r, ring_words, hw + 10, (h.nbytes + 3u) >> 2);
-  Cursor c{0u, 0u, h.smallidx, 0};
-  uint32_t prev_atom = kNoAtom;
+  Walk w{0u, 0u, (uint32_t)h.smallidx, 0u, kNoAtom};
   U4* table = ck + (size_t)f * n_ck;
-  const uint32_t natoms = (uint32_t)n_atoms;
+  const uint32_t natoms = (uint32_t)n_atoms, large_bits = (uint32_t)h.large_bits;
   bool ok = true;
-  while (ok && c.atom < natoms) {
-    const uint32_t nsm = (uint32_t)c.run / 3u;
-    const uint32_t len = (uint32_t)h.large_bits + 1u + nsm * (uint32_t)c.smallidx, gs = 1u + nsm;
-    const uint32_t cw = c.pos >> 5;
+  while (ok && w.atom < natoms) {
+    const uint32_t cw = w.pos >> 5;
     while (ring_can_issue(r, cw)) {
       ring_issue_lane(r, lane);
       ring_issued(r);
     }
     if (ring_must_wait(r, cw)) ring_wait(r);
-    const Probe p = probe_ring(r, c, len, gs, h.large_bits, lane);
-    const bool valid = p.atom < natoms;
-    const uint32_t set = __ballot_sync(0xFFFFFFFFu, valid && p.flag != 0u);
-    const int nv = __popc(__ballot_sync(0xFFFFFFFFu, valid));
-    const Cand mine = cand_after(p, c, h.large_bits, natoms);
-    const IndexStep st = plan_index_step(set, nv);
-    index_lane_emit(lane, p, c, prev_atom, st, table);
-    const int src = st.fl & 31;
-    Cand fc;
-    fc.pos = __shfl_sync(0xFFFFFFFFu, mine.pos, src);
-    fc.atom = __shfl_sync(0xFFFFFFFFu, mine.atom, src);
-    fc.smallidx = __shfl_sync(0xFFFFFFFFu, mine.smallidx, src);
-    fc.run = __shfl_sync(0xFFFFFFFFu, mine.run, src);
-    fc.ok = __shfl_sync(0xFFFFFFFFu, mine.ok, src);
-    ok = index_advance_cand(c, prev_atom, st, nv, fc, len, gs, natoms);
+    const LaneView v = walk_lane(r, w, large_bits, natoms, lane);
+    const bool valid = v.atom < natoms;
+    const uint32_t set = __ballot_sync(0xFFFFFFFFu, valid && v.flag != 0u);
+    const uint32_t nv = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, valid));
+    const uint32_t winner = walk_winner(set, nv);
+    walk_lane_emit(lane, v, w, winner, table);
+    ok = walk_advance(w, winner, __shfl_sync(0xFFFFFFFFu, v.npos, (int)winner), __shfl_sync(0xFFFFFFFFu, v.natom, (int)winner),
+                      __shfl_sync(0xFFFFFFFFu, v.nstate, (int)winner));
   }
   asm volatile("cp.async.wait_all;" ::: "memory");   // nothing may still be landing in shared memory when the CTA ends
-  if (ok && c.pos > 8u * h.nbytes) ok = false;
+  if (ok && w.pos > 8u * h.nbytes) ok = false;
   if (!ok && lane == 0) raise_flag(err_flags, kDecBadXtcBit);
 }
 
@@ -108,12 +99,13 @@ xtc_index_scalar_kernel(const char* __restrict__ text, int64_t text_bytes, const
   if (!ok || c.pos > 8u * h.nbytes) raise_flag(err_flags, kDecBadXtcBit);
 }
 
-__global__ void __launch_bounds__(kXtcThreads)
+__global__ void __launch_bounds__(kXtcThreads, 3)
 xtc_decode_kernel(DecodeArgs a) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   __shared__ DecodeCta cta;
   const int f = blockIdx.y;
   const uint32_t tid = threadIdx.x;
+  const MyCheckpoint mine = decode_cta_my_checkpoint(a, f, blockIdx.x, tid);
   if (tid == 0) {
     cta.stage = reinterpret_cast<float*>(sm_raw);
     cta.sw = reinterpret_cast<uint32_t*>(sm_raw + sizeof(float) * 3 * kXtcStagePitch);
@@ -122,7 +114,7 @@ xtc_decode_kernel(DecodeArgs a) {
   __syncthreads();
   decode_cta_stage_stream(cta, tid);
   __syncthreads();
-  decode_cta_unpack(a, cta, f, blockIdx.x, tid);
+  decode_cta_unpack(a, cta, blockIdx.x, tid, mine);
   __syncthreads();
   decode_cta_write_back(a, cta, f, blockIdx.x, blockIdx.x == gridDim.x - 1, tid);
 }
@@ -145,18 +137,27 @@ void launch_xtc_decode(const DeviceSystem& sys, const char* text, int64_t text_b
   } else {
     xtc_index_kernel<<<(unsigned)n_frames, 32, 0, st>>>(text, text_bytes, coords_off, sys.n_atoms, n_ck, ck, err_flags);
   }
-  const size_t smem = sizeof(float) * 3 * kXtcStagePitch + sizeof(uint32_t) * kXtcStreamWords;
+  // Stream words a 4096-atom window spans on average in this batch, with a quarter to spare: 23 KB hold them for boxes up
+  // to ~20 nm at precision 1000 (three CTAs per SM); frames that need more get up to 48 KB (two CTAs per SM).
+  const int64_t per_window = text_bytes / n_frames * kXtcWindow / std::max(1, sys.n_atoms) / 4;
+  int stream_words = kXtcStreamWords;
+  if (per_window + per_window / 4 + 64 > kXtcStreamWords) {
+    stream_words = (int)std::min<int64_t>(kXtcStreamWordsMax, (per_window + per_window / 4 + 64 + 255) / 256 * 256);
+  }
+  const size_t smem = sizeof(float) * 3 * kXtcStagePitch + sizeof(uint32_t) * (size_t)stream_words;
   static bool granted[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!granted[dev & 15]) {
-    cudaFuncSetAttribute(xtc_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(xtc_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(sizeof(float) * 3 * kXtcStagePitch + sizeof(uint32_t) * kXtcStreamWordsMax));
     granted[dev & 15] = true;
   }
   DecodeArgs a;
   a.text = text; a.text_bytes = text_bytes; a.coords_off = coords_off;
   a.n_atoms = sys.n_atoms; a.n_pad = sys.n_pad; a.n_ck = n_ck;
   a.ck = ck; a.slot = sys.slot; a.slot_dq = sys.slot_dq; a.sites_stride = sys.n_sites * sys.site_cap;
+  a.stream_words = stream_words;
   a.xyz8 = xyz8; a.sites = reinterpret_cast<F4*>(sites); a.err_flags = err_flags;
   const dim3 grid((unsigned)((sys.n_atoms + kXtcWindow - 1) / kXtcWindow), (unsigned)n_frames);
   xtc_decode_kernel<<<grid, kXtcThreads, smem, st>>>(a);

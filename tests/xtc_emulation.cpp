@@ -29,37 +29,32 @@ int64_t index_frame_warp(const char* text, int64_t text_bytes, int64_t off, int 
   std::vector<uint32_t> ring_words(kRingWords, kRingPoison);   // the kernel's shared memory
   Ring r;
   ring_init(r, ring_words.data(), hw + 10, (h.nbytes + 3u) >> 2);
-  Cursor c{0u, 0u, h.smallidx, 0};
-  uint32_t prev_atom = kNoAtom;
-  const uint32_t natoms = (uint32_t)n_atoms;
+  Walk w{0u, 0u, (uint32_t)h.smallidx, 0u, kNoAtom};
+  const uint32_t natoms = (uint32_t)n_atoms, large_bits = (uint32_t)h.large_bits;
   bool ok = true;
   int64_t steps = 0;
-  while (ok && c.atom < natoms) {
-    const uint32_t nsm = (uint32_t)c.run / 3u;
-    const uint32_t len = (uint32_t)h.large_bits + 1u + nsm * (uint32_t)c.smallidx, gs = 1u + nsm;
-    const uint32_t cw = c.pos >> 5;
+  while (ok && w.atom < natoms) {
+    const uint32_t cw = w.pos >> 5;
     while (ring_can_issue(r, cw)) {
       for (uint32_t lane = 0; lane < 32; lane++) ring_issue_lane(r, lane);
       ring_issued(r);
     }
     if (ring_must_wait(r, cw)) ring_wait(r);
-    Probe p[32];
-    Cand mine[32];
+    LaneView v[32];
     uint32_t set = 0, vmask = 0;
     for (uint32_t lane = 0; lane < 32; lane++) {
-      p[lane] = probe_ring(r, c, len, gs, h.large_bits, lane);
-      const bool valid = p[lane].atom < natoms;
+      v[lane] = walk_lane(r, w, large_bits, natoms, lane);
+      const bool valid = v[lane].atom < natoms;
       if (valid) vmask |= 1u << lane;
-      if (valid && p[lane].flag != 0u) set |= 1u << lane;
-      mine[lane] = cand_after(p[lane], c, h.large_bits, natoms);
+      if (valid && v[lane].flag != 0u) set |= 1u << lane;
     }
-    const int nv = __builtin_popcount(vmask);
-    const IndexStep st = plan_index_step(set, nv);
-    for (uint32_t lane = 0; lane < 32; lane++) index_lane_emit(lane, p[lane], c, prev_atom, st, table);
-    ok = index_advance_cand(c, prev_atom, st, nv, mine[st.fl & 31], len, gs, natoms);
+    const uint32_t nv = (uint32_t)__builtin_popcount(vmask);
+    const uint32_t winner = walk_winner(set, nv);
+    for (uint32_t lane = 0; lane < 32; lane++) walk_lane_emit(lane, v[lane], w, winner, table);
+    ok = walk_advance(w, winner, v[winner].npos, v[winner].natom, v[winner].nstate);
     steps++;
   }
-  if (ok && c.pos > 8u * h.nbytes) ok = false;
+  if (ok && w.pos > 8u * h.nbytes) ok = false;
   if (!ok) raise_flag(err, kDecBadXtcBit);
   (void)n_ck;
   return steps;
@@ -117,9 +112,10 @@ int emu_xtc_decode(const char* text, int64_t text_bytes, const int64_t* coords_o
   a.text = text; a.text_bytes = text_bytes; a.coords_off = coords_off;
   a.n_atoms = n_atoms; a.n_pad = n_pad; a.n_ck = n_ck;
   a.ck = ck.data(); a.slot = slot; a.slot_dq = slot_dq; a.sites_stride = sites_stride;
+  a.stream_words = max_stream_words > 0 ? max_stream_words : kXtcStreamWords;   // smaller values force the unstaged path
   a.xyz8 = xyz8; a.sites = reinterpret_cast<F4*>(sites); a.err_flags = &err;
   std::vector<float> stage((size_t)3 * kXtcStagePitch);
-  std::vector<uint32_t> sw((size_t)kXtcStreamWords);
+  std::vector<uint32_t> sw((size_t)a.stream_words);
   const uint32_t ctas = (uint32_t)((n_atoms + kXtcWindow - 1) / kXtcWindow);
   int64_t n_staged = 0, n_global = 0;
   for (int f = 0; f < n_frames; f++) {
@@ -130,11 +126,12 @@ int emu_xtc_decode(const char* text, int64_t text_bytes, const int64_t* coords_o
       DecodeCta cta;
       cta.stage = stage.data();
       cta.sw = sw.data();
-      decode_cta_setup(a, cta, f, b);                                  // thread 0
-      if (max_stream_words > 0 && cta.a_first != kNoAtom && (int)(cta.w_hi - cta.w_lo) > max_stream_words) cta.staged = 0;
+      MyCheckpoint mine[kXtcThreads];
+      for (uint32_t tid = 0; tid < kXtcThreads; tid++) mine[tid] = decode_cta_my_checkpoint(a, f, b, tid);
+      decode_cta_setup(a, cta, f, b);                                  // thread 0; __syncthreads
       if (cta.a_first != kNoAtom) (cta.staged ? n_staged : n_global)++;
       for (uint32_t tid = 0; tid < kXtcThreads; tid++) decode_cta_stage_stream(cta, tid);          // __syncthreads
-      for (uint32_t tid = 0; tid < kXtcThreads; tid++) decode_cta_unpack(a, cta, f, b, tid);        // __syncthreads
+      for (uint32_t tid = 0; tid < kXtcThreads; tid++) decode_cta_unpack(a, cta, b, tid, mine[tid]);   // __syncthreads
       for (uint32_t tid = 0; tid < kXtcThreads; tid++) decode_cta_write_back(a, cta, f, b, b == ctas - 1, tid);
     }
   }
