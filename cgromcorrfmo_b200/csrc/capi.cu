@@ -614,7 +614,9 @@ int default_batch(const cgc_context* c) {
   // the FP64 bins of a batch should stay small next to the text
   const int64_t per_frame_out = (int64_t)c->sys.n_sites * c->sys.num_tot * 12;
   b = std::min<int64_t>(b, ((int64_t)2 << 30) / std::max<int64_t>(1, per_frame_out));
-  return (int)std::max<int64_t>(1, std::min<int64_t>(256, b));
+  // .xtc: the index pass of K1x takes the same time for 32 frames as for 512 (one warp per frame, all at once), so its
+  // batches are as large as the buffers sensibly allow
+  return (int)std::max<int64_t>(1, std::min<int64_t>(c->xtc ? 512 : 256, b));
 }
 
 // n_slots: kSlots for the streaming ring (run_impl), 1 for the entry points that work on text already on the device (they

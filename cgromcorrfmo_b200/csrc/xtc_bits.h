@@ -100,8 +100,10 @@ struct Stream {
   bool swap;
 };
 XTC_HD uint32_t stream_word(const Stream& s, uint32_t idx) {
-  idx = idx < s.lo ? s.lo : (idx >= s.hi ? s.hi - 1 : idx);
-  const uint32_t v = s.w[idx - s.lo];
+  uint32_t at = idx - s.lo;                       // a word below lo wraps to a huge offset: one unsigned minimum covers both ends
+  const uint32_t last = s.hi - s.lo - 1u;
+  at = at < last ? at : last;
+  const uint32_t v = s.w[at];
   return s.swap ? bswap32(v) : v;
 }
 // the 32 bits that start at bit position p
@@ -126,8 +128,25 @@ XTC_HD uint32_t value_of_stream_bits(uint32_t y, int rem) {
   const uint32_t keep = nfull ? (0xFFFFFFFFu >> (32 - 8 * nfull)) : 0u;
   return (v & keep) | ((((v >> (8 * nfull)) & 0xFFu) >> (8 - last)) << (8 * nfull));
 }
+// A packed number of nbits (1..64) bits at p: two chunks of up to 32 stream bits.
+XTC_HD uint64_t read_packed64(const Stream& s, uint32_t p, int nbits) {
+  if (nbits <= 32) {
+    const uint32_t y = peek32(s, p);
+    return value_of_stream_bits(nbits == 32 ? y : (y & (0xFFFFFFFFu << (32 - nbits))), nbits);
+  }
+  const uint32_t w0 = bswap32(peek32(s, p));
+  const int rem = nbits - 32;
+  const uint32_t y = peek32(s, p + 32u);
+  const uint32_t w1 = value_of_stream_bits(rem == 32 ? y : (y & (0xFFFFFFFFu << (32 - rem))), rem);
+  return (uint64_t)w0 | ((uint64_t)w1 << 32);
+}
 // A packed number of nbits (1..96) bits at p.
 XTC_HD void read_packed(const Stream& s, uint32_t p, int nbits, uint64_t& lo, uint32_t& hi) {
+  if (nbits <= 64) {
+    lo = read_packed64(s, p, nbits);
+    hi = 0u;
+    return;
+  }
   uint32_t w[3] = {0u, 0u, 0u};
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -370,8 +389,7 @@ XTC_HD bool decode_groups(const Stream& s, const FrameHdr& h, Cursor c, uint32_t
       for (uint32_t k = 0; k < nsm; k++) {
         uint32_t d3[3];
         if (c.smallidx <= 32) {
-          const uint32_t y = c.smallidx == 32 ? peek32(s, p) : (peek32(s, p) & (0xFFFFFFFFu << (32 - c.smallidx)));
-          uint32_t q = value_of_stream_bits(y, c.smallidx);
+          uint32_t q = (uint32_t)read_packed64(s, p, c.smallidx);
           q = divmod32(q, small_size, small_m32, d3[2]);
           d3[0] = divmod32(q, small_size, small_m32, d3[1]);
         } else {

@@ -137,13 +137,14 @@ void launch_xtc_decode(const DeviceSystem& sys, const char* text, int64_t text_b
   } else {
     xtc_index_kernel<<<(unsigned)n_frames, 32, 0, st>>>(text, text_bytes, coords_off, sys.n_atoms, n_ck, ck, err_flags);
   }
-  // Stream words a 4096-atom window spans on average in this batch, with a quarter to spare: 23 KB hold them for boxes up
-  // to ~20 nm at precision 1000 (three CTAs per SM); frames that need more get up to 48 KB (two CTAs per SM).
+  // Stream words a 4096-atom window spans on average in this batch, with a twelfth to spare (a window of isolated atoms in
+  // a frame that also holds bonded runs is longer than the average): 23 KB hold them for boxes up to ~20 nm at precision
+  // 1000 (three CTAs per SM); frames that need more get up to 48 KB (two CTAs per SM); a window that still does not fit
+  // reads its stream from global memory.
   const int64_t per_window = text_bytes / n_frames * kXtcWindow / std::max(1, sys.n_atoms) / 4;
+  const int64_t want_words = per_window + per_window / 12 + 64;
   int stream_words = kXtcStreamWords;
-  if (per_window + per_window / 4 + 64 > kXtcStreamWords) {
-    stream_words = (int)std::min<int64_t>(kXtcStreamWordsMax, (per_window + per_window / 4 + 64 + 255) / 256 * 256);
-  }
+  if (want_words > kXtcStreamWords) stream_words = (int)std::min<int64_t>(kXtcStreamWordsMax, (want_words + 255) / 256 * 256);
   const size_t smem = sizeof(float) * 3 * kXtcStagePitch + sizeof(uint32_t) * (size_t)stream_words;
   static bool granted[16] = {};
   int dev = 0;
