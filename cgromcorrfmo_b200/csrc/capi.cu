@@ -1594,7 +1594,8 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
       int want = (int)std::min<int64_t>(B, n_frames - planned);
       {
         const int64_t min_b = std::max<int64_t>(1, B / 4), left = n_frames - planned;
-        want = (int)std::min<int64_t>(want, planned + min_b);
+        // (not for .xtc: its stream is a tenth of the text, and every launch of K1x pays the full latency of the index walk)
+        if (!ctx->xtc) want = (int)std::min<int64_t>(want, planned + min_b);
         // the ramp down only pays when the copies are the bottleneck (text): a compute-bound stream (.trr) would just
         // finish on small, less efficient launches
         if (ramp_down && left > min_b) want = (int)std::min<int64_t>(want, std::max<int64_t>(min_b, (left + 1) / 2));
