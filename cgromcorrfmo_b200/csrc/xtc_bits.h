@@ -513,6 +513,8 @@ XTC_HD bool index_advance(Cursor& c, uint32_t& prev_atom, const IndexStep& st, i
 constexpr uint32_t kRingWords = 4096;      // 16 KB per warp
 constexpr uint32_t kRingChunk = 1024;
 constexpr uint32_t kRingLook = 704;        // 31 * (96 + 1 + 8 * 72) + 96 + 32 bits, rounded up, in words
+constexpr uint32_t kWide = 4;              // groups per lane in a wide step (below)
+constexpr uint32_t kRingLookWide = 2816;   // the same for 32 * kWide groups; kRingWords >= kRingChunk + kRingLookWide
 constexpr uint32_t kRingPoison = 0xDEADBEEFu;
 struct Ring {
   uint32_t* w;           // [kRingWords]
@@ -550,7 +552,7 @@ XTC_HD void ring_issued(Ring& r) {   // after every lane has issued its share
   r.issued += kRingChunk;
 }
 // does the step at word cw need words that are still on their way?
-XTC_HD bool ring_must_wait(const Ring& r, uint32_t cw) { return r.ready < r.issued && cw + kRingLook > r.ready; }
+XTC_HD bool ring_must_wait(const Ring& r, uint32_t cw, uint32_t look) { return r.ready < r.issued && cw + look > r.ready; }
 XTC_HD void ring_wait(Ring& r) {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.wait_all;" ::: "memory");
@@ -631,6 +633,52 @@ XTC_HD bool walk_advance(Walk& w, uint32_t winner, uint32_t npos, uint32_t natom
   w.smallidx = nstate & 0xFFu;
   w.nsm = (nstate >> 8) & 0xFFu;
   return (nstate >> 16) != 0u;
+}
+
+// The wide step, for stretches without a single set flag bit (isolated atoms, or runs of one length: nothing but the
+// position changes from group to group): every lane looks at kWide groups, 32 * kWide in all, and the step consumes the
+// clear groups in front of the first set flag (or the last atom) — none of the per-lane "state after my group" work of
+// the narrow step is needed, because a clear flag leaves the state as it is.  The walk goes wide after a narrow step that
+// found 32 clear flags and stays wide while every flag it sees is clear; a set flag is always taken by a narrow step.
+XTC_HD uint32_t wide_flag(const Ring& r, const Walk& w, uint32_t large_bits, uint32_t len, uint32_t g) {
+  return ring_peek32(r, w.pos + g * len + large_bits) >> 31;
+}
+// set[k] / valid[k]: ballots over the lanes for group lane + 32 k.  The number of leading groups that exist and are clear.
+XTC_HD uint32_t wide_count(const uint32_t set[kWide], const uint32_t valid[kWide]) {
+  uint32_t n = 0;
+  for (uint32_t k = 0; k < kWide; k++) {
+    const uint32_t stop = set[k] | ~valid[k];
+    if (stop) {
+#if defined(__CUDA_ARCH__)
+      return n + (uint32_t)__ffs((int)stop) - 1u;
+#else
+      return n + (uint32_t)__builtin_ctz(stop);
+#endif
+    }
+    n += 32u;
+  }
+  return n;
+}
+XTC_HD void wide_lane_emit(uint32_t lane, const Walk& w, uint32_t len, uint32_t gs, uint32_t n, U4* table) {
+  for (uint32_t k = 0; k < kWide; k++) {
+    const uint32_t g = lane + 32u * k;
+    if (g >= n) return;
+    const uint32_t atom = w.atom + g * gs;
+    const uint32_t before = g == 0u ? w.prev_atom : atom - gs;
+    if (before == kNoAtom || (before / kCkAtoms) < (atom / kCkAtoms)) {
+      U4 rec;
+      rec.x = w.pos + g * len; rec.y = atom; rec.z = w.smallidx | ((3u * w.nsm) << 8); rec.w = 0u;
+      table[atom / kCkAtoms] = rec;
+    }
+  }
+}
+// after n clear groups.  False: the last of them passes the atom count (impossible stream).
+XTC_HD bool wide_advance(Walk& w, uint32_t len, uint32_t gs, uint32_t n, uint32_t natoms) {
+  if (n == 0u) return true;
+  w.prev_atom = w.atom + (n - 1u) * gs;
+  w.pos += n * len;
+  w.atom += n * gs;
+  return w.atom <= natoms;
 }
 
 // ---- decode pass: one CTA of kXtcThreads threads per window of kXtcWindow atoms ------------------------------------------

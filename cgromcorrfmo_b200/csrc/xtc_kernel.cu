@@ -49,20 +49,38 @@ xtc_index_kernel(const char* __restrict__ text, int64_t text_bytes, const int64_
   Walk w{0u, 0u, (uint32_t)h.smallidx, 0u, kNoAtom};
   U4* table = ck + (size_t)f * n_ck;
   const uint32_t natoms = (uint32_t)n_atoms, large_bits = (uint32_t)h.large_bits;
-  bool ok = true;
+  bool ok = true, wide = false;
   while (ok && w.atom < natoms) {
     const uint32_t cw = w.pos >> 5;
     while (ring_can_issue(r, cw)) {
       ring_issue_lane(r, lane);
       ring_issued(r);
     }
-    if (ring_must_wait(r, cw)) ring_wait(r);
+    if (ring_must_wait(r, cw, wide ? kRingLookWide : kRingLook)) ring_wait(r);
+    if (wide) {
+      const uint32_t len = large_bits + 1u + w.nsm * w.smallidx, gs = 1u + w.nsm;
+      uint32_t set[kWide], valid[kWide];
+#pragma unroll
+      for (uint32_t k = 0; k < kWide; k++) {
+        const uint32_t g = lane + 32u * k;
+        const bool exists = w.atom + g * gs < natoms;
+        const uint32_t flag = wide_flag(r, w, large_bits, len, g);
+        set[k] = __ballot_sync(0xFFFFFFFFu, exists && flag != 0u);
+        valid[k] = __ballot_sync(0xFFFFFFFFu, exists);
+      }
+      const uint32_t n = wide_count(set, valid);
+      wide_lane_emit(lane, w, len, gs, n, table);
+      ok = wide_advance(w, len, gs, n, natoms);
+      wide = n == 32u * kWide;
+      continue;
+    }
     const LaneView v = walk_lane(r, w, large_bits, natoms, lane);
     const bool valid = v.atom < natoms;
     const uint32_t set = __ballot_sync(0xFFFFFFFFu, valid && v.flag != 0u);
     const uint32_t nv = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, valid));
     const uint32_t winner = walk_winner(set, nv);
     walk_lane_emit(lane, v, w, winner, table);
+    wide = set == 0u && nv == 32u;   // 32 clear flags: look further next time
     ok = walk_advance(w, winner, __shfl_sync(0xFFFFFFFFu, v.npos, (int)winner), __shfl_sync(0xFFFFFFFFu, v.natom, (int)winner),
                       __shfl_sync(0xFFFFFFFFu, v.nstate, (int)winner));
   }

@@ -31,7 +31,7 @@ int64_t index_frame_warp(const char* text, int64_t text_bytes, int64_t off, int 
   ring_init(r, ring_words.data(), hw + 10, (h.nbytes + 3u) >> 2);
   Walk w{0u, 0u, (uint32_t)h.smallidx, 0u, kNoAtom};
   const uint32_t natoms = (uint32_t)n_atoms, large_bits = (uint32_t)h.large_bits;
-  bool ok = true;
+  bool ok = true, wide = false;
   int64_t steps = 0;
   while (ok && w.atom < natoms) {
     const uint32_t cw = w.pos >> 5;
@@ -39,7 +39,27 @@ int64_t index_frame_warp(const char* text, int64_t text_bytes, int64_t off, int 
       for (uint32_t lane = 0; lane < 32; lane++) ring_issue_lane(r, lane);
       ring_issued(r);
     }
-    if (ring_must_wait(r, cw)) ring_wait(r);
+    if (ring_must_wait(r, cw, wide ? kRingLookWide : kRingLook)) ring_wait(r);
+    steps++;
+    if (wide) {
+      const uint32_t len = large_bits + 1u + w.nsm * w.smallidx, gs = 1u + w.nsm;
+      uint32_t set[kWide], valid[kWide];
+      for (uint32_t k = 0; k < kWide; k++) {
+        set[k] = valid[k] = 0u;
+        for (uint32_t lane = 0; lane < 32; lane++) {
+          const uint32_t g = lane + 32u * k;
+          const bool exists = w.atom + g * gs < natoms;
+          const uint32_t flag = wide_flag(r, w, large_bits, len, g);
+          if (exists) valid[k] |= 1u << lane;
+          if (exists && flag != 0u) set[k] |= 1u << lane;
+        }
+      }
+      const uint32_t n = wide_count(set, valid);
+      for (uint32_t lane = 0; lane < 32; lane++) wide_lane_emit(lane, w, len, gs, n, table);
+      ok = wide_advance(w, len, gs, n, natoms);
+      wide = n == 32u * kWide;
+      continue;
+    }
     LaneView v[32];
     uint32_t set = 0, vmask = 0;
     for (uint32_t lane = 0; lane < 32; lane++) {
@@ -51,8 +71,8 @@ int64_t index_frame_warp(const char* text, int64_t text_bytes, int64_t off, int 
     const uint32_t nv = (uint32_t)__builtin_popcount(vmask);
     const uint32_t winner = walk_winner(set, nv);
     for (uint32_t lane = 0; lane < 32; lane++) walk_lane_emit(lane, v[lane], w, winner, table);
+    wide = set == 0u && nv == 32u;
     ok = walk_advance(w, winner, v[winner].npos, v[winner].natom, v[winner].nstate);
-    steps++;
   }
   if (ok && w.pos > 8u * h.nbytes) ok = false;
   if (!ok) raise_flag(err, kDecBadXtcBit);
