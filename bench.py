@@ -759,7 +759,9 @@ def run_ours(args):
                 log("bench: %d .xtc frames encoded in %.1f s (%.2f B/atom)" % (F, time.time() - t_enc, n_xtc / F / n_atoms))
             ctx3 = capi.Context(top, itp, local)
             ctx3.open_memory_xtc((host_xtc.data_ptr(), n_xtc), struct_gro)
-            xtc_batch = args.e2e_batch or int(min(F, 128))            # the index pass costs the same for 32 frames as for 256
+            # a call of F frames in four batches: the copy and the kernels of consecutive batches overlap inside the call
+            # (every launch of K1x pays the latency of its index walk once, so long runs use batches of up to 512 frames)
+            xtc_batch = args.e2e_batch or int(min(F, 64))
             ctx3.set_option("batch_frames", xtc_batch)
             ctx3.set_option("profile", 1)
             if not cov_on:

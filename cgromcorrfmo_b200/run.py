@@ -1,6 +1,7 @@
 """traj2dEcsv as a Python call, one process per GPU (launch with torchrun for more than one):
 
     python -m cgromcorrfmo_b200.run traj_in topology excited_itp csv_out num_frames [--sites N] [--mtx-compat]
+                                    [--structure frame0.gro   (traj_in is then a GROMACS .trr or .xtc)]
 
 Same five positionals and the same two output files as the reference program (reference README.md:25-31); with R ranks
 every rank streams its frame range, writes csv_out.time.part<r>, and the Correlate sums are combined by one NCCL
@@ -16,7 +17,16 @@ import numpy as np
 from . import capi, dist as cdist
 
 
-def traj2dEcsv(traj, top, itp, out, num_frames, sites=0, mtx_compat=False, chunk_frames=0, device=None):
+def open_trajectory(c, traj, structure=None):
+    """.gro text on its own; a binary .trr / compressed .xtc (by extension) with the names taken from `structure`."""
+    if structure:
+        return c.open_xtc(traj, structure) if traj.endswith(".xtc") else c.open_trr(traj, structure)
+    if traj.endswith((".trr", ".xtc")):
+        raise capi.CgcError(capi.CGC_ERR_ARG, "a %s trajectory holds no atom names: pass structure=<file.gro>" % traj[-4:])
+    return c.open(traj)
+
+
+def traj2dEcsv(traj, top, itp, out, num_frames, sites=0, mtx_compat=False, chunk_frames=0, device=None, structure=None):
     import torch
     import torch.distributed as tdist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -40,7 +50,7 @@ def traj2dEcsv(traj, top, itp, out, num_frames, sites=0, mtx_compat=False, chunk
         else:
             tdist.init_process_group(backend)
     with capi.Context(top, itp, local) as c:
-        c.open(traj)
+        open_trajectory(c, traj, structure)
         if sites:
             c.set_option("sites", sites)
         if mtx_compat:
@@ -84,8 +94,10 @@ def main(argv=None):
     ap.add_argument("--sites", type=int, default=0)
     ap.add_argument("--mtx-compat", action="store_true")
     ap.add_argument("--device", type=int, default=None, help="CUDA device for this rank (default: LOCAL_RANK)")
+    ap.add_argument("--structure", default=None, help="a .gro frame of the same system; traj_in is then a .trr or .xtc")
     a = ap.parse_args(argv)
-    traj2dEcsv(a.traj_in, a.topology, a.excited_itp, a.csv_out, a.num_frames, a.sites, a.mtx_compat, device=a.device)
+    traj2dEcsv(a.traj_in, a.topology, a.excited_itp, a.csv_out, a.num_frames, a.sites, a.mtx_compat, device=a.device,
+               structure=a.structure)
     return 0
 
 

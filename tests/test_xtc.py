@@ -545,3 +545,19 @@ def test_cli_reads_xtc(small_inputs, tmp_path):
     assert a.shape == b.shape and np.allclose(a, b, rtol=1e-5, atol=1e-12)
     r = subprocess.run([build.CLI, xtc, top, itp, out_x, str(frames)], capture_output=True, text=True)
     assert r.returncode == 1 and "--structure" in r.stderr
+
+
+@pytest.mark.gpu
+def test_python_driver_reads_xtc(small_inputs, tmp_path):
+    """python -m cgromcorrfmo_b200.run with --structure: the .xtc run writes the same .time text as the .gro run."""
+    from cgromcorrfmo_b200 import run
+    traj, top, itp, frames = small_inputs("tiny")
+    s, _ = _system("tiny")
+    xtc = str(tmp_path / "t.xtc")
+    synth.write_xtc(xtc, s, frames)
+    out_g, out_x = str(tmp_path / "g"), str(tmp_path / "x")
+    assert run.traj2dEcsv(traj, top, itp, out_g, frames) == frames
+    assert run.traj2dEcsv(xtc, top, itp, out_x, frames + 5, structure=traj) == frames
+    assert open(out_g + ".time", "rb").read() == open(out_x + ".time", "rb").read()
+    with pytest.raises(capi.CgcError):
+        run.traj2dEcsv(xtc, top, itp, out_x, frames)                  # no structure file
