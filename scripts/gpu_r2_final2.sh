@@ -7,6 +7,8 @@ timeout 300 python __graft_entry__.py smoke > $O/smoke.log 2>&1; echo "smoke rc=
 timeout 900 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "bench n1 rc=$?"; tail -3 $O/bench_n1.err
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:xtc_index_kernel -s 2 -c 1 -f -o $O/xtc_index python scripts/dev_xtc_check.py 256 0 256 > $O/ncu_index.log 2>&1; echo "ncu index rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:xtc_decode_kernel -s 2 -c 1 -f -o $O/xtc_decode python scripts/dev_xtc_check.py 256 0 256 > $O/ncu_decode.log 2>&1; echo "ncu decode rc=$?"
+timeout 300 python scripts/dev_xtc_check.py 256 0 64,256 water > $O/dev_xtc_check_water.log 2>&1; echo "water check rc=$?"; tail -3 $O/dev_xtc_check_water.log
+timeout 200 python scripts/dev_xtc_check.py 256 0 64,256 > $O/dev_xtc_check.log 2>&1; echo "check rc=$?"; tail -3 $O/dev_xtc_check.log
 python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/r2/final2/bench_n1.json").read().strip().splitlines()[-1])
