@@ -818,8 +818,10 @@ def run_ours(args):
                    "note": "same frames as the headline; not the reference's input format (it reads .gro text); at N > 1 the one all-reduce of the Correlate sums is timed after the ranks agreed that the leg ran and added to the leg's time",
                    "rows_bit_identical_to_gro_path": xtc_same,
                    "kernel_ms": {k: v[0] for k, v in xtc_ktimes.items()},
-                   "k1x_ms_per_launch": (kd_ms / kd_n) if kd_n else None, "k1x_launches": int(kd_n),
-                   "k1x_frames_per_launch": xtc_batch, "wall_ms": xtc_s * 1e3}
+                   "k1x_unpack_ms_per_launch": (kd_ms / kd_n) if kd_n else None, "k1x_launches": int(kd_n),
+                   "k1x_frames_per_launch": xtc_batch, "wall_ms": xtc_s * 1e3,
+                   "k1x_note": "kernel_ms.decode is the unpack pass; the index pass runs on a stream of its own beside the previous "
+                               "batch's kernels (0.5-0.6 ms per launch on these frames, profiles/r02_xtc_launches.csv)"}
         else:
             xtc = {"failed": xtc_err}
         del cov, d_text, d_dE

@@ -249,6 +249,7 @@ struct Slot {
   int* d_fmt_flag = nullptr;    // K5: this batch held a value outside the device formatter's range
   int64_t ttext_cap = 0;
   cudaEvent_t ev_copied = nullptr, ev_done = nullptr;
+  cudaEvent_t ev_text = nullptr;       // .xtc: the H2D copy alone (ev_copied then follows the index pass)
   cudaEvent_t ev_text_out = nullptr;   // the D2H copy of d_ttext has finished (the next batch may overwrite d_ttext)
   bool text_out_pending = false;
   CopyPool::Job stage_job;   // staging copy of the batch planned into this slot
@@ -305,6 +306,7 @@ struct cgc_context {
   int64_t alloc_text = 0;
   int alloc_slots = 0;          // slots that have their buffers (1 for the device-resident entry points, kSlots for the ring)
   cudaStream_t st_copy = nullptr, st_comp = nullptr, st_out = nullptr;
+  cudaStream_t st_index = nullptr;   // .xtc: the index pass of K1x, beside the previous batch's kernels (high priority)
   int* d_err = nullptr;
   int* d_fmt_flags = nullptr;   // K5 flag word of the one-shot formatter calls (cgc_write_mtx); the ring has one per slot
   int64_t launches = 0;
@@ -374,11 +376,12 @@ void free_pipeline(cgc_context* c) {
     if (s.h_tinfo) cudaFreeHost(s.h_tinfo);
     if (s.d_fmt_flag) guard_free(s.d_fmt_flag);
     if (s.ev_copied) cudaEventDestroy(s.ev_copied);
+    if (s.ev_text) cudaEventDestroy(s.ev_text);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
     if (s.ev_text_out) cudaEventDestroy(s.ev_text_out);
     s.h_text = nullptr; s.d_text = nullptr; s.d_off = nullptr; s.h_off = nullptr; s.d_xyz8 = nullptr; s.d_xtc = nullptr; s.d_sites = nullptr;
     s.d_acc = nullptr; s.d_dE = nullptr; s.h_dE = nullptr; s.d_ttext = nullptr; s.d_rowoff = nullptr; s.h_tinfo = nullptr;
-    s.d_fmt_flag = nullptr; s.ttext_cap = 0; s.ev_copied = s.ev_done = s.ev_text_out = nullptr;
+    s.d_fmt_flag = nullptr; s.ttext_cap = 0; s.ev_copied = s.ev_done = s.ev_text_out = s.ev_text = nullptr;
     s.text_out_pending = false; s.staged_here = false; s.src = nullptr; s.nb = 0; s.frames = 0; s.out_frame = 0; s.busy = false;
   }
   for (int i = 0; i < cgc_context::kSinkBufs; i++) {
@@ -428,6 +431,7 @@ cgc_context::~cgc_context() {
     for (auto& t : timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto& e : ev_pool) cudaEventDestroy(e);
     if (st_copy) cudaStreamDestroy(st_copy);
+    if (st_index) cudaStreamDestroy(st_index);
     if (st_comp) cudaStreamDestroy(st_comp);
     if (st_out) cudaStreamDestroy(st_out);
     if (d_fmt_flags) guard_free(d_fmt_flags);
@@ -566,6 +570,11 @@ void build_static(cgc_context* c) {
   CUDA_OK(cudaMemcpy(sys.slot, slot.data(), sizeof(int32_t) * sys.n_pad, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(sys.slot_dq, slot_dq.data(), sizeof(float) * slot_dq.size(), cudaMemcpyHostToDevice));
   if (!c->st_copy) CUDA_OK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+  if (!c->st_index) {
+    int least = 0, greatest = 0;
+    CUDA_OK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CUDA_OK(cudaStreamCreateWithPriority(&c->st_index, cudaStreamNonBlocking, greatest));
+  }
   if (!c->st_comp) CUDA_OK(cudaStreamCreateWithFlags(&c->st_comp, cudaStreamNonBlocking));
   if (!c->st_out) CUDA_OK(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
   if (!c->d_fmt_flags) {
@@ -652,6 +661,7 @@ void ensure_pipeline(cgc_context* c, int batch, int64_t text_bytes, bool need_ho
       s.h_dE = (float*)s.h_dE_block.p;
     }
     CUDA_OK(cudaEventCreateWithFlags(&s.ev_copied, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&s.ev_text, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&s.ev_text_out, cudaEventDisableTiming));
     launch_init_sites(sys, s.d_sites, batch, c->st_comp);
@@ -984,11 +994,15 @@ void accumulate_rows(cgc_context* c, const float* d_dE, int n_frames, cudaStream
 
 // K1 -> K2 -> finish (-> K3) for one batch whose text is already in d_text; everything on `st`
 void enqueue_decode(cgc_context* c, const char* d_text, int64_t text_bytes, const int64_t* d_off, int n_frames, const Slot& s,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool xtc_indexed = false) {
   ScopedKernelTimer t(c, 0, st);
   if (c->sys.traj_mode == 3) {
-    launch_xtc_decode(c->sys, d_text, text_bytes, d_off, n_frames, s.d_xtc, s.d_xyz8, s.d_sites, c->d_err, st);
-    c->launches += 1;   // index pass + unpack pass: one launch more than the callers count for the decode step
+    if (xtc_indexed) {   // the streaming loop has run the index pass on its own stream already
+      launch_xtc_unpack(c->sys, d_text, text_bytes, d_off, n_frames, s.d_xtc, s.d_xyz8, s.d_sites, c->d_err, st);
+    } else {
+      launch_xtc_decode(c->sys, d_text, text_bytes, d_off, n_frames, s.d_xtc, s.d_xyz8, s.d_sites, c->d_err, st);
+      c->launches += 1;   // index pass + unpack pass: one launch more than the callers count for the decode step
+    }
   } else {
     launch_decode(c->sys, d_text, text_bytes, d_off, n_frames, s.d_xyz8, s.d_sites, c->d_err, st);
   }
@@ -996,12 +1010,12 @@ void enqueue_decode(cgc_context* c, const char* d_text, int64_t text_bytes, cons
 
 // `s`: the slot whose scratch (coordinates, site blocks, bins, .xtc checkpoints) the batch uses
 void enqueue_compute(cgc_context* c, const char* d_text, int64_t text_bytes, const int64_t* d_off, int n_frames,
-                     const Slot& s, float* d_dE, bool accumulate, cudaStream_t st) {
+                     const Slot& s, float* d_dE, bool accumulate, cudaStream_t st, bool xtc_indexed = false) {
   const DeviceSystem& sys = c->sys;
   float* d_xyz8 = s.d_xyz8;
   float4* d_sites = s.d_sites;
   double* d_acc = s.d_acc;
-  enqueue_decode(c, d_text, text_bytes, d_off, n_frames, s, st);
+  enqueue_decode(c, d_text, text_bytes, d_off, n_frames, s, st, xtc_indexed);
   {
     ScopedKernelTimer t(c, 1, st);
     launch_cdc(sys, d_xyz8, d_sites, d_acc, n_frames, c->sm_count, st);
@@ -1536,6 +1550,7 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
     for (auto& sl : ctx->slot) {
       if (sl.busy || sl.text_out_pending) {
         CUDA_OK(cudaStreamSynchronize(ctx->st_copy));
+        if (ctx->st_index) CUDA_OK(cudaStreamSynchronize(ctx->st_index));
         CUDA_OK(cudaStreamSynchronize(ctx->st_comp));
         CUDA_OK(cudaStreamSynchronize(ctx->st_out));
       }
@@ -1546,6 +1561,9 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
     ctx->host_cov_gather_s = ctx->host_cov_flush_s = 0;
     const int64_t sg = (int64_t)sys.n_sites * sys.num_tot;
     const bool want_rows = dE_kcal != nullptr || sink != nullptr;   // the text path keeps the rows for its host fallback
+    // .xtc: index pass on its own stream (CGC_XTC_OVERLAP=0: both passes of K1x in the batch's turn on the compute stream)
+    bool xtc_overlap = ctx->xtc;
+    if (const char* e = getenv("CGC_XTC_OVERLAP")) xtc_overlap = xtc_overlap && *e && *e != '0';
 
     // The shift c of the Correlate sums is the dE row of the trajectory's frame 0 on EVERY rank (so partial sums of
     // different frame ranges add up).  A run that does not start at frame 0 evaluates frame 0 first, unaccumulated.
@@ -1647,9 +1665,21 @@ int run_impl(cgc_context* ctx, int64_t first_frame, int64_t n_frames, float* dE_
         CUDA_OK(cudaMemcpyAsync(s.d_text, s.src, (size_t)s.nb, cudaMemcpyHostToDevice, ctx->st_copy));
       }
       CUDA_OK(cudaMemcpyAsync(s.d_off, s.h_off, sizeof(int64_t) * want, cudaMemcpyHostToDevice, ctx->st_copy));
-      CUDA_OK(cudaEventRecord(s.ev_copied, ctx->st_copy));
+      if (xtc_overlap) {
+        // K1x's index pass needs only the bytes of the frames: it goes on a high-priority stream of its own, so that it
+        // neither holds up the next batch's copy nor waits for this batch's turn on the compute stream — the pair kernel
+        // of the batch before fills every SM, and the walk (one warp per frame) slips in as that kernel drains and runs
+        // on beside the next one
+        CUDA_OK(cudaEventRecord(s.ev_text, ctx->st_copy));
+        CUDA_OK(cudaStreamWaitEvent(ctx->st_index, s.ev_text, 0));
+        launch_xtc_index(sys, s.d_text, s.nb, s.d_off, want, s.d_xtc, ctx->d_err, ctx->st_index);
+        ctx->launches++;
+        CUDA_OK(cudaEventRecord(s.ev_copied, ctx->st_index));
+      } else {
+        CUDA_OK(cudaEventRecord(s.ev_copied, ctx->st_copy));
+      }
       CUDA_OK(cudaStreamWaitEvent(ctx->st_comp, s.ev_copied, 0));
-      enqueue_compute(ctx, s.d_text, s.nb, s.d_off, want, s, s.d_dE, true, ctx->st_comp);
+      enqueue_compute(ctx, s.d_text, s.nb, s.d_off, want, s, s.d_dE, true, ctx->st_comp, xtc_overlap);
       if (want_rows) {
         CUDA_OK(cudaMemcpyAsync(s.h_dE, s.d_dE, sizeof(float) * (size_t)(sg * want), cudaMemcpyDeviceToHost, ctx->st_comp));
       }

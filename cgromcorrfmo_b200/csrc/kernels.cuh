@@ -46,6 +46,12 @@ void launch_decode(const DeviceSystem& sys, const char* text, int64_t text_bytes
 size_t xtc_scratch_bytes(const DeviceSystem& sys, int n_frames);
 void launch_xtc_decode(const DeviceSystem& sys, const char* text, int64_t text_bytes, const int64_t* coords_off, int n_frames,
                        void* scratch, float* xyz8, float4* sites, int* err_flags, cudaStream_t st);
+// ... and its two passes on their own: the index pass (checkpoints into `scratch`) needs nothing but the frames' bytes, so
+// the streaming loop runs it on a stream of its own as soon as a batch has been copied — beside the previous batch's kernels.
+void launch_xtc_index(const DeviceSystem& sys, const char* text, int64_t text_bytes, const int64_t* coords_off, int n_frames,
+                      void* scratch, int* err_flags, cudaStream_t st);
+void launch_xtc_unpack(const DeviceSystem& sys, const char* text, int64_t text_bytes, const int64_t* coords_off, int n_frames,
+                       const void* scratch, float* xyz8, float4* sites, int* err_flags, cudaStream_t st);
 // xyz8 -> plain float32 [n_frames][n_atoms][3]
 void launch_unblock(const DeviceSystem& sys, const float* xyz8, float* xyz, int n_frames, cudaStream_t st);
 

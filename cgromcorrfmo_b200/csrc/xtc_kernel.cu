@@ -142,8 +142,8 @@ size_t xtc_scratch_bytes(const DeviceSystem& sys, int n_frames) {
   return sizeof(U4) * n_ck * (size_t)n_frames;
 }
 
-void launch_xtc_decode(const DeviceSystem& sys, const char* text, int64_t text_bytes, const int64_t* coords_off, int n_frames,
-                       void* scratch, float* xyz8, float4* sites, int* err_flags, cudaStream_t st) {
+void launch_xtc_index(const DeviceSystem& sys, const char* text, int64_t text_bytes, const int64_t* coords_off, int n_frames,
+                      void* scratch, int* err_flags, cudaStream_t st) {
   if (n_frames <= 0 || sys.n_atoms <= 0) return;
   const int n_ck = (sys.n_atoms + kCkAtoms - 1) / kCkAtoms;
   U4* ck = reinterpret_cast<U4*>(scratch);
@@ -155,6 +155,12 @@ void launch_xtc_decode(const DeviceSystem& sys, const char* text, int64_t text_b
   } else {
     xtc_index_kernel<<<(unsigned)n_frames, 32, 0, st>>>(text, text_bytes, coords_off, sys.n_atoms, n_ck, ck, err_flags);
   }
+}
+
+void launch_xtc_unpack(const DeviceSystem& sys, const char* text, int64_t text_bytes, const int64_t* coords_off, int n_frames,
+                       const void* scratch, float* xyz8, float4* sites, int* err_flags, cudaStream_t st) {
+  if (n_frames <= 0 || sys.n_atoms <= 0) return;
+  const int n_ck = (sys.n_atoms + kCkAtoms - 1) / kCkAtoms;
   // Stream words a 4096-atom window spans on average in this batch, with a twelfth to spare (a window of isolated atoms in
   // a frame that also holds bonded runs is longer than the average): 23 KB hold them for boxes up to ~20 nm at precision
   // 1000 (three CTAs per SM); frames that need more get up to 48 KB (two CTAs per SM); a window that still does not fit
@@ -175,11 +181,17 @@ void launch_xtc_decode(const DeviceSystem& sys, const char* text, int64_t text_b
   DecodeArgs a;
   a.text = text; a.text_bytes = text_bytes; a.coords_off = coords_off;
   a.n_atoms = sys.n_atoms; a.n_pad = sys.n_pad; a.n_ck = n_ck;
-  a.ck = ck; a.slot = sys.slot; a.slot_dq = sys.slot_dq; a.sites_stride = sys.n_sites * sys.site_cap;
+  a.ck = reinterpret_cast<const U4*>(scratch); a.slot = sys.slot; a.slot_dq = sys.slot_dq; a.sites_stride = sys.n_sites * sys.site_cap;
   a.stream_words = stream_words;
   a.xyz8 = xyz8; a.sites = reinterpret_cast<F4*>(sites); a.err_flags = err_flags;
   const dim3 grid((unsigned)((sys.n_atoms + kXtcWindow - 1) / kXtcWindow), (unsigned)n_frames);
   xtc_decode_kernel<<<grid, kXtcThreads, smem, st>>>(a);
+}
+
+void launch_xtc_decode(const DeviceSystem& sys, const char* text, int64_t text_bytes, const int64_t* coords_off, int n_frames,
+                       void* scratch, float* xyz8, float4* sites, int* err_flags, cudaStream_t st) {
+  launch_xtc_index(sys, text, text_bytes, coords_off, n_frames, scratch, err_flags, st);
+  launch_xtc_unpack(sys, text, text_bytes, coords_off, n_frames, scratch, xyz8, sites, err_flags, st);
 }
 
 }  // namespace cgc

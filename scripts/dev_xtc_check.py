@@ -81,8 +81,8 @@ def main():
                         c.run(0, F, out=out)
                     dt = (time.perf_counter() - t0) / reps
                     kt = c.kernel_times(reset=True)
-                    print("index %s batch %3d: %7.0f frames/s e2e | per launch: K1x %.3f ms, K2 %.3f ms (%d launches) | rows == .gro path: %s | errors %d" % (
-                        "scalar" if scalar == "1" else "warp  ", batch, F / dt, kt["decode"][0] / max(1, kt["decode"][1]),
+                    print("overlap %s index %s batch %3d: %7.0f frames/s e2e | per launch: K1x %.3f ms, K2 %.3f ms (%d launches) | rows == .gro path: %s | errors %d" % (
+                        os.environ.get("CGC_XTC_OVERLAP", "1"), "scalar" if scalar == "1" else "warp  ", batch, F / dt, kt["decode"][0] / max(1, kt["decode"][1]),
                         kt["cdc"][0] / max(1, kt["cdc"][1]), kt["decode"][1], same, c.decode_errors()), flush=True)
         os.environ.pop("CGC_XTC_SCALAR_INDEX", None)
 
