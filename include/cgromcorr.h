@@ -111,7 +111,8 @@ int cgc_get_columns(const cgc_context *ctx, int32_t *out);
 int cgc_get_site_charges(const cgc_context *ctx, int site, float *out);
 /* lookup key "<mol>,<atom><ordinal>" of one atom (src/grom2atomFMO.cpp:460) */
 int cgc_get_key(const cgc_context *ctx, int atom, char *buf, int cap);
-/* frame geometry found by cgc_open: bytes per atom line (incl. newline), column of x, field width, decimals */
+/* frame geometry found by cgc_open: bytes per atom line (incl. newline), column of x, field width, decimals.  .trr: line_bytes
+ * is the 12 or 24 bytes of one atom's coordinates; .xtc (frames of varying size): the largest frame's bytes per atom, rounded up. */
 int cgc_get_layout(const cgc_context *ctx, int *line_bytes, int *x_col, int *field_width, int *decimals);
 /* Index the whole trajectory and return the number of complete frames. */
 int cgc_frame_count(cgc_context *ctx, int64_t *n_frames);

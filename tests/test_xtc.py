@@ -561,3 +561,52 @@ def test_python_driver_reads_xtc(small_inputs, tmp_path):
     assert open(out_g + ".time", "rb").read() == open(out_x + ".time", "rb").read()
     with pytest.raises(capi.CgcError):
         run.traj2dEcsv(xtc, top, itp, out_x, frames)                  # no structure file
+
+
+def _random_stream(rng):
+    """A random system: stretches of isolated atoms, bonded chains, small clusters and exact repeats, at a random scale."""
+    n = int(rng.choice([10, 11, 15, 16, 17, 31, 33, 100, 255, 256, 257, 1000, 4095, 4096, 4097, 4111, 4112, 4113, 8192, 8200,
+                        int(rng.integers(10, 9000))]))
+    scale = int(rng.choice([50, 2000, 60000, 3_000_000, 17_000_000, 400_000_000]))
+    pts = np.empty((n, 3), np.int64)
+    k = 0
+    while k < n:
+        kind = int(rng.integers(0, 5))
+        ln = min(n - k, int(rng.integers(1, 40)))
+        base = rng.integers(-scale, scale, 3)
+        if kind == 0:                                                 # isolated atoms
+            pts[k:k + ln] = rng.integers(-scale, scale, (ln, 3))
+        elif kind == 1:                                               # a bonded chain
+            step = int(rng.choice([3, 40, 150, 900, 5000]))
+            pts[k:k + ln] = base + np.cumsum(rng.integers(-step, step + 1, (ln, 3)), axis=0)
+        elif kind == 2:                                               # a cluster around one point
+            r = int(rng.choice([2, 30, 120, 700]))
+            pts[k:k + ln] = base + rng.integers(-r, r + 1, (ln, 3))
+        elif kind == 3:                                               # the same point again and again
+            pts[k:k + ln] = base
+        else:                                                         # triples: one atom and two close companions
+            for j in range(k, k + ln):
+                pts[j] = base + rng.integers(-110, 111, 3) if (j - k) % 3 else rng.integers(-scale, scale, 3)
+                if (j - k) % 3 == 0:
+                    base = pts[j]
+        k += ln
+    pts = np.clip(pts, -(1 << 31) + 1000, (1 << 31) - 1000)
+    prec = float(rng.choice([1000.0, 1000.0, 100.0, 10000.0, 10.0]))
+    return pts, prec
+
+
+def test_emulated_kernels_on_random_streams(emu, oracle_mod, tmp_path):
+    """A hundred and fifty random systems through the library's writer, the oracle's reader and the emulated kernels (both index walks,
+    staged and unstaged stream): the integers that went in come out, bit for bit, every time."""
+    O = oracle_mod
+    rng = np.random.default_rng(20241020)
+    for case in range(150):
+        ints, prec = _random_stream(rng)
+        blob = capi.xtc_encode(ints, step=case, precision=prec)
+        if case % 6 == 0:                                             # the reader in Python is slow: a sample of the cases
+            p = tmp_path / "r.xtc"
+            p.write_bytes(blob)
+            fr = O.read_xtc(str(p))
+            assert len(fr) == 1 and np.array_equal(fr[0]["ints"], ints), case
+        for scalar, words in ((False, 0), (True, 0), (False, 48)):
+            check_against([ints], prec, emu_decode(emu, blob, ints.shape[0], scalar=scalar, max_stream_words=words, seed=case))
