@@ -280,7 +280,6 @@ struct cgc_context {
   bool opened = false;
   int trr_real = 0;               // 0: .gro text; 4 / 8: .trr with single / double precision coordinates
   bool xtc = false;               // GROMACS .xtc (compressed coordinates, frames of varying size)
-  float xtc_precision = 0.f;      // of frame 0
   int64_t frame_span_max = 0;     // .trr / .xtc: largest distance between the coordinate data of consecutive frames
 
   // static per-atom data (host copies kept for the getters)
@@ -992,7 +991,7 @@ void accumulate_rows(cgc_context* c, const float* d_dE, int n_frames, cudaStream
   c->host_cov_flush_s += wall() - t1;
 }
 
-// K1 -> K2 -> finish (-> K3) for one batch whose text is already in d_text; everything on `st`
+// K1 (or K1x) for one batch whose bytes are in d_text.  xtc_indexed: the streaming loop has run K1x's index pass already
 void enqueue_decode(cgc_context* c, const char* d_text, int64_t text_bytes, const int64_t* d_off, int n_frames, const Slot& s,
                     cudaStream_t st, bool xtc_indexed = false) {
   ScopedKernelTimer t(c, 0, st);
@@ -1008,6 +1007,7 @@ void enqueue_decode(cgc_context* c, const char* d_text, int64_t text_bytes, cons
   }
 }
 
+// K1 -> K2 -> finish (-> K3) for one batch whose text is already in d_text; everything on `st`.
 // `s`: the slot whose scratch (coordinates, site blocks, bins, .xtc checkpoints) the batch uses
 void enqueue_compute(cgc_context* c, const char* d_text, int64_t text_bytes, const int64_t* d_off, int n_frames,
                      const Slot& s, float* d_dE, bool accumulate, cudaStream_t st, bool xtc_indexed = false) {
@@ -1068,7 +1068,6 @@ void open_common(cgc_context* c, const char* structure_gro = nullptr, TrajKind k
   c->opened = false;
   c->trr_real = 0;
   c->xtc = false;
-  c->xtc_precision = 0.f;
   c->frame_span_max = 0;
   FrameSpan sp;
   c->L = FrameLayout();
@@ -1088,7 +1087,6 @@ void open_common(cgc_context* c, const char* structure_gro = nullptr, TrajKind k
                                  std::to_string(xf.n_atoms));
       }
       c->xtc = true;
-      c->xtc_precision = xf.precision;
       // the whole index up front (one header per frame): frames differ in size, the staging buffers take the largest
       index_upto(c, INT64_MAX - 1);
       // "bytes per atom" of the largest frame: what the batch sizing works with
