@@ -610,3 +610,55 @@ def test_emulated_kernels_on_random_streams(emu, oracle_mod, tmp_path):
             assert len(fr) == 1 and np.array_equal(fr[0]["ints"], ints), case
         for scalar, words in ((False, 0), (True, 0), (False, 48)):
             check_against([ints], prec, emu_decode(emu, blob, ints.shape[0], scalar=scalar, max_stream_words=words, seed=case))
+
+
+@pytest.mark.parametrize("tag", ["tiny", "permol"])
+def test_gro2xtc_converter(tag, small_inputs, oracle_mod, tmp_path):
+    """python -m cgromcorrfmo_b200.gro2xtc: the .xtc holds exactly the integers the .gro text prints (45- and 69-byte lines),
+    with the frames' time stamps and box; the oracle's reader and the library's front end agree on the result."""
+    from cgromcorrfmo_b200 import gro2xtc
+    O = oracle_mod
+    traj, top, itp, frames = small_inputs(tag)
+    s, _ = _system(tag)
+    xtc = str(tmp_path / "conv.xtc")
+    assert gro2xtc.convert(traj, xtc) == frames
+    fr = O.read_xtc(xtc)
+    assert len(fr) == frames
+    for t, f in enumerate(fr):
+        assert np.array_equal(f["ints"], synth.frame_milli(s, t))
+        assert f["step"] == t and abs(f["time"] - 0.2 * t) < 1e-6 and f["precision"] == 1000.0
+    assert gro2xtc.convert(traj, str(tmp_path / "p100.xtc"), precision=100.0) == frames
+    f100 = O.read_xtc(str(tmp_path / "p100.xtc"))[0]
+    assert np.array_equal(f100["ints"], np.round(synth.frame_milli(s, 0) / 10.0).astype(np.int64))
+    with capi.Context(top, itp, device=-1) as c:
+        c.open_xtc(xtc, traj)
+        assert c.frame_count() == frames
+
+
+def test_reference_fixture_as_xtc(ref_fixture, emu, oracle_mod, tmp_path):
+    """The reference's own test trajectory (src/test/test.gro: a real MD structure of the FMO protein, 6383 atoms, 69-byte
+    lines) converted with gro2xtc: the oracle's .xtc reader and the emulated kernels return, bit for bit, the float32
+    coordinates the reference's reader (ReadOneTimeGrom2Atom, reference src/grom2atomFMO.cpp:448-450) takes from the text.
+    Real bonded structure is what the stream looks like in practice: ~7.6 atoms per group, nine groups in ten flagged."""
+    from cgromcorrfmo_b200 import gro2xtc
+    O = oracle_mod
+    gro, top, itp = ref_fixture
+    xtc = str(tmp_path / "ref.xtc")
+    frames = gro2xtc.convert(gro, xtc)
+    assert frames == 2
+    fr = O.read_xtc(xtc)
+    pos = None
+    want = []
+    for t in range(frames):
+        pos, Xi, keys, groups, _ = O.read_frame(gro, pos)
+        assert np.array_equal(fr[t]["x"].reshape(-1).view(np.uint32), Xi.view(np.uint32))
+        want.append(Xi.reshape(-1, 3))
+    blob = open(xtc, "rb").read()
+    for scalar in (False, True):
+        err, xyz, pads, sites, slot, slot_dq, stats = emu_decode(emu, blob, fr[0]["natoms"], scalar=scalar)
+        assert err == 0 and np.all(pads == 0.0)
+        assert np.array_equal(xyz.view(np.uint32), np.stack(want).view(np.uint32))
+    with capi.Context(top, itp, device=-1) as c:
+        c.open_xtc(xtc, gro)
+        assert c.frame_count() == frames and c.n_atoms == fr[0]["natoms"]
+        assert np.array_equal(c.groups(), groups)
