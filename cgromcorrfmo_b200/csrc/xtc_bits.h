@@ -516,6 +516,11 @@ constexpr uint32_t kRingLook = 704;        // 31 * (96 + 1 + 8 * 72) + 96 + 32 b
 constexpr uint32_t kWide = 4;              // groups per lane in a wide step (below)
 constexpr uint32_t kRingLookWide = 2816;   // the same for 32 * kWide groups; kRingWords >= kRingChunk + kRingLookWide
 constexpr uint32_t kRingPoison = 0xDEADBEEFu;
+static_assert((kRingWords & (kRingWords - 1u)) == 0u, "ring indices are masked");
+static_assert(kRingWords >= kRingChunk + kRingLookWide, "a chunk may only overwrite words the widest step no longer looks at");
+constexpr uint32_t kMaxGroupBits = 96u + 1u + 8u * 72u;   // large triple + flag + eight small triples of the widest kind
+static_assert((31u * kMaxGroupBits + 96u + 32u + 31u) / 32u <= kRingLook, "narrow step: 32 groups of the longest kind");
+static_assert(((32u * kWide - 1u) * kMaxGroupBits + 96u + 32u + 31u) / 32u <= kRingLookWide, "wide step: 128 groups of the longest kind");
 struct Ring {
   uint32_t* w;           // [kRingWords]
   const uint32_t* src;   // the frame's stream in global memory
