@@ -662,3 +662,25 @@ def test_reference_fixture_as_xtc(ref_fixture, emu, oracle_mod, tmp_path):
         c.open_xtc(xtc, gro)
         assert c.frame_count() == frames and c.n_atoms == fr[0]["natoms"]
         assert np.array_equal(c.groups(), groups)
+
+
+def test_index_walk_steps_on_rigid_water(emu):
+    """What the speculative walk is for: in rigid bulk water (TIP3P geometry, random orientations) the writer settles on one
+    table index, every molecule is one clear-flag group of three, and the walk confirms up to 128 groups per step."""
+    rng = np.random.default_rng(4)
+    nw = 4000
+    q = rng.normal(size=(nw, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    a, b, c, d = q.T
+    R = np.stack([np.stack([a*a+b*b-c*c-d*d, 2*(b*c-a*d), 2*(b*d+a*c)], 1), np.stack([2*(b*c+a*d), a*a-b*b+c*c-d*d, 2*(c*d-a*b)], 1),
+                  np.stack([2*(b*d-a*c), 2*(c*d+a*b), a*a-b*b-c*c+d*d], 1)], 1)
+    th = np.deg2rad(104.52) / 2
+    h = np.array([[np.sin(th), np.cos(th), 0.0], [-np.sin(th), np.cos(th), 0.0]]) * 95.72
+    O_ = rng.uniform(0, 6000, (nw, 3))
+    m = np.round(np.stack([O_, O_ + R @ h[0], O_ + R @ h[1]], 1).reshape(-1, 3)).astype(np.int64)
+    blob = capi.xtc_encode(m)
+    st_warp = check_against([m], 1000.0, emu_decode(emu, blob, m.shape[0]))
+    st_scalar = check_against([m], 1000.0, emu_decode(emu, blob, m.shape[0], scalar=True))
+    assert st_scalar[0] <= nw + 50                                    # one group per molecule
+    assert st_warp[0] * 20 < st_scalar[0]                             # and dozens of them per step of the speculative walk
+    assert len(blob) / m.shape[0] < 3.7                               # bytes per atom
